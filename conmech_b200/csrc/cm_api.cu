@@ -1,0 +1,538 @@
+// C-ABI entry points of libconmech_b200 (see include/conmech_b200.h) and the host-side,
+// once-per-model precomputation: node->element incidence, the static solver ordering
+// (reverse Cuthill-McKee on the node graph), envelope statistics and the workspace layout.
+#include "cm_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <queue>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(CM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+struct cm_handle {
+    int device = 0;
+    cm_model_dev m{};
+    cm_model_info info{};
+    cm_ws_layout L{};
+    std::vector<void *> allocs;          // device allocations owned by the handle
+    std::vector<int> order;              // host copy of the ordering
+    // load tables
+    double *d_q = nullptr, *d_pnodal = nullptr;
+    double rot_tol = 0.0;
+    int variant = 1;                     // 1 = FP64 MMA factorisation, 0 = scalar validation variant
+    // counters / timing
+    long long launches = 0;
+    int timing = 0;
+    double stage_ms[3] = {0, 0, 0};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // staging for the host-buffer entry point (grow only)
+    char *stage = nullptr;
+    size_t stage_bytes = 0;
+    char *wsbuf = nullptr;
+    size_t ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+template <typename T>
+static int dev_upload(cm_handle *h, const T *src, size_t n, T **dst) {
+    void *p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(p);
+    if (n && src) CU(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = static_cast<T *>(p);
+    return CM_OK;
+}
+
+// ---- reverse Cuthill-McKee over the node graph (all components), host side
+static std::vector<int> rcm_order(int nV, const std::vector<std::vector<int>> &adj) {
+    std::vector<int> order;
+    order.reserve(nV);
+    std::vector<char> seen(nV, 0);
+    std::vector<int> level(nV);
+    auto bfs_far = [&](int root, std::vector<int> &comp) {
+        // returns a node of the last BFS level with minimum degree, fills comp with the component
+        comp.clear();
+        std::queue<int> q;
+        std::vector<int> touched;
+        level[root] = 0;
+        q.push(root);
+        std::vector<char> mark(nV, 0);
+        mark[root] = 1;
+        int last = 0;
+        while (!q.empty()) {
+            int v = q.front(); q.pop();
+            comp.push_back(v);
+            last = level[v];
+            for (int w : adj[v]) if (!mark[w]) { mark[w] = 1; level[w] = level[v] + 1; q.push(w); }
+        }
+        int best = root;
+        size_t bestdeg = (size_t)-1;
+        for (int v : comp) if (level[v] == last && adj[v].size() < bestdeg) { best = v; bestdeg = adj[v].size(); }
+        return std::make_pair(best, last);
+    };
+    for (int s = 0; s < nV; ++s) {
+        if (seen[s]) continue;
+        std::vector<int> comp;
+        // pseudo-peripheral start
+        int root = s, ecc = -1;
+        for (int it = 0; it < 8; ++it) {
+            auto r = bfs_far(root, comp);
+            if (r.second <= ecc) break;
+            ecc = r.second;
+            root = r.first;
+        }
+        // Cuthill-McKee from root
+        std::vector<int> cm;
+        std::queue<int> q;
+        seen[root] = 1;
+        q.push(root);
+        while (!q.empty()) {
+            int v = q.front(); q.pop();
+            cm.push_back(v);
+            std::vector<int> nb;
+            for (int w : adj[v]) if (!seen[w]) { seen[w] = 1; nb.push_back(w); }
+            std::sort(nb.begin(), nb.end(), [&](int a, int b) {
+                return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b;
+            });
+            for (int w : nb) q.push(w);
+        }
+        order.insert(order.end(), cm.rbegin(), cm.rend());
+    }
+    return order;
+}
+
+// envelope statistics of the full structure for an ordering: half bandwidth, sum h^2, n_free
+static void envelope_stats(int nV, int nE, const int32_t *conn, const std::vector<int> &nfree,
+                           const std::vector<int> &order, int *n_free, int *halfbw, long long *flops) {
+    std::vector<int> base(nV, 0);
+    int run = 0;
+    for (int p = 0; p < nV; ++p) { base[order[p]] = run; run += nfree[order[p]]; }
+    *n_free = run;
+    std::vector<int> first(nV);
+    for (int v = 0; v < nV; ++v) first[v] = base[v];
+    for (int e = 0; e < nE; ++e) {
+        int u = conn[2 * e], v = conn[2 * e + 1];
+        if (nfree[u] == 0 || nfree[v] == 0) continue;
+        first[u] = std::min(first[u], base[v]);
+        first[v] = std::min(first[v], base[u]);
+    }
+    int bw = 0;
+    long long fl = 0;
+    for (int v = 0; v < nV; ++v)
+        for (int i = 0; i < nfree[v]; ++i) {
+            int r = base[v] + i;
+            int hgt = r - first[v];
+            bw = std::max(bw, hgt);
+            fl += (long long)hgt * hgt;
+        }
+    *halfbw = bw;
+    *flops = fl;
+}
+
+extern "C" {
+
+const char *cm_last_error(void) { return g_err.c_str(); }
+const char *cm_version(void) { return "conmech_b200 0.1.0 (sm_100a)"; }
+
+int cm_create(const cm_model_desc *d, cm_handle **out) {
+    if (!d || !out) return fail(CM_ERR_INVALID, "cm_create: null argument");
+    if (d->n_nodes <= 0 || d->n_elems <= 0) return fail(CM_ERR_INVALID, "cm_create: empty model");
+    if (d->n_supports <= 0)
+        return fail(CM_ERR_INVALID, "there needs to be at least one support (fixed) vertex in the model!");
+    const int nV = d->n_nodes, nE = d->n_elems, nS = d->n_supports;
+    for (int e = 0; e < nE; ++e) {
+        int u = d->conn[2 * e], v = d->conn[2 * e + 1];
+        if (u < 0 || u >= nV || v < 0 || v >= nV || u == v)
+            return fail(CM_ERR_INVALID, "cm_create: element " + std::to_string(e) + " has invalid end nodes");
+        double dx = d->xyz[3 * u] - d->xyz[3 * v], dy = d->xyz[3 * u + 1] - d->xyz[3 * v + 1],
+               dz = d->xyz[3 * u + 2] - d->xyz[3 * v + 2];
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) < CM_EPS)      // numpy_stiffness_assembly.py:288-289
+            return fail(CM_ERR_INVALID, "E#" + std::to_string(e) + " - Bar length too small!");
+        if (!(std::fabs(d->props[7 * e + 4]) > CM_EPS) || !(std::fabs(d->props[7 * e + 3]) > CM_EPS))
+            return fail(CM_ERR_INVALID, "E#" + std::to_string(e) + " - E and Iz must be non-zero");   // :146
+    }
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (d->device < 0 || d->device >= ndev) return fail(CM_ERR_INVALID, "cm_create: no such CUDA device");
+    CU(cudaSetDevice(d->device));
+
+    cm_handle *h = new cm_handle();
+    h->device = d->device;
+    cm_model_dev &m = h->m;
+    m.nV = nV; m.nE = nE; m.nS = nS; m.n_lc = 0;
+    m.mask_words = (nE + 31) / 32;
+    m.trans_tol = 1e-3;
+    h->rot_tol = 3.14159265358979323846 / 180 * 3;
+
+    // incidence (ascending element ids per node) and node adjacency
+    std::vector<int> ne_ptr(nV + 1, 0);
+    for (int e = 0; e < nE; ++e) { ne_ptr[d->conn[2 * e] + 1]++; ne_ptr[d->conn[2 * e + 1] + 1]++; }
+    for (int v = 0; v < nV; ++v) ne_ptr[v + 1] += ne_ptr[v];
+    std::vector<int> ne_elem(2 * (size_t)nE), fill(ne_ptr.begin(), ne_ptr.end() - 1);
+    std::vector<unsigned char> ne_end(2 * (size_t)nE);
+    for (int e = 0; e < nE; ++e)
+        for (int k = 0; k < 2; ++k) {
+            int v = d->conn[2 * e + k];
+            ne_elem[fill[v]] = e;
+            ne_end[fill[v]] = (unsigned char)k;
+            fill[v]++;
+        }
+    std::vector<std::vector<int>> adj(nV);
+    for (int e = 0; e < nE; ++e) {
+        adj[d->conn[2 * e]].push_back(d->conn[2 * e + 1]);
+        adj[d->conn[2 * e + 1]].push_back(d->conn[2 * e]);
+    }
+    for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+
+    std::vector<int> node_sup(nV, -1), nfree(nV, 6);
+    for (int s = 0; s < nS; ++s) {
+        int v = d->sup_node[s];
+        if (v < 0 || v >= nV) { delete h; return fail(CM_ERR_INVALID, "cm_create: support node out of range"); }
+        if (node_sup[v] >= 0) { delete h; return fail(CM_ERR_INVALID, "cm_create: duplicate support node"); }
+        node_sup[v] = s;
+        int nf = 6;
+        for (int i = 0; i < 6; ++i) nf -= d->sup_cond[6 * s + i] ? 1 : 0;
+        nfree[v] = nf;
+    }
+
+    // static ordering: best of natural and RCM by profile flops of the full structure
+    std::vector<int> nat(nV);
+    std::iota(nat.begin(), nat.end(), 0);
+    std::vector<int> rcm = rcm_order(nV, adj);
+    int nf0, bw0, nf1, bw1;
+    long long fl0, fl1;
+    envelope_stats(nV, nE, d->conn, nfree, nat, &nf0, &bw0, &fl0);
+    envelope_stats(nV, nE, d->conn, nfree, rcm, &nf1, &bw1, &fl1);
+    const bool use_rcm = fl1 < fl0;
+    h->order = use_rcm ? rcm : nat;
+    const int n_free_full = nf0, halfbw = use_rcm ? bw1 : bw0;
+    std::vector<int> pos(nV);
+    for (int p = 0; p < nV; ++p) pos[h->order[p]] = p;
+
+    m.n_tile_rows_max = std::max(1, (n_free_full + CM_TILE - 1) / CM_TILE);
+    m.band_tiles = (halfbw + CM_TILE - 1) / CM_TILE + 1;
+    if (m.band_tiles > m.n_tile_rows_max) m.band_tiles = m.n_tile_rows_max;
+
+    cm_model_info &I = h->info;
+    I.n_nodes = nV; I.n_elems = nE; I.n_supports = nS; I.n_loadcases = 0;
+    I.mask_words = m.mask_words;
+    I.n_free_full = n_free_full;
+    I.half_bandwidth = halfbw;
+    I.tile = CM_TILE;
+    I.n_tile_rows_max = m.n_tile_rows_max;
+    I.band_tiles = m.band_tiles;
+    I.profile_flops_full = use_rcm ? fl1 : fl0;
+
+    int rc;
+    double *xyz, *props, *cr; int *conn, *d_ne_ptr, *d_ne_elem, *d_sup_node, *d_node_sup, *d_order, *d_pos;
+    unsigned char *d_ne_end, *d_sup_cond;
+#define UP(expr) do { rc = (expr); if (rc != CM_OK) { cm_destroy(h); return rc; } } while (0)
+    UP(dev_upload(h, d->xyz, (size_t)3 * nV, &xyz));
+    UP(dev_upload(h, d->conn, (size_t)2 * nE, &conn));
+    UP(dev_upload(h, d->props, (size_t)7 * nE, &props));
+    UP(dev_upload(h, d->cr, (size_t)6 * nE, &cr));
+    UP(dev_upload(h, ne_ptr.data(), ne_ptr.size(), &d_ne_ptr));
+    UP(dev_upload(h, ne_elem.data(), ne_elem.size(), &d_ne_elem));
+    UP(dev_upload(h, ne_end.data(), ne_end.size(), &d_ne_end));
+    UP(dev_upload(h, d->sup_node, (size_t)nS, &d_sup_node));
+    UP(dev_upload(h, d->sup_cond, (size_t)6 * nS, &d_sup_cond));
+    UP(dev_upload(h, node_sup.data(), (size_t)nV, &d_node_sup));
+    UP(dev_upload(h, h->order.data(), (size_t)nV, &d_order));
+    UP(dev_upload(h, pos.data(), (size_t)nV, &d_pos));
+    UP(dev_upload<double>(h, nullptr, (size_t)144 * nE, &m.Kg));
+    UP(dev_upload<double>(h, nullptr, (size_t)9 * nE, &m.R3));
+    UP(dev_upload<double>(h, nullptr, (size_t)nE, &m.elen));
+#undef UP
+    m.xyz = xyz; m.conn = conn; m.props = props; m.cr = cr;
+    m.ne_ptr = d_ne_ptr; m.ne_elem = d_ne_elem; m.ne_end = d_ne_end;
+    m.sup_node = d_sup_node; m.sup_cond = d_sup_cond; m.node_sup = d_node_sup;
+    m.order = d_order; m.pos = d_pos;
+    m.q = nullptr; m.pnodal = nullptr;
+
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    if (ce == cudaSuccess) ce = cm_launch_element_tables(m, h->stream);
+    h->launches++;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    if (ce != cudaSuccess) {
+        std::string msg = std::string("cm_create: ") + cudaGetErrorString(ce);
+        cm_destroy(h);
+        return fail(CM_ERR_CUDA, msg);
+    }
+    *out = h;
+    return CM_OK;
+}
+
+int cm_destroy(cm_handle *h) {
+    if (!h) return CM_OK;
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->d_q) cudaFree(h->d_q);
+    if (h->d_pnodal) cudaFree(h->d_pnodal);
+    if (h->stage) cudaFree(h->stage);
+    if (h->wsbuf) cudaFree(h->wsbuf);
+    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CM_OK;
+}
+
+int cm_get_info(const cm_handle *h, cm_model_info *info) {
+    if (!h || !info) return fail(CM_ERR_INVALID, "cm_get_info: null argument");
+    *info = h->info;
+    return CM_OK;
+}
+
+int cm_get_element_tables(cm_handle *h, double *Kg, double *R3, int32_t *id_map) {
+    if (!h) return fail(CM_ERR_INVALID, "cm_get_element_tables: null handle");
+    CU(cudaSetDevice(h->device));
+    const int nE = h->m.nE;
+    if (Kg) CU(cudaMemcpy(Kg, h->m.Kg, (size_t)144 * nE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (R3) CU(cudaMemcpy(R3, h->m.R3, (size_t)9 * nE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (id_map) {
+        std::vector<int> conn(2 * (size_t)nE);
+        CU(cudaMemcpy(conn.data(), h->m.conn, conn.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int e = 0; e < nE; ++e)                          // numpy_stiffness.py:567-570
+            for (int k = 0; k < 2; ++k)
+                for (int i = 0; i < 6; ++i) id_map[12 * (size_t)e + 6 * k + i] = 6 * conn[2 * e + k] + i;
+    }
+    return CM_OK;
+}
+
+int cm_get_node_order(const cm_handle *h, int32_t *order) {
+    if (!h || !order) return fail(CM_ERR_INVALID, "cm_get_node_order: null argument");
+    std::copy(h->order.begin(), h->order.end(), order);
+    return CM_OK;
+}
+
+static void make_layout(cm_handle *h) {
+    const cm_model_dev &m = h->m;
+    cm_ws_layout &L = h->L;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const int n_lc = std::max(1, m.n_lc);
+    L.n_pad = m.n_tile_rows_max * CM_TILE;
+    size_t o = 0;
+    L.off_tiles = o;  o = al(o + (size_t)m.n_tile_rows_max * m.band_tiles * CM_TILE_ELEMS * sizeof(double));
+    L.off_sidx = o;   o = al(o + (size_t)6 * m.nV * sizeof(int));
+    L.off_dinv = o;   o = al(o + (size_t)L.n_pad * sizeof(double));
+    L.off_dpiv = o;   o = al(o + (size_t)(L.n_pad + 8) * sizeof(double));
+    L.off_x = o;      o = al(o + (size_t)n_lc * L.n_pad * sizeof(double));
+    L.off_p = o;      o = al(o + (size_t)n_lc * 6 * m.nV * sizeof(double));
+    L.off_kfirst = o; o = al(o + (size_t)m.n_tile_rows_max * sizeof(int));
+    L.off_info = o;   o = al(o + CM_INFO_INTS * sizeof(int));
+    L.per_subset = o;
+}
+
+int cm_set_loadcases(cm_handle *h, int32_t n_lc, const double *nodal, const double *w_udl,
+                     const uint8_t *has_udl, const uint8_t *grav_on, const double *grav_dir) {
+    if (!h) return fail(CM_ERR_INVALID, "cm_set_loadcases: null handle");
+    if (n_lc < 1 || n_lc > CM_MAX_LC) return fail(CM_ERR_INVALID, "cm_set_loadcases: 1..8 load cases supported");
+    if (!nodal || !grav_on || !grav_dir) return fail(CM_ERR_INVALID, "cm_set_loadcases: null argument");
+    if (has_udl && !w_udl) return fail(CM_ERR_INVALID, "cm_set_loadcases: has_udl without w_udl");
+    CU(cudaSetDevice(h->device));
+    cm_model_dev &m = h->m;
+    const size_t nE = m.nE, nV = m.nV;
+    if (h->d_q) { cudaFree(h->d_q); h->d_q = nullptr; }
+    if (h->d_pnodal) { cudaFree(h->d_pnodal); h->d_pnodal = nullptr; }
+    CU(cudaMalloc((void **)&h->d_q, n_lc * nE * 12 * sizeof(double)));
+    CU(cudaMalloc((void **)&h->d_pnodal, n_lc * 6 * nV * sizeof(double)));
+    CU(cudaMemcpy(h->d_pnodal, nodal, n_lc * 6 * nV * sizeof(double), cudaMemcpyHostToDevice));
+    double *d_w = nullptr, *d_g = nullptr;
+    unsigned char *d_has = nullptr, *d_on = nullptr;
+    int rc = CM_OK;
+    cudaError_t ce = cudaSuccess;
+    if (has_udl) {
+        ce = cudaMalloc((void **)&d_w, n_lc * nE * 3 * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_has, n_lc * nE);
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_w, w_udl, n_lc * nE * 3 * sizeof(double), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_has, has_udl, n_lc * nE, cudaMemcpyHostToDevice);
+    }
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_g, n_lc * 3 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_on, n_lc);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_g, grav_dir, n_lc * 3 * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_on, grav_on, n_lc, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cm_launch_element_loads(m, n_lc, d_w, d_has, d_on, d_g, h->d_q, h->stream);
+    h->launches++;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    if (ce != cudaSuccess) rc = fail(CM_ERR_CUDA, std::string("cm_set_loadcases: ") + cudaGetErrorString(ce));
+    cudaFree(d_w); cudaFree(d_has); cudaFree(d_g); cudaFree(d_on);
+    if (rc != CM_OK) return rc;
+    m.n_lc = n_lc;
+    m.q = h->d_q;
+    m.pnodal = h->d_pnodal;
+    h->info.n_loadcases = n_lc;
+    make_layout(h);
+    return CM_OK;
+}
+
+int cm_get_element_loads(cm_handle *h, int32_t lc, double *q) {
+    if (!h || !q) return fail(CM_ERR_INVALID, "cm_get_element_loads: null argument");
+    if (lc < 0 || lc >= h->m.n_lc) return fail(CM_ERR_STATE, "cm_get_element_loads: load case not set");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(q, h->d_q + (size_t)lc * h->m.nE * 12, (size_t)h->m.nE * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+
+int cm_set_tol(cm_handle *h, double trans_tol, double rot_tol) {
+    if (!h) return fail(CM_ERR_INVALID, "cm_set_tol: null handle");
+    h->m.trans_tol = trans_tol;
+    h->rot_tol = rot_tol;
+    return CM_OK;
+}
+
+size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
+    if (!h || h->m.n_lc == 0 || n <= 0) return 0;
+    return (size_t)n * h->L.per_subset;
+}
+
+int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 1 FP64 MMA (default)
+    if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
+    h->variant = variant;
+    return CM_OK;
+}
+
+int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *o, uint64_t ws_dev,
+                  size_t ws_bytes, uint64_t stream) {
+    if (!h || !o) return fail(CM_ERR_INVALID, "cm_solve_many: null argument");
+    if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many: call cm_set_loadcases first");
+    if (B <= 0) return CM_OK;
+    if (!masks_dev || !ws_dev) return fail(CM_ERR_INVALID, "cm_solve_many: null device buffer");
+    const size_t per = h->L.per_subset;
+    long long wave = (long long)(ws_bytes / per);
+    if (wave < 1) return fail(CM_ERR_NOMEM, "cm_solve_many: workspace smaller than one subset (" + std::to_string(per) + " bytes)");
+    if (wave > B) wave = B;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cm_out_dev od;
+    od.flag = reinterpret_cast<unsigned char *>(o->flag);
+    od.status = reinterpret_cast<unsigned char *>(o->status);
+    od.n_free = reinterpret_cast<int *>(o->n_free);
+    od.n_fixed = reinterpret_cast<int *>(o->n_fixed);
+    od.dof_map = reinterpret_cast<int *>(o->dof_map);
+    od.node_exists = reinterpret_cast<unsigned char *>(o->node_exists);
+    od.U = reinterpret_cast<double *>(o->U);
+    od.Rf = reinterpret_cast<double *>(o->Rf);
+    od.eR = reinterpret_cast<double *>(o->eR);
+    od.compliance = reinterpret_cast<double *>(o->compliance);
+    od.max_trans = reinterpret_cast<double *>(o->max_trans);
+    od.max_rot = reinterpret_cast<double *>(o->max_rot);
+    od.min_pivot = reinterpret_cast<double *>(o->min_pivot);
+    char *ws = reinterpret_cast<char *>(ws_dev);
+    const uint32_t *masks = reinterpret_cast<const uint32_t *>(masks_dev);
+    double acc_ms[3] = {0, 0, 0};
+    for (long long first = 0; first < B; first += wave) {
+        const int count = (int)std::min<long long>(wave, B - first);
+        if (h->timing) CU(cudaEventRecord(h->ev[0], st));
+        CU(cm_launch_dofmap_assemble(h->m, h->L, ws, masks, first, count, od, st));
+        if (h->timing) CU(cudaEventRecord(h->ev[1], st));
+        CU(cm_launch_factor(h->m, h->L, ws, count, h->variant, st));
+        if (h->timing) CU(cudaEventRecord(h->ev[2], st));
+        CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
+        h->launches += 3;
+        if (h->timing) {
+            CU(cudaEventRecord(h->ev[3], st));
+            CU(cudaEventSynchronize(h->ev[3]));
+            for (int i = 0; i < 3; ++i) {
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+                acc_ms[i] += ms;
+            }
+        }
+    }
+    if (h->timing) for (int i = 0; i < 3; ++i) h->stage_ms[i] = acc_ms[i];
+    return CM_OK;
+}
+
+int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, const cm_solve_out_host *o) {
+    if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host: null argument");
+    if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many_host: call cm_set_loadcases first");
+    if (B <= 0) return CM_OK;
+    CU(cudaSetDevice(h->device));
+    const cm_model_dev &m = h->m;
+    const size_t nV = m.nV, nE = m.nE, Lc = m.n_lc, Bn = (size_t)B;
+    // device staging: masks + every requested output
+    struct Item { size_t bytes; size_t off; void *host; };
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto item = [&](void *host, size_t bytes) { Item it{host ? bytes : 0, off, host}; if (host) off = al(off + bytes); return it; };
+    Item i_mask = item((void *)masks_host, Bn * m.mask_words * 4);
+    Item i_flag = item(o->flag, Bn * Lc), i_status = item(o->status, Bn * Lc);
+    Item i_nfree = item(o->n_free, Bn * 4), i_nfixed = item(o->n_fixed, Bn * 4);
+    Item i_dof = item(o->dof_map, Bn * 6 * nV * 4), i_ex = item(o->node_exists, Bn * nV);
+    Item i_U = item(o->U, Bn * Lc * 6 * nV * 8), i_R = item(o->Rf, Bn * Lc * 6 * nV * 8);
+    Item i_E = item(o->eR, Bn * Lc * nE * 12 * 8);
+    Item i_c = item(o->compliance, Bn * Lc * 8), i_mt = item(o->max_trans, Bn * Lc * 8);
+    Item i_mr = item(o->max_rot, Bn * Lc * 8), i_mp = item(o->min_pivot, Bn * 8);
+    if (off > h->stage_bytes) {
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr; h->stage_bytes = 0;
+        CU(cudaMalloc((void **)&h->stage, off));
+        h->stage_bytes = off;
+    }
+    // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
+    size_t freeb = 0, totalb = 0;
+    CU(cudaMemGetInfo(&freeb, &totalb));
+    const size_t per = h->L.per_subset;
+    size_t want = std::min<size_t>(Bn, 4096) * per;
+    size_t cap = (freeb + h->ws_bytes) / 2;
+    if (want > cap) want = std::max(per, cap / per * per);
+    if (want > h->ws_bytes) {
+        if (h->wsbuf) cudaFree(h->wsbuf);
+        h->wsbuf = nullptr; h->ws_bytes = 0;
+        CU(cudaMalloc((void **)&h->wsbuf, want));
+        h->ws_bytes = want;
+    }
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(h->stage + i_mask.off, masks_host, i_mask.bytes, cudaMemcpyHostToDevice, st));
+    cm_solve_out od;
+    auto dp = [&](const Item &it) { return it.host ? (uint64_t)(h->stage + it.off) : (uint64_t)0; };
+    od.flag = dp(i_flag); od.status = dp(i_status); od.n_free = dp(i_nfree); od.n_fixed = dp(i_nfixed);
+    od.dof_map = dp(i_dof); od.node_exists = dp(i_ex); od.U = dp(i_U); od.Rf = dp(i_R); od.eR = dp(i_E);
+    od.compliance = dp(i_c); od.max_trans = dp(i_mt); od.max_rot = dp(i_mr); od.min_pivot = dp(i_mp);
+    int rc = cm_solve_many(h, (uint64_t)(h->stage + i_mask.off), B, &od, (uint64_t)h->wsbuf, h->ws_bytes, (uint64_t)st);
+    if (rc != CM_OK) return rc;
+    const Item *outs[] = {&i_flag, &i_status, &i_nfree, &i_nfixed, &i_dof, &i_ex, &i_U, &i_R, &i_E, &i_c, &i_mt, &i_mr, &i_mp};
+    for (const Item *it : outs)
+        if (it->host) CU(cudaMemcpyAsync(it->host, h->stage + it->off, it->bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CM_OK;
+}
+
+int64_t cm_kernel_launches(const cm_handle *h) { return h ? h->launches : 0; }
+int cm_reset_counters(cm_handle *h) {
+    if (!h) return fail(CM_ERR_INVALID, "cm_reset_counters: null handle");
+    h->launches = 0;
+    h->stage_ms[0] = h->stage_ms[1] = h->stage_ms[2] = 0;
+    return CM_OK;
+}
+int cm_enable_timing(cm_handle *h, int32_t on) {
+    if (!h) return fail(CM_ERR_INVALID, "cm_enable_timing: null handle");
+    h->timing = on;
+    return CM_OK;
+}
+int cm_last_stage_ms(const cm_handle *h, double *ms) {
+    if (!h || !ms) return fail(CM_ERR_INVALID, "cm_last_stage_ms: null argument");
+    for (int i = 0; i < 3; ++i) ms[i] = h->stage_ms[i];
+    return CM_OK;
+}
+
+int cm_element_kernel_dev(uint64_t xyz_u, uint64_t xyz_v, uint64_t props, uint64_t cr, int64_t n, uint64_t Kg,
+                          uint64_t R3, uint64_t stream) {
+    if (n <= 0) return CM_OK;
+    if (!xyz_u || !xyz_v || !props || !cr || !Kg || !R3) return fail(CM_ERR_INVALID, "cm_element_kernel_dev: null buffer");
+    CU(cm_launch_element_generic((const double *)xyz_u, (const double *)xyz_v, (const double *)props,
+                                 (const double *)cr, n, (double *)Kg, (double *)R3, (cudaStream_t)stream));
+    return CM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Shared declarations of the conmech_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <vector>
+#include <string>
+#include "../../include/conmech_b200.h"
+
+#define CM_TILE 32                 // tile edge of the block-band storage
+#define CM_TILE_ELEMS 1024         // doubles per tile (8 KB)
+#define CM_EPS 1e-14               // reference DOUBLE_EPS (numpy_stiffness_assembly.py:8)
+#define CM_BIG 1e14                // reference DOUBLE_INF (numpy_stiffness_assembly.py:9)
+#define CM_MAX_LC 8                // load cases solved together per subset
+#define CM_INFO_INTS 16            // per-subset info record (ints)
+
+// info record slots
+#define CM_INFO_NS 0               // free DOFs of the subset (solver matrix order)
+#define CM_INFO_NT 1               // tile rows
+#define CM_INFO_STATUS 2           // CM_ST_OK / NO_SUPPORT / NO_FIXED_DOF / SINGULAR
+#define CM_INFO_NFIXED 3
+#define CM_INFO_ZERO_LOAD 4        // bit lc set: ||P_lc|| <= eps
+#define CM_INFO_JACOBI 5           // 1: Jacobi scaling applied, 0: identity (a |k_ii| <= eps)
+
+// Element (r,k) of a 32x32 tile.  Rows are contiguous (k fastest) and the eight 4-double groups
+// of a row are XOR-swizzled with the row index, so that the warp-wide 8-rows x 4-doubles
+// fragment reads of the FP64 MMA are bank-conflict free once a tile sits in shared memory.
+__host__ __device__ __forceinline__ int cm_tile_off(int r, int k) {
+    return (r << 5) + ((((k >> 2) ^ (r & 7))) << 2) + (k & 3);
+}
+
+// Model tables on the device (all sizes fixed at cm_create).
+struct cm_model_dev {
+    int nV, nE, nS, n_lc;
+    int mask_words;
+    int n_tile_rows_max;   // tile rows of the full structure
+    int band_tiles;        // tiles stored per tile row: columns I-band_tiles+1 .. I
+    const double *xyz;     // [nV*3]
+    const int *conn;       // [nE*2]
+    const double *props;   // [nE*7] A,Jx,Iy,Iz,E,mu,rho
+    const double *cr;      // [nE*6]
+    double *Kg;            // [nE*144] row major global element stiffness
+    double *R3;            // [nE*9]
+    double *elen;          // [nE]
+    const int *ne_ptr;     // [nV+1] node -> incident elements (ascending ids)
+    const int *ne_elem;    // [2nE]
+    const unsigned char *ne_end;   // [2nE] which end of that element the node is
+    const int *sup_node;   // [nS]
+    const unsigned char *sup_cond; // [nS*6]
+    const int *node_sup;   // [nV] support index or -1
+    const int *order;      // [nV] solver position -> node
+    const int *pos;        // [nV] node -> solver position
+    const double *q;       // [n_lc*nE*12] lumped element loads
+    const double *pnodal;  // [n_lc*6nV]
+    double trans_tol;
+};
+
+// Per-subset workspace layout: byte offsets inside one subset's slab.
+struct cm_ws_layout {
+    size_t per_subset;
+    size_t off_tiles;      // double [n_tile_rows_max*band_tiles*1024]
+    size_t off_sidx;       // int    [6nV]  DOF -> solver row (-1: not free)
+    size_t off_dinv;       // double [n_pad] Jacobi scale per solver row
+    size_t off_dpiv;       // double [n_pad] LDL^T pivots
+    size_t off_x;          // double [n_lc*n_pad] rhs -> forward solution -> solution
+    size_t off_p;          // double [n_lc*6nV] full load vector, DOF order
+    size_t off_kfirst;     // int    [n_tile_rows_max] first tile column in the envelope
+    size_t off_info;       // int    [CM_INFO_INTS]
+    int n_pad;             // n_tile_rows_max*32
+};
+
+// Output pointers as typed device pointers (0 = not wanted).
+struct cm_out_dev {
+    unsigned char *flag, *status;
+    int *n_free, *n_fixed, *dof_map;
+    unsigned char *node_exists;
+    double *U, *Rf, *eR, *compliance, *max_trans, *max_rot, *min_pivot;
+};
+
+// kernel launchers (one per stage); all enqueue on `st` and return the launch error
+cudaError_t cm_launch_element_tables(const cm_model_dev &m, cudaStream_t st);
+cudaError_t cm_launch_element_loads(const cm_model_dev &m, int n_lc, const double *w_udl,
+                                    const unsigned char *has_udl, const unsigned char *grav_on,
+                                    const double *grav_dir, double *q, cudaStream_t st);
+cudaError_t cm_launch_element_generic(const double *xyz_u, const double *xyz_v, const double *props,
+                                      const double *cr, long long n, double *Kg, double *R3,
+                                      cudaStream_t st);
+cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
+                                      const uint32_t *masks, long long first, int count,
+                                      const cm_out_dev &out, cudaStream_t st);
+cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+                             int variant, cudaStream_t st);
+cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
+                                    const uint32_t *masks, long long first, int count,
+                                    const cm_out_dev &out, cudaStream_t st);

@@ -1,0 +1,356 @@
+// K2 - per subset: DOF status / permutation (bit-exact integers), compacted solver numbering in
+// the static node ordering, and the deterministic assembly of the Jacobi-scaled K_mm and the
+// right-hand sides into block-band tile storage.
+//
+// Reference: numpy_stiffness.py:147-219 (compute_dof_permutation), numpy_stiffness_assembly.py:
+// 347-389 (assemble_global_stiffness_matrix, entries |k| <= 1e-14 dropped),
+// numpy_stiffness.py:244-257 (K_mm slice, load vector), :283-291 (Jacobi scaling).
+//
+// Assembly is a GATHER: every matrix entry is owned by one thread, which sums the contributing
+// element entries in ascending element id.  No atomics touch floating-point data, so results
+// are run-to-run deterministic.  One CTA per subset.
+#include "cm_common.cuh"
+
+namespace {
+
+constexpr int K2_THREADS = 256;
+
+__device__ __forceinline__ double thr(double k) { return (fabs(k) > CM_EPS) ? k : 0.0; }
+
+// exclusive scan of n ints in shared memory, in place; returns the total (all threads).
+// scratch: K2_THREADS+1 ints.
+__device__ int block_excl_scan(int *data, int n, int *scratch) {
+    const int t = threadIdx.x, T = blockDim.x;
+    const int chunk = (n + T - 1) / T;
+    const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += data[i];
+    scratch[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int run = 0;
+        for (int i = 0; i < T; ++i) { int v = scratch[i]; scratch[i] = run; run += v; }
+        scratch[T] = run;
+    }
+    __syncthreads();
+    int run = scratch[t];
+    for (int i = lo; i < hi; ++i) { int v = data[i]; data[i] = run; run += v; }
+    int total = scratch[T];
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (mask[e >> 5] >> (e & 31)) & 1u; }
+
+// solver row of local DOF i of node v (-1 if fixed); base = first solver row of the node
+__device__ __forceinline__ int node_row(const cm_model_dev &m, int v, int i, int base) {
+    int s = m.node_sup[v];
+    if (s < 0) return base + i;
+    const unsigned char *c = m.sup_cond + 6 * s;
+    if (c[i]) return -1;
+    int r = base;
+    for (int j = 0; j < i; ++j) r += c[j] ? 0 : 1;
+    return r;
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
+                   cm_out_dev out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // shared layout
+    int *s_base = reinterpret_cast<int *>(smem_raw);             // [nV] first solver row of node
+    int *s_tmp = s_base + m.nV;                                    // [nV] scan input / scratch
+    int *s_kfirst = s_tmp + m.nV;                                  // [n_tile_rows_max]
+    int *s_scan = s_kfirst + m.n_tile_rows_max;                    // [K2_THREADS+1]
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_scan + K2_THREADS + 1);   // [mask_words]
+    unsigned char *s_free = reinterpret_cast<unsigned char *>(s_mask + m.mask_words);   // [nV] free DOFs (0 if absent)
+    unsigned char *s_exist = s_free + m.nV;                        // [nV]
+    __shared__ int s_red[8];
+    __shared__ double s_dred[K2_THREADS / 32];
+
+    const int t = threadIdx.x, T = blockDim.x;
+    const int sb = blockIdx.x;
+    const long long gs = first + sb;
+    char *slab = ws + (size_t)sb * L.per_subset;
+    double *tiles = reinterpret_cast<double *>(slab + L.off_tiles);
+    int *sidx = reinterpret_cast<int *>(slab + L.off_sidx);
+    double *dinv = reinterpret_cast<double *>(slab + L.off_dinv);
+    double *X = reinterpret_cast<double *>(slab + L.off_x);
+    double *P = reinterpret_cast<double *>(slab + L.off_p);
+    int *kfirst_g = reinterpret_cast<int *>(slab + L.off_kfirst);
+    int *info = reinterpret_cast<int *>(slab + L.off_info);
+    const uint32_t *gmask = masks + (size_t)gs * m.mask_words;
+    const int nV = m.nV;
+
+    for (int w = t; w < m.mask_words; w += T) s_mask[w] = gmask[w];
+    if (t < 8) s_red[t] = 0;
+    __syncthreads();
+
+    // ---- node existence, support status (numpy_stiffness.py:156-184)
+    int my_fixed = 0, my_exist = 0, my_sup = 0;
+    for (int v = t; v < nV; v += T) {
+        bool ex = false;
+        for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) ex |= elem_on(s_mask, m.ne_elem[p]);
+        int nfix = 0;
+        int s = m.node_sup[v];
+        if (ex && s >= 0) {
+            for (int i = 0; i < 6; ++i) nfix += m.sup_cond[6 * s + i] ? 1 : 0;
+            my_sup = 1;
+        }
+        s_exist[v] = ex ? 1 : 0;
+        s_free[v] = ex ? (unsigned char)(6 - nfix) : 0;
+        my_fixed += nfix;
+        my_exist += ex ? 1 : 0;
+    }
+    atomicAdd(&s_red[0], my_fixed);
+    atomicAdd(&s_red[1], my_exist);
+    atomicOr(&s_red[2], my_sup);
+    __syncthreads();
+    const int n_fixed = s_red[0], n_exist = s_red[1];
+    const int status = (s_red[2] == 0) ? CM_ST_NO_SUPPORT : (n_fixed == 0 ? CM_ST_NO_FIXED_DOF : CM_ST_OK);
+    const int n_free = 6 * n_exist - n_fixed;
+
+    if (out.node_exists)
+        for (int v = t; v < nV; v += T) out.node_exists[(size_t)gs * nV + v] = s_exist[v];
+    if (t == 0) {
+        if (out.n_free) out.n_free[gs] = status == CM_ST_OK ? n_free : 0;
+        if (out.n_fixed) out.n_fixed[gs] = status == CM_ST_OK ? n_fixed : 0;
+        info[CM_INFO_STATUS] = status;
+        info[CM_INFO_NS] = status == CM_ST_OK ? n_free : 0;
+        info[CM_INFO_NT] = status == CM_ST_OK ? (n_free + CM_TILE - 1) / CM_TILE : 0;
+        info[CM_INFO_NFIXED] = n_fixed;
+        info[CM_INFO_ZERO_LOAD] = 0;
+        info[CM_INFO_JACOBI] = 1;
+    }
+    if (status != CM_ST_OK) return;      // uniform for the block
+
+    // ---- the reference's id_map_RO: stable partition free | fixed | absent in DOF order
+    // (numpy_stiffness.py:193-208); three node-level exclusive scans
+    if (out.dof_map) {
+        int *dm = out.dof_map + (size_t)gs * 6 * nV;
+        // free
+        for (int v = t; v < nV; v += T) s_tmp[v] = s_free[v];
+        __syncthreads();
+        block_excl_scan(s_tmp, nV, s_scan);
+        for (int v = t; v < nV; v += T) {
+            if (!s_exist[v]) continue;
+            int r = s_tmp[v];
+            int s = m.node_sup[v];
+            for (int i = 0; i < 6; ++i)
+                if (s < 0 || !m.sup_cond[6 * s + i]) dm[r++] = 6 * v + i;
+        }
+        __syncthreads();
+        // fixed
+        for (int v = t; v < nV; v += T) s_tmp[v] = s_exist[v] ? 6 - s_free[v] : 0;
+        __syncthreads();
+        block_excl_scan(s_tmp, nV, s_scan);
+        for (int v = t; v < nV; v += T) {
+            if (!s_exist[v]) continue;
+            int s = m.node_sup[v];
+            if (s < 0) continue;
+            int r = n_free + s_tmp[v];
+            for (int i = 0; i < 6; ++i)
+                if (m.sup_cond[6 * s + i]) dm[r++] = 6 * v + i;
+        }
+        __syncthreads();
+        // absent
+        for (int v = t; v < nV; v += T) s_tmp[v] = s_exist[v] ? 0 : 6;
+        __syncthreads();
+        block_excl_scan(s_tmp, nV, s_scan);
+        for (int v = t; v < nV; v += T) {
+            if (s_exist[v]) continue;
+            int r = n_free + n_fixed + s_tmp[v];
+            for (int i = 0; i < 6; ++i) dm[r + i] = 6 * v + i;
+        }
+        __syncthreads();
+    }
+
+    // ---- compacted solver numbering: free DOFs of existing nodes in the static node ordering
+    for (int p = t; p < nV; p += T) s_tmp[p] = s_free[m.order[p]];
+    __syncthreads();
+    block_excl_scan(s_tmp, nV, s_scan);
+    for (int p = t; p < nV; p += T) s_base[m.order[p]] = s_tmp[p];
+    const int ns = n_free;
+    const int NT = (ns + CM_TILE - 1) / CM_TILE;
+    for (int I = t; I < NT; I += T) s_kfirst[I] = I;
+    __syncthreads();
+    for (int v = t; v < nV; v += T) {
+        int base = s_base[v];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sidx[6 * v + i] = s_exist[v] ? node_row(m, v, i, base) : -1;
+        // envelope: first column touched by the rows of this node
+        int nf = s_free[v];
+        if (nf == 0) continue;
+        int cmin = base;
+        for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
+            int e = m.ne_elem[p];
+            if (!elem_on(s_mask, e)) continue;
+            int c = m.conn[2 * e + (m.ne_end[p] ? 0 : 1)];
+            if (s_free[c]) cmin = min(cmin, s_base[c]);
+        }
+        int I0 = base / CM_TILE, I1 = (base + nf - 1) / CM_TILE;
+        atomicMin(&s_kfirst[I0], cmin / CM_TILE);
+        if (I1 != I0) atomicMin(&s_kfirst[I1], cmin / CM_TILE);
+    }
+    __syncthreads();
+    for (int I = t; I < NT; I += T) kfirst_g[I] = s_kfirst[I];
+
+    // ---- zero the tiles of the envelope (16-byte stores)
+    {
+        const int bt = m.band_tiles;
+        double2 z2 = make_double2(0.0, 0.0);
+        for (int I = 0; I < NT; ++I) {
+            int kf = s_kfirst[I];
+            int ntile = I - kf + 1;
+            double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)I * bt + (kf - I + bt - 1)) * CM_TILE_ELEMS);
+            int n2 = ntile * (CM_TILE_ELEMS / 2);
+            for (int i = t; i < n2; i += T) dst[i] = z2;
+        }
+    }
+
+    // ---- diagonal of K_mm and the Jacobi scale (numpy_stiffness.py:283-290)
+    int ok = 1;
+    for (int idx = t; idx < 6 * nV; idx += T) {
+        int v = idx / 6, i = idx - 6 * v;
+        if (!s_exist[v]) continue;
+        int r = node_row(m, v, i, s_base[v]);
+        if (r < 0) continue;
+        double kii = 0.0;
+        for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
+            int e = m.ne_elem[p];
+            if (!elem_on(s_mask, e)) continue;
+            int l = 6 * m.ne_end[p] + i;
+            kii += thr(m.Kg[(size_t)e * 144 + l * 12 + l]);
+        }
+        dinv[r] = kii;
+        if (!(fabs(kii) > CM_EPS)) ok = 0;
+    }
+    if (!ok) atomicOr(&s_red[3], 1);
+    __syncthreads();           // also orders the zero fill before the scatter below
+    const int jacobi = s_red[3] ? 0 : 1;
+    for (int r = t; r < NT * CM_TILE; r += T) {
+        double d = 1.0;
+        if (r < ns && jacobi) d = 1.0 / sqrt(dinv[r]);
+        dinv[r] = d;
+    }
+    if (t == 0) info[CM_INFO_JACOBI] = jacobi;
+    __syncthreads();
+
+    // ---- gather assembly, one warp per node row block
+    {
+        const int bt = m.band_tiles;
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        for (int a = warp; a < nV; a += nw) {
+            if (s_free[a] == 0) continue;
+            const int base_a = s_base[a];
+            const int p0 = m.ne_ptr[a], p1 = m.ne_ptr[a + 1];
+            // diagonal node block, lower triangle
+            for (int idx = lane; idx < 36; idx += 32) {
+                int i = idx / 6, j = idx - 6 * i;
+                if (j > i) continue;
+                int r = node_row(m, a, i, base_a), c = node_row(m, a, j, base_a);
+                if (r < 0 || c < 0) continue;
+                double s = 0.0;
+                for (int p = p0; p < p1; ++p) {
+                    int e = m.ne_elem[p];
+                    if (!elem_on(s_mask, e)) continue;
+                    int o = 6 * m.ne_end[p];
+                    s += thr(m.Kg[(size_t)e * 144 + (o + i) * 12 + o + j]);
+                }
+                s = (dinv[r] * s) * dinv[c];
+                int I = r >> 5, K = c >> 5;
+                tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, c & 31)] = s;
+            }
+            // off-diagonal node blocks (a,c) with c before a in the solver order
+            for (int p = p0; p < p1; ++p) {
+                int e = m.ne_elem[p];
+                if (!elem_on(s_mask, e)) continue;
+                int enda = m.ne_end[p];
+                int c = m.conn[2 * e + (enda ? 0 : 1)];
+                if (s_free[c] == 0 || s_base[c] > base_a) continue;
+                bool dup = false;            // an earlier existing element joins the same pair
+                for (int p2 = p0; p2 < p; ++p2) {
+                    int e2 = m.ne_elem[p2];
+                    if (elem_on(s_mask, e2) && m.conn[2 * e2 + (m.ne_end[p2] ? 0 : 1)] == c) dup = true;
+                }
+                if (dup) continue;
+                const int base_c = s_base[c];
+                for (int idx = lane; idx < 36; idx += 32) {
+                    int i = idx / 6, j = idx - 6 * i;
+                    int r = node_row(m, a, i, base_a), cc = node_row(m, c, j, base_c);
+                    if (r < 0 || cc < 0) continue;
+                    double s = 0.0;
+                    for (int p2 = p; p2 < p1; ++p2) {
+                        int e2 = m.ne_elem[p2];
+                        if (!elem_on(s_mask, e2)) continue;
+                        int ea2 = m.ne_end[p2];
+                        if (m.conn[2 * e2 + (ea2 ? 0 : 1)] != c) continue;
+                        s += thr(m.Kg[(size_t)e2 * 144 + (6 * ea2 + i) * 12 + 6 * (1 - ea2) + j]);
+                    }
+                    s = (dinv[r] * s) * dinv[cc];
+                    int I = r >> 5, K = cc >> 5;
+                    tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = s;
+                }
+            }
+        }
+        // unit diagonal on the padding rows of the last tile
+        for (int r = ns + t; r < NT * CM_TILE; r += T) {
+            int I = r >> 5;
+            tiles[((size_t)I * bt + (bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, r & 31)] = 1.0;
+        }
+    }
+
+    // ---- load vectors (numpy_stiffness.py:250-270): P = point + sum_e q_e; rhs = D * P_m
+    int zero_bits = 0;
+    for (int lc = 0; lc < m.n_lc; ++lc) {
+        double *Pl = P + (size_t)lc * 6 * nV;
+        double *Xl = X + (size_t)lc * L.n_pad;
+        for (int r = ns + t; r < NT * CM_TILE; r += T) Xl[r] = 0.0;
+        double sq = 0.0;
+        for (int idx = t; idx < 6 * nV; idx += T) {
+            int v = idx / 6, i = idx - 6 * v;
+            double pv = m.pnodal[(size_t)lc * 6 * nV + idx];
+            double qs = 0.0;
+            for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
+                int e = m.ne_elem[p];
+                if (!elem_on(s_mask, e)) continue;
+                qs += m.q[((size_t)lc * m.nE + e) * 12 + 6 * m.ne_end[p] + i];
+            }
+            pv += qs;
+            Pl[idx] = pv;
+            sq += pv * pv;
+            if (s_exist[v]) {
+                int r = node_row(m, v, i, s_base[v]);
+                if (r >= 0) Xl[r] = dinv[r] * pv;
+            }
+        }
+        // deterministic block reduction of the squared norm
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if ((t & 31) == 0) s_dred[t >> 5] = sq;
+        __syncthreads();
+        if (t == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < T / 32; ++w) tot += s_dred[w];
+            if (!(sqrt(tot) > CM_EPS)) zero_bits |= 1 << lc;
+        }
+        __syncthreads();
+    }
+    if (t == 0) info[CM_INFO_ZERO_LOAD] = zero_bits;
+}
+
+}  // namespace
+
+cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
+                                      const uint32_t *masks, long long first, int count,
+                                      const cm_out_dev &out, cudaStream_t st) {
+    size_t smem = (size_t)(2 * m.nV + m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV + 16;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k2_dofmap_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k2_dofmap_assemble<<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out);
+    return cudaGetLastError();
+}

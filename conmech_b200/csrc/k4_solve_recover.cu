@@ -1,0 +1,234 @@
+// K4 - fused back substitution and result recovery per (subset, load case): U_m = D L^-T D_piv^-1 y,
+// scatter to DOF order, compliance, fixity reactions R_f = K_fm U_m - P_f, element end forces
+// eR = -R12 (K_G,e U_e), max nodal translation/rotation and the success flag.
+//
+// Reference: numpy_stiffness.py:353-359 (solve, unscale, compliance), :366-372 (reactions),
+// :386-391 (element reactions, sign flipped: quirk Q4), :438-441 / :457-464 (criterion:
+// max_v ||u_v[0:3]||_2 < trans_tol, strict, NaN -> False).  One CTA per subset.
+#include "cm_common.cuh"
+
+namespace {
+
+constexpr int K4_THREADS = 256;
+constexpr int K4_WARPS = K4_THREADS / 32;
+
+__device__ __forceinline__ double thr(double k) { return (fabs(k) > CM_EPS) ? k : 0.0; }
+__device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (mask[e >> 5] >> (e & 31)) & 1u; }
+
+__device__ __forceinline__ const double *tile_ptr(const double *tiles, int bt, int I, int K) {
+    return tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS;
+}
+
+// NaN-propagating max (np.max semantics)
+__device__ __forceinline__ double nanmax(double a, double b) {
+    if (a != a) return a;
+    if (b != b) return b;
+    return a > b ? a : b;
+}
+
+__device__ double block_sum(double v, double *s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < K4_WARPS; ++w) tot += s_red[w];
+    return tot;
+}
+
+__device__ double block_nanmax(double v, double *s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = s_red[0];
+    for (int w = 1; w < K4_WARPS; ++w) tot = nanmax(tot, s_red[w]);
+    return tot;
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
+                 cm_out_dev out) {
+    __shared__ double s_part[K4_WARPS][32];
+    __shared__ double s_red[K4_WARPS];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long gs = first + blockIdx.x;
+    char *slab = ws + (size_t)blockIdx.x * L.per_subset;
+    const int *info = reinterpret_cast<const int *>(slab + L.off_info);
+    const int status = info[CM_INFO_STATUS];
+    const int NT = info[CM_INFO_NT];
+    const double *tiles = reinterpret_cast<const double *>(slab + L.off_tiles);
+    const int *kfirst = reinterpret_cast<const int *>(slab + L.off_kfirst);
+    const int *sidx = reinterpret_cast<const int *>(slab + L.off_sidx);
+    const double *dinv = reinterpret_cast<const double *>(slab + L.off_dinv);
+    const double *dpiv = reinterpret_cast<const double *>(slab + L.off_dpiv);
+    double *X = reinterpret_cast<double *>(slab + L.off_x);
+    const double *P = reinterpret_cast<const double *>(slab + L.off_p);
+    const uint32_t *mask = masks + (size_t)gs * m.mask_words;
+    const int bt = m.band_tiles, nV = m.nV, nE = m.nE, n_lc = m.n_lc;
+    const int zero_bits = info[CM_INFO_ZERO_LOAD];
+
+    if (out.min_pivot && t == 0)
+        out.min_pivot[gs] = (status == CM_ST_OK || status == CM_ST_SINGULAR) ? dpiv[L.n_pad] : nan("");
+
+    for (int lc = 0; lc < n_lc; ++lc) {
+        const size_t ol = (size_t)gs * n_lc + lc;
+        double *Uo = out.U ? out.U + ol * 6 * nV : nullptr;
+        double *Ro = out.Rf ? out.Rf + ol * 6 * nV : nullptr;
+        double *Eo = out.eR ? out.eR + ol * (size_t)nE * 12 : nullptr;
+        const bool zero_load = (zero_bits >> lc) & 1;
+        // a zero load vector skips the factorisation in the reference (numpy_stiffness.py:267), so a
+        // singular matrix does not fail that load case
+        if (status != CM_ST_OK && !(status == CM_ST_SINGULAR && zero_load)) {
+            // no stored result in the reference (has_stored_result() == False)
+            if (Uo) for (int i = t; i < 6 * nV; i += K4_THREADS) Uo[i] = 0.0;
+            if (Ro) for (int i = t; i < 6 * nV; i += K4_THREADS) Ro[i] = 0.0;
+            if (Eo) for (int i = t; i < 12 * nE; i += K4_THREADS) Eo[i] = 0.0;
+            if (t == 0) {
+                if (out.flag) out.flag[ol] = 0;
+                if (out.status) out.status[ol] = (unsigned char)status;
+                if (out.compliance) out.compliance[ol] = 0.0;
+                if (out.max_trans) out.max_trans[ol] = nan("");
+                if (out.max_rot) out.max_rot[ol] = nan("");
+            }
+            continue;
+        }
+        double *Xl = X + (size_t)lc * L.n_pad;
+
+        if (zero_load) {
+            for (int r = t; r < NT * CM_TILE; r += K4_THREADS) Xl[r] = 0.0;
+            __syncthreads();
+        } else {
+            // ---- back substitution L^T x = D^-1 y, block column by block column from the end
+            for (int J = NT - 1; J >= 0; --J) {
+                const int Iend = min(J + bt - 1, NT - 1);
+                double part = 0.0;
+                for (int I = J + 1 + warp; I <= Iend; I += K4_WARPS) {
+                    if (kfirst[I] > J) continue;
+                    const double *Lij = tile_ptr(tiles, bt, I, J);
+                    const double *xI = Xl + I * CM_TILE;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) part += Lij[cm_tile_off(r, lane)] * xI[r];
+                }
+                s_part[warp][lane] = part;
+                __syncthreads();
+                if (warp == 0) {
+                    double s = Xl[J * CM_TILE + lane] / dpiv[J * CM_TILE + lane];
+#pragma unroll
+                    for (int w = 0; w < K4_WARPS; ++w) s -= s_part[w][lane];
+                    const double *Ljj = tile_ptr(tiles, bt, J, J);
+#pragma unroll
+                    for (int c = 31; c > 0; --c) {
+                        const double xc = __shfl_sync(0xffffffffu, s, c);
+                        if (lane < c) s -= Ljj[cm_tile_off(c, lane)] * xc;
+                    }
+                    Xl[J * CM_TILE + lane] = s;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- displacements in DOF order (U = D x on free DOFs, 0 elsewhere), compliance
+        auto u_at = [&](int d) -> double {
+            int r = sidx[d];
+            return r >= 0 ? dinv[r] * Xl[r] : 0.0;
+        };
+        const double *Pl = P + (size_t)lc * 6 * nV;
+        double comp = 0.0;
+        for (int d = t; d < 6 * nV; d += K4_THREADS) {
+            double u = u_at(d);
+            if (Uo) Uo[d] = u;
+            if (sidx[d] >= 0) comp += u * Pl[d];
+        }
+        comp = 0.5 * block_sum(comp, s_red);
+
+        // ---- max nodal translation / rotation over existing nodes (row = 6 consecutive DOFs)
+        double mt = -1.0, mr = -1.0;
+        for (int v = t; v < nV; v += K4_THREADS) {
+            bool ex = false;
+            for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) ex |= elem_on(mask, m.ne_elem[p]);
+            if (!ex) continue;
+            double u0 = u_at(6 * v), u1 = u_at(6 * v + 1), u2 = u_at(6 * v + 2);
+            double r0 = u_at(6 * v + 3), r1 = u_at(6 * v + 4), r2 = u_at(6 * v + 5);
+            // np.linalg.norm(axis=1): sqrt(x0^2 + x1^2 + x2^2), no fused multiply-add
+            double nt = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(u0, u0), __dmul_rn(u1, u1)), __dmul_rn(u2, u2)));
+            double nr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
+            mt = nanmax(mt, nt);
+            mr = nanmax(mr, nr);
+        }
+        mt = block_nanmax(mt, s_red);
+        mr = block_nanmax(mr, s_red);
+
+        // ---- fixity reactions at the fixed DOFs of existing support nodes
+        if (Ro) {
+            for (int d = t; d < 6 * nV; d += K4_THREADS) Ro[d] = 0.0;
+            __syncthreads();
+            for (int idx = t; idx < 6 * m.nS; idx += K4_THREADS) {
+                int s = idx / 6, i = idx - 6 * s;
+                int v = m.sup_node[s];
+                if (!m.sup_cond[6 * s + i]) continue;
+                bool ex = false;
+                double acc = 0.0;
+                for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
+                    int e = m.ne_elem[p];
+                    if (!elem_on(mask, e)) continue;
+                    ex = true;
+                    const double *krow = m.Kg + (size_t)e * 144 + (6 * m.ne_end[p] + i) * 12;
+                    int n0 = m.conn[2 * e], n1 = m.conn[2 * e + 1];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc += thr(krow[j]) * u_at(6 * n0 + j);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc += thr(krow[6 + j]) * u_at(6 * n1 + j);
+                }
+                if (ex) Ro[6 * v + i] = acc - (zero_load ? 0.0 : Pl[6 * v + i]);   // P_f stays 0 when the solve is skipped (:260-270)
+            }
+        }
+
+        // ---- element end forces in local axes, four threads per element (one per 3-row block)
+        if (Eo) {
+            for (int idx = t; idx < 4 * nE; idx += K4_THREADS) {
+                int e = idx >> 2, pblk = idx & 3;
+                double *dst = Eo + (size_t)e * 12 + 3 * pblk;
+                if (!elem_on(mask, e)) { dst[0] = dst[1] = dst[2] = 0.0; continue; }
+                int n0 = m.conn[2 * e], n1 = m.conn[2 * e + 1];
+                double ue[12];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { ue[j] = u_at(6 * n0 + j); ue[6 + j] = u_at(6 * n1 + j); }
+                double tv[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double *krow = m.Kg + (size_t)e * 144 + (3 * pblk + a) * 12;
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) s += krow[j] * ue[j];
+                    tv[a] = s;
+                }
+                const double *R3 = m.R3 + (size_t)e * 9;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    dst[a] = -(R3[3 * a] * tv[0] + R3[3 * a + 1] * tv[1] + R3[3 * a + 2] * tv[2]);
+            }
+        }
+
+        if (t == 0) {
+            if (out.flag) out.flag[ol] = (mt < m.trans_tol) ? 1 : 0;
+            if (out.status) out.status[ol] = zero_load ? CM_ST_ZERO_LOAD : CM_ST_OK;
+            if (out.compliance) out.compliance[ol] = comp;
+            if (out.max_trans) out.max_trans[ol] = mt;
+            if (out.max_rot) out.max_rot[ol] = mr;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
+                                    const uint32_t *masks, long long first, int count,
+                                    const cm_out_dev &out, cudaStream_t st) {
+    k4_solve_recover<<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, first, out);
+    return cudaGetLastError();
+}

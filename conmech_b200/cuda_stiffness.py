@@ -1,0 +1,507 @@
+"""``CudaStiffness``: the B200 engine behind ``StiffnessChecker(checker_engine="cuda")``.
+
+Host-side mirror of the reference's ``NumpyStiffness`` (``src/pyconmech/frame_analysis/
+numpy_stiffness.py:34-634``): same constructor, load setters, ``solve`` / ``get_solved_results``
+and procedural getters, same return conventions (numerical failure is a ``False`` return,
+programmer errors raise).  All arithmetic of the hot path runs in hand-written sm_100a
+kernels reached through the C ABI of ``include/conmech_b200.h``; this module only flattens the
+``Model`` into arrays once, packs element-id lists into bit masks and reshapes results.
+There is no CPU fallback: without the CUDA library or a CUDA device the constructor raises.
+
+Beyond the reference interface it adds the batched entry points ``solve_many`` (host
+buffers) and ``solve_many_device`` (torch CUDA tensors, caller's stream).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import OUT_FIELDS, ST_OK, ST_NO_SUPPORT, ST_NO_FIXED_DOF, ST_SINGULAR, ST_ZERO_LOAD
+from .masks import pack_masks
+from .stiffness_base import StiffnessBase
+
+DOUBLE_EPS = 1e-14
+DEFAULT_GRAVITY_DIRECTION = np.array([0., 0., -1.])
+
+_OUT_DTYPE = {'flag': np.uint8, 'status': np.uint8, 'n_free': np.int32, 'n_fixed': np.int32,
+              'dof_map': np.int32, 'node_exists': np.uint8, 'U': np.float64, 'Rf': np.float64,
+              'eR': np.float64, 'compliance': np.float64, 'max_trans': np.float64,
+              'max_rot': np.float64, 'min_pivot': np.float64}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class CudaStiffness(StiffnessBase):
+    def __init__(self, model, verbose=False, output_json=False, device=None):
+        super(CudaStiffness, self).__init__(model, verbose, output_json)
+        self._lib = _capi.load()
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', 0)) if 'LOCAL_RANK' in os.environ else 0
+        self._device = int(device)
+        self._handle = C.c_void_p()
+
+        self._trans_tol = 1e-3
+        self._rot_tol = np.pi / 180 * 3
+        self._include_self_weight_load = False
+        self._gravity_direction = np.array(DEFAULT_GRAVITY_DIRECTION)
+        self._node_neighbors = self.get_node_neighbors()
+        self._e_ind_from_tag = self.get_elem_ind_from_elem_tag()
+
+        nV, nE = self.nV, self.nE
+        self._nodal_load = np.zeros(nV * 6)
+        self._udl = None                       # None or {elem index: q (3,)}
+        self._loadcase_list = None             # set_load_cases(): explicit multi load case table
+        self._loads_dirty = True
+        self._n_lc = 1
+
+        self._has_stored_deformation = False
+        self._stored_existing_ids = []
+        self._stored_nD = None
+        self._stored_eR = None
+        self._stored_fR = None
+        self._stored_compliance = None
+        self._last_status = None
+
+        self._element_k_list = None
+        self._rot_list = None
+        self._ws_cache = {}
+
+        self._v_id_map = np.arange(6 * nV, dtype=int).reshape(nV, 6)         # numpy_stiffness.py:563-565
+        self._flatten_and_create(model)
+        self._lib.cm_set_tol(self._handle, self._trans_tol, self._rot_tol)
+
+    def __del__(self):
+        h = getattr(self, '_handle', None)
+        if h is not None and h.value:
+            try:
+                self._lib.cm_destroy(h)
+            except Exception:
+                pass
+            self._handle = C.c_void_p()
+
+    # ------------------------------------------------------------------ model flattening
+    @property
+    def nV(self):
+        return len(self._nodes)
+
+    @property
+    def nE(self):
+        return len(self._elements)
+
+    def _flatten_and_create(self, model):
+        """Model -> SoA arrays -> cm_create.  Per-element lookups follow
+        numpy_stiffness.py:579-614; the support table follows :172-184 (Q11: the rotational
+        pin looks at neighbours in the FULL model)."""
+        nV, nE = self.nV, self.nE
+        xyz = np.array([n.point for n in self._nodes], dtype=np.float64).reshape(nV, 3)
+        conn = np.array([e.end_node_inds for e in self._elements], dtype=np.int32).reshape(nE, 2)
+        props = np.zeros((nE, 7))
+        cr = np.full((nE, 6), np.inf)
+        for i, element in enumerate(self._elements):
+            u, v = element.end_node_inds
+            L = np.linalg.norm(xyz[u] - xyz[v])
+            if L < DOUBLE_EPS:
+                raise ValueError('E#{} - Bar length too small!: Node {} - Node {}'.format(i, xyz[u], xyz[v]))
+            joint = self.get_element_joint(i)
+            if joint is not None:
+                c = joint.c_conditions
+                assert all([x is None or x == np.inf for x in c[0:3]]) and \
+                       all([x is None or x == np.inf for x in c[6:9]]), "We do not support translational joint now!"
+                cr[i, 0:3] = [np.inf if x is None else x for x in c[3:6]]
+                cr[i, 3:6] = [np.inf if x is None else x for x in c[9:12]]
+            if not element.bending_stiff:
+                cr[i, :] = 0.0
+            cs = self.get_element_crosssec(i)
+            mat = self.get_element_material(i)
+            assert abs(mat.E) > DOUBLE_EPS and abs(cs.Iz) > DOUBLE_EPS
+            props[i] = [cs.A, cs.Jx, cs.Iy, cs.Iz, mat.E, mat.mu, mat.density]
+        sup_node = np.array(list(self._supports.keys()), dtype=np.int32)
+        sup_cond = np.zeros((len(sup_node), 6), dtype=np.uint8)
+        for k, v in enumerate(sup_node):
+            cond = np.array(self._supports[int(v)].condition, dtype=int)
+            assert all(s >= 0 for s in cond)
+            if all([not self._elements[e].bending_stiff for e in self._node_neighbors[int(v)]]):
+                cond[3:] = 1
+            sup_cond[k] = cond
+        self._xyz, self._conn, self._props, self._cr = xyz, conn, props, cr
+        self._sup_node, self._sup_cond = sup_node, sup_cond
+        self._id_map = np.hstack([self._v_id_map[conn[:, 0]], self._v_id_map[conn[:, 1]]])   # :567-570
+
+        desc = _capi.ModelDesc(nV, nE, len(sup_node), self._device,
+                               xyz.ctypes.data_as(_capi.c_double_p), conn.ctypes.data_as(_capi.c_int32_p),
+                               props.ctypes.data_as(_capi.c_double_p), cr.ctypes.data_as(_capi.c_double_p),
+                               sup_node.ctypes.data_as(_capi.c_int32_p), sup_cond.ctypes.data_as(_capi.c_uint8_p))
+        _capi.check(self._lib.cm_create(C.byref(desc), C.byref(self._handle)))
+        self._info = _capi.ModelInfo()
+        _capi.check(self._lib.cm_get_info(self._handle, C.byref(self._info)))
+
+    @property
+    def info(self):
+        """Static solver facts (free DOFs, half bandwidth, tile counts, profile flops)."""
+        i = self._info
+        return {f: getattr(i, f) for f, _ in i._fields_}
+
+    # ------------------------------------------------------------------ loads
+    def set_self_weight_load(self, include_self_weight=True, gravity_direction=DEFAULT_GRAVITY_DIRECTION):
+        """numpy_stiffness.py:98-111."""
+        self._include_self_weight_load = include_self_weight
+        if include_self_weight:
+            assert len(gravity_direction) == 3
+            self._gravity_direction = np.array(gravity_direction, dtype=float)
+        self._loadcase_list = None
+        self._loads_dirty = True
+
+    def set_uniformly_distributed_loads(self, unif_dist_loads):
+        """numpy_stiffness.py:113-123: {elem_tag: UniformlyDistLoad} or None to reset."""
+        if unif_dist_loads is not None:
+            d = {}
+            for e_tag, uload in unif_dist_loads.items():
+                for e_ind in self._e_ind_from_tag[e_tag]:
+                    d[e_ind] = np.array(uload.q, dtype=float)
+            self._udl = d
+        else:
+            self._udl = None
+        self._loadcase_list = None
+        self._loads_dirty = True
+
+    def set_load(self, nodal_forces):
+        """numpy_stiffness.py:125-138: {node id: PointLoad}; None resets.  Like the reference,
+        a dict only overwrites the listed nodes (Q6)."""
+        if nodal_forces is not None:
+            for v_id, pf in nodal_forces.items():
+                self._nodal_load[self._v_id_map[v_id, :]] = np.array(list(pf.force) + list(pf.moment))
+        else:
+            self._nodal_load = np.zeros(self.nV * 6)
+        self._loadcase_list = None
+        self._loads_dirty = True
+
+    def set_load_cases(self, loadcases):
+        """Batched extension: solve several ``LoadCase`` objects per subset in one pass (the
+        factorisation is shared).  Each case is taken on its own (no carry-over between cases)."""
+        tabs = []
+        for lc in loadcases:
+            nodal = np.zeros(6 * self.nV)
+            for pl in lc.point_loads:
+                nodal[6 * pl.node_ind:6 * pl.node_ind + 6] = list(pl.force) + list(pl.moment)
+            udl = None
+            if lc.uniform_element_loads:
+                udl = {}
+                for ul in lc.uniform_element_loads:
+                    tags = ul.elem_tags if len(ul.elem_tags) > 0 else [""]
+                    for tg in tags:
+                        for e in self._e_ind_from_tag[tg]:
+                            udl[e] = np.array(ul.q, dtype=float)
+            g = lc.gravity_load
+            tabs.append((nodal, udl, g is not None, np.array(g.force, dtype=float) if g is not None else DEFAULT_GRAVITY_DIRECTION))
+        assert 1 <= len(tabs) <= 8
+        self._loadcase_list = tabs
+        self._loads_dirty = True
+
+    def _push_loads(self):
+        if not self._loads_dirty:
+            return
+        tabs = self._loadcase_list or [(self._nodal_load, self._udl, self._include_self_weight_load,
+                                        self._gravity_direction)]
+        n_lc, nV, nE = len(tabs), self.nV, self.nE
+        nodal = np.zeros((n_lc, 6 * nV))
+        w = np.zeros((n_lc, nE, 3))
+        has = np.zeros((n_lc, nE), dtype=np.uint8)
+        on = np.zeros(n_lc, dtype=np.uint8)
+        gd = np.zeros((n_lc, 3))
+        for k, (nl, udl, sw, gdir) in enumerate(tabs):
+            nodal[k] = nl
+            if udl:
+                for e, q in udl.items():
+                    w[k, e] = q
+                    has[k, e] = 1
+            on[k] = 1 if sw else 0
+            gd[k] = gdir
+        any_udl = bool(has.any())
+        _capi.check(self._lib.cm_set_loadcases(self._handle, n_lc, _ptr(nodal), _ptr(w) if any_udl else None,
+                                               _ptr(has) if any_udl else None, _ptr(on), _ptr(gd)))
+        self._n_lc = n_lc
+        self._loads_dirty = False
+
+    # ------------------------------------------------------------------ tolerances
+    def set_nodal_displacement_tol(self, transl_tol, rot_tol):
+        self._trans_tol = transl_tol
+        self._rot_tol = rot_tol
+        self._lib.cm_set_tol(self._handle, float(transl_tol), float(rot_tol))
+
+    def get_nodal_deformation_tol(self):
+        return (self._trans_tol, self._rot_tol)
+
+    def set_factor_variant(self, variant):
+        """1 = FP64 tensor-core factorisation (default), 0 = scalar validation variant."""
+        _capi.check(self._lib.cm_set_variant(self._handle, int(variant)))
+
+    # ------------------------------------------------------------------ batched solves
+    def _as_masks(self, subsets):
+        if isinstance(subsets, np.ndarray) and subsets.dtype == np.uint32 and subsets.ndim == 2:
+            assert subsets.shape[1] == self._info.mask_words
+            return np.ascontiguousarray(subsets)
+        return pack_masks(subsets, self.nE)
+
+    def _out_shapes(self, B):
+        nV, nE, L = self.nV, self.nE, self._n_lc
+        return {'flag': (B, L), 'status': (B, L), 'n_free': (B,), 'n_fixed': (B,), 'dof_map': (B, 6 * nV),
+                'node_exists': (B, nV), 'U': (B, L, 6 * nV), 'Rf': (B, L, 6 * nV), 'eR': (B, L, nE, 12),
+                'compliance': (B, L), 'max_trans': (B, L), 'max_rot': (B, L), 'min_pivot': (B,)}
+
+    def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):
+        """Solve B element subsets (list of id lists, [] = full structure, or a (B, words)
+        uint32 mask matrix) with HOST buffers: masks are copied to the GPU, the kernels run, and
+        the requested outputs are copied back.  Returns {name: ndarray}; see ``cm_solve_out``
+        in include/conmech_b200.h for names and shapes.  ``out`` may hold preallocated
+        (e.g. pinned) arrays to write into."""
+        self._push_loads()
+        masks = self._as_masks(subsets)
+        B = masks.shape[0]
+        shapes = self._out_shapes(B)
+        res = {}
+        oh = _capi.SolveOutHost()
+        for name in OUT_FIELDS:
+            if name in want:
+                a = out[name] if out is not None and name in out else np.empty(shapes[name], dtype=_OUT_DTYPE[name])
+                assert a.flags['C_CONTIGUOUS'] and a.dtype == _OUT_DTYPE[name] and a.size == int(np.prod(shapes[name]))
+                res[name] = a
+                setattr(oh, name, a.ctypes.data)
+            else:
+                setattr(oh, name, None)
+        _capi.check(self._lib.cm_solve_many_host(self._handle, _ptr(masks), B, C.byref(oh)))
+        return res
+
+    def solve_many_device(self, masks, want=('flag', 'status', 'max_trans', 'compliance'), out=None,
+                          max_in_flight=4096):
+        """Same on DEVICE buffers: ``masks`` is a (B, words) int32/uint32 torch CUDA tensor; outputs
+        are torch CUDA tensors; kernels are enqueued on torch's current stream and the call
+        returns without synchronising."""
+        import torch
+        self._push_loads()
+        assert masks.is_cuda and masks.dim() == 2 and masks.shape[1] == self._info.mask_words
+        assert masks.element_size() == 4 and masks.is_contiguous()
+        dev = masks.device
+        B = masks.shape[0]
+        shapes = self._out_shapes(B)
+        tdt = {np.uint8: torch.uint8, np.int32: torch.int32, np.float64: torch.float64}
+        res = {}
+        od = _capi.SolveOut()
+        for name in OUT_FIELDS:
+            if name in want:
+                tns = out[name] if out is not None and name in out else \
+                    torch.empty(shapes[name], dtype=tdt[_OUT_DTYPE[name]], device=dev)
+                assert tns.is_contiguous()
+                res[name] = tns
+                setattr(od, name, tns.data_ptr())
+            else:
+                setattr(od, name, 0)
+        n_fly = int(min(B, max_in_flight))
+        nbytes = int(self._lib.cm_workspace_bytes(self._handle, n_fly))
+        key = (dev.index, self._n_lc)
+        ws = self._ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws_cache = {key: ws}
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(self._lib.cm_solve_many(self._handle, masks.data_ptr(), B, C.byref(od), ws.data_ptr(),
+                                            ws.numel(), stream))
+        return res
+
+    def kernel_launches(self):
+        return int(self._lib.cm_kernel_launches(self._handle))
+
+    def reset_counters(self):
+        self._lib.cm_reset_counters(self._handle)
+
+    def enable_timing(self, on=True):
+        self._lib.cm_enable_timing(self._handle, 1 if on else 0)
+
+    def last_stage_ms(self):
+        ms = np.zeros(3)
+        self._lib.cm_last_stage_ms(self._handle, _ptr(ms))
+        return ms
+
+    # ------------------------------------------------------------------ the reference interface
+    def solve(self, exist_element_ids=[], if_cond_num=False):
+        """numpy_stiffness.py:228-397 for one subset; stores nD / fR / eR like the reference
+        (row orders per SURVEY Q8)."""
+        ids = list(exist_element_ids)
+        if len(ids) == 0:
+            ids = list(range(self.nE))
+        r = self.solve_many([ids], want=('flag', 'status', 'U', 'Rf', 'eR', 'compliance', 'n_free', 'n_fixed'))
+        status = int(r['status'][0, 0])
+        self._last_status = status
+        if status in (ST_NO_SUPPORT, ST_NO_FIXED_DOF, ST_SINGULAR):
+            if self._verbose:
+                print({ST_NO_SUPPORT: 'Structure floating: no fixed node exists in the partial structure.',
+                       ST_NO_FIXED_DOF: 'Not stable: At least one node needs to be fixed in the considered substructure!',
+                       ST_SINGULAR: 'ERROR: Stiffness Solver fail! Stiffness matrix not Positive Definite, '
+                                    'the sub-structure might contain mechanism.'}[status])
+            self._has_stored_deformation = False
+            return False
+        U, R, E = r['U'][0, 0], r['Rf'][0, 0], r['eR'][0, 0]
+        exist_node_set = set()
+        for e in ids:
+            exist_node_set.update(self._elements[e].end_node_inds)
+        self._stored_nD = np.zeros((len(exist_node_set), 7))
+        for i, v in enumerate(list(exist_node_set)):
+            self._stored_nD[i, 0] = v
+            self._stored_nD[i, 1:] = U[6 * v:6 * v + 6]
+        fix_rows = [v for v in self._supports if v in exist_node_set]
+        self._stored_fR = np.zeros((len(fix_rows), 7))
+        for i, v in enumerate(fix_rows):
+            self._stored_fR[i, 0] = v
+            self._stored_fR[i, 1:] = R[6 * v:6 * v + 6]
+        self._stored_eR = np.zeros((len(ids), 13))
+        for i, e in enumerate(ids):
+            self._stored_eR[i, 0] = e
+            self._stored_eR[i, 1:] = E[e]
+        self._stored_compliance = float(r['compliance'][0, 0])
+        self._stored_existing_ids = np.copy(ids)
+        self._has_stored_deformation = True
+        return bool(r['flag'][0, 0])
+
+    def check_stiffness_criteria(self, node_displ, fixities_reaction, element_reaction, ord=None):
+        nD_trans_max, _, _, _ = self.get_max_nodal_deformation(ord=ord)
+        return bool(nD_trans_max < self._trans_tol)
+
+    def has_stored_result(self):
+        return self._has_stored_deformation
+
+    def get_solved_results(self):
+        assert self.has_stored_result()
+        success = self.check_stiffness_criteria(self._stored_nD, self._stored_fR, self._stored_eR)
+        return (success, self._stored_nD, self._stored_fR, self._stored_eR)
+
+    def get_compliance(self):
+        assert self.has_stored_result()
+        return self._stored_compliance
+
+    def get_max_nodal_deformation(self, ord=None):
+        """numpy_stiffness.py:457-464 (Q5: the indices are ROW indices of nD)."""
+        assert self.has_stored_result()
+        t = np.linalg.norm(self._stored_nD[:, 1:4], ord=ord, axis=1)
+        r = np.linalg.norm(self._stored_nD[:, 4:7], ord=ord, axis=1)
+        return (np.max(t), np.max(r), np.argmax(t), np.argmax(r))
+
+    def get_frame_stat(self):
+        return (self.nV, self.nE)
+
+    # ---- procedural data
+    def _element_loads(self, lc=0):
+        q = np.zeros((self.nE, 12))
+        _capi.check(self._lib.cm_get_element_loads(self._handle, lc, _ptr(q)))
+        return q
+
+    def _scatter_element_loads(self, q, ids):
+        P = np.zeros(6 * self.nV)
+        ids = np.asarray(list(ids), dtype=int)
+        np.add.at(P, self._id_map[ids].ravel(), q[ids].ravel())
+        return P
+
+    def get_gravity_nodal_loads(self, existing_ids=[]):
+        assert self._include_self_weight_load, 'Call `set_self_weight_load` first to init the load!'
+        if len(existing_ids) == 0:
+            existing_ids = range(self.nE)
+        # gravity-only table: push a temporary load case, fetch, restore lazily
+        saved = (self._loadcase_list, self._loads_dirty)
+        self._loadcase_list = [(np.zeros(6 * self.nV), None, True, self._gravity_direction)]
+        self._loads_dirty = True
+        self._push_loads()
+        q = self._element_loads(0)
+        self._loadcase_list = saved[0]
+        self._loads_dirty = True
+        return self._scatter_element_loads(q, existing_ids)
+
+    def get_lumped_nodal_loads(self, existing_ids=[]):
+        if len(existing_ids) == 0:
+            existing_ids = range(self.nE)
+        self._push_loads()
+        P = np.copy(self._nodal_load) if self._loadcase_list is None else np.copy(self._loadcase_list[0][0])
+        return P + self._scatter_element_loads(self._element_loads(0), existing_ids)
+
+    def _fetch_tables(self):
+        if self._element_k_list is None:
+            K = np.zeros((self.nE, 12, 12))
+            R3 = np.zeros((self.nE, 3, 3))
+            _capi.check(self._lib.cm_get_element_tables(self._handle, _ptr(K), _ptr(R3), None))
+            R12 = np.zeros((self.nE, 12, 12))
+            for i in range(4):
+                R12[:, 3 * i:3 * i + 3, 3 * i:3 * i + 3] = R3
+            self._element_k_list = [K[e] for e in range(self.nE)]
+            self._rot_list = [R12[e] for e in range(self.nE)]
+
+    def get_element_stiffness_matrices(self):
+        self._fetch_tables()
+        return self._element_k_list
+
+    def get_element_local2global_rot_matrices(self):
+        self._fetch_tables()
+        return self._rot_list
+
+    def get_element2dof_id_map(self):
+        return self._id_map
+
+    def get_node2dof_id_map(self):
+        return self._v_id_map
+
+    def compute_full_stiffness_matrix(self, exist_element_ids=[]):
+        """numpy_stiffness.py:221-226: the (6nV)^2 sparse K of a subset, from the GPU-built
+        element tables (a procedural getter, not on the batched path)."""
+        from scipy.sparse import csc_matrix
+        ids = np.asarray(list(exist_element_ids) or list(range(self.nE)), dtype=int)
+        K = np.asarray(self.get_element_stiffness_matrices())
+        rows = np.repeat(self._id_map[ids][:, :, None], 12, axis=2).ravel()
+        cols = np.repeat(self._id_map[ids][:, None, :], 12, axis=1).ravel()
+        data = K[ids].ravel()
+        keep = np.abs(data) > DOUBLE_EPS
+        n = 6 * self.nV
+        return csc_matrix((data[keep], (rows[keep], cols[keep])), shape=(n, n), dtype=float)
+
+    def compute_dof_permutation(self, exist_element_ids=[]):
+        """numpy_stiffness.py:147-219 from the GPU DOF map: (Perm, (node set, n_free, n_fixed,
+        n existing fixed nodes)); ValueError when no support exists, bare False when the
+        supports fix nothing (Q10)."""
+        from scipy.sparse import csc_matrix
+        ids = list(exist_element_ids) or list(range(self.nE))
+        r = self.solve_many([ids], want=('status', 'n_free', 'n_fixed', 'dof_map', 'node_exists'))
+        status = int(r['status'][0, 0])
+        if status == ST_NO_SUPPORT:
+            raise ValueError('Structure floating: no fixed node exists in the partial structure.')
+        if status == ST_NO_FIXED_DOF:
+            return False
+        n = 6 * self.nV
+        Perm = csc_matrix((np.ones(n, dtype=int), (np.arange(n), r['dof_map'][0])), shape=(n, n))
+        node_set = set(int(v) for v in np.flatnonzero(r['node_exists'][0]))
+        n_fix_nodes = len([v for v in self._supports if v in node_set])
+        return Perm, (node_set, int(r['n_free'][0]), int(r['n_fixed'][0]), n_fix_nodes)
+
+    def get_node_neighbors(self):
+        nb = {}
+        for e in self._elements:
+            for n in e.end_node_inds:
+                nb.setdefault(n, set()).add(e.elem_ind)
+        for v in range(len(self._nodes)):
+            nb.setdefault(v, set())
+        return nb
+
+    def get_elem_ind_from_elem_tag(self):
+        d = {}
+        for e in self._elements:
+            d.setdefault(e.elem_tag, []).append(e.elem_ind)
+        return d
+
+    def get_original_shape(self):
+        raise NotImplementedError()
+
+    def get_deformed_shape(self, exagg_ratio=1.0, disc=10):
+        raise NotImplementedError()
+
+    def set_output_json_path(self, file_path, file_name):
+        raise NotImplementedError()
+
+    def set_output_json(self, output_json=False):
+        raise NotImplementedError()

@@ -1,0 +1,37 @@
+"""Element-subset bit masks: the wire format of the batched solve (uint32 words, bit e%32 of
+word e//32 set = element e exists)."""
+import numpy as np
+
+
+def ids_to_mask(ids, nE):
+    m = np.zeros((nE + 31) // 32, dtype=np.uint32)
+    ids = np.asarray(ids, dtype=np.int64)
+    np.bitwise_or.at(m, ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
+    return m
+
+
+def pack_masks(list_of_ids, nE, out=None):
+    """(B, ceil(nE/32)) uint32 masks for a list of id lists.  An empty list means the full
+    structure (reference ``numpy_stiffness.py:230-231``).  Ids out of range raise IndexError."""
+    B = len(list_of_ids)
+    W = (nE + 31) // 32
+    bits = np.zeros((B, W * 32), dtype=np.uint8)
+    for b, ids in enumerate(list_of_ids):
+        if len(ids) == 0:
+            bits[b, :nE] = 1
+        else:
+            idx = np.asarray(ids, dtype=np.int64)
+            if idx.min() < 0 or idx.max() >= nE:
+                raise IndexError('element id not within range!')
+            bits[b, idx] = 1
+    packed = np.packbits(bits.reshape(B, W, 32), axis=2, bitorder='little')      # (B, W, 4) bytes
+    packed = np.ascontiguousarray(packed).view('<u4').reshape(B, W)
+    if out is not None:
+        out[...] = packed
+        return out
+    return packed
+
+
+def mask_to_ids(mask, nE):
+    bits = np.unpackbits(np.ascontiguousarray(mask).view(np.uint8), bitorder='little')[:nE]
+    return np.flatnonzero(bits)

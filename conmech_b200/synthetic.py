@@ -166,24 +166,4 @@ def config4_loadcases(model, seed=0):
                      gravity_load=g())]
 
 
-def ids_to_mask(ids, nE):
-    """Bit mask (uint32 words, little-endian bit order) of an element id list."""
-    m = np.zeros((nE + 31) // 32, dtype=np.uint32)
-    ids = np.asarray(ids, dtype=np.int64)
-    np.bitwise_or.at(m, ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
-    return m
-
-
-def pack_masks(list_of_ids, nE):
-    """(B, ceil(nE/32)) uint32 mask matrix for a list of id lists; an empty list means all
-    elements (reference ``numpy_stiffness.py:230-231``)."""
-    B = len(list_of_ids)
-    W = (nE + 31) // 32
-    bits = np.zeros((B, W * 32), dtype=np.uint8)
-    for b, ids in enumerate(list_of_ids):
-        if len(ids) == 0:
-            bits[b, :nE] = 1
-        else:
-            bits[b, np.asarray(ids, dtype=np.int64)] = 1
-    packed = np.packbits(bits.reshape(B, W, 32), axis=2, bitorder='little')   # (B, W, 4) bytes
-    return np.ascontiguousarray(packed).view('<u4').reshape(B, W)
+from .masks import ids_to_mask, pack_masks, mask_to_ids   # noqa: E402,F401  (re-exported)

@@ -1,0 +1,189 @@
+/*
+ * conmech_b200 - C ABI of the B200-native partial-structure stiffness solver.
+ *
+ * This is the drop-in boundary for the reference's engine plug-in point
+ * (reference src/pyconmech/frame_analysis/stiffness_checker.py:57-66 selects an engine
+ * object; src/pyconmech/frame_analysis/stiffness_base.py:8-155 is the interface that
+ * object implements; src/pyconmech_bindings/pybind_stiffness_checker.cpp:19-243 is the
+ * reference's existing native binding of the same surface).  The Python host class
+ * conmech_b200.CudaStiffness binds these entry points with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (CM_OK) or a negative CM_ERR_* code and
+ *     leaves a message retrievable with cm_last_error() (thread-local).  No C++ exception
+ *     crosses the boundary.  Numerical failure of a solve is NOT an error: it is reported
+ *     per subset in `status` / `flag`, like the reference returns False
+ *     (numpy_stiffness.py:238-240, 301-319, 326-336).
+ *   - "dev" pointers are CUDA device addresses passed as uint64_t (what torch's
+ *     Tensor.data_ptr() returns); "host" pointers are ordinary pointers.
+ *   - the caller owns every input/output buffer and the workspace; the library owns only the
+ *     opaque handle (model tables, load tables, small scratch) on the device it was created on.
+ *   - one handle per device; a handle is not thread-safe; different handles may be used
+ *     concurrently.
+ *   - all floating point is IEEE fp64; indices are int32; DOF numbering is 6*node + {0..5}
+ *     (numpy_stiffness.py:563-570).
+ */
+#ifndef CONMECH_B200_H
+#define CONMECH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_OK 0
+#define CM_ERR_INVALID (-1)   /* bad argument / inconsistent model                     */
+#define CM_ERR_CUDA (-2)      /* CUDA runtime error, message has the CUDA error string */
+#define CM_ERR_NOMEM (-3)     /* workspace too small / allocation failed               */
+#define CM_ERR_STATE (-4)     /* call order (e.g. solve before cm_set_loadcases)       */
+
+/* per (subset, load case) status, mirrors the reference's routes to `return False`
+ *  */
+#define CM_ST_OK 0            /* solved; flag = max_trans < trans_tol                              */
+#define CM_ST_NO_SUPPORT 1    /* no support node in the subset (numpy_stiffness.py:166-168)        */
+#define CM_ST_NO_FIXED_DOF 2  /* existing supports fix zero DOFs (numpy_stiffness.py:186-189)      */
+#define CM_ST_SINGULAR 3      /* zero / negative (<= -1e-14) / NaN pivot (numpy_stiffness.py:301-336) */
+#define CM_ST_ZERO_LOAD 4     /* ||P|| <= 1e-14: solve skipped, U = 0, flag = 0 < tol (:267,360-363) */
+
+typedef struct cm_handle cm_handle;
+
+/* Frame description, host pointers.  Replaces the constructor arguments of the reference's
+ * native engine (pybind_stiffness_checker.cpp:37-54: V, E, Fixities, materials) and the
+ * per-element lookups of NumpyStiffness._precompute_element_stiffness_matrices
+ * (numpy_stiffness.py:579-614). */
+typedef struct cm_model_desc {
+    int32_t n_nodes;
+    int32_t n_elems;
+    int32_t n_supports;
+    int32_t device;          /* CUDA device ordinal                                              */
+    const double *xyz;       /* [n_nodes*3] metres                                               */
+    const int32_t *conn;     /* [n_elems*2] end node ids                                         */
+    const double *props;     /* [n_elems*7] A, Jx, Iy, Iz, E, mu, density                        */
+    const double *cr;        /* [n_elems*6] rotational end springs (x,y,z at end 0, then end 1): */
+                             /*   +inf rigid, 0 released; all 0 for bending_stiff=false          */
+    const int32_t *sup_node; /* [n_supports] support node ids in model (JSON) order              */
+    const uint8_t *sup_cond; /* [n_supports*6] 1 = fixed, after the all-truss-neighbours         */
+                             /*   rotational pin rule (numpy_stiffness.py:179-181)               */
+} cm_model_desc;
+
+/* Static facts about a created model (sizes a caller needs to allocate outputs). */
+typedef struct cm_model_info {
+    int32_t n_nodes, n_elems, n_supports, n_loadcases;
+    int32_t mask_words;        /* uint32 words per subset mask = ceil(n_elems/32)                */
+    int32_t n_free_full;       /* free DOFs of the full structure                                */
+    int32_t half_bandwidth;    /* of the full structure in the static solver ordering            */
+    int32_t tile;              /* tile edge of the block-band storage (32)                       */
+    int32_t n_tile_rows_max;   /* ceil(n_free_full / tile)                                       */
+    int32_t band_tiles;        /* tiles kept per tile row (half bandwidth in tiles + 1)          */
+    int64_t profile_flops_full;/* sum_j h_j^2 of the full structure in the solver ordering       */
+} cm_model_info;
+
+int cm_create(const cm_model_desc *desc, cm_handle **out);
+int cm_destroy(cm_handle *h);
+int cm_get_info(const cm_handle *h, cm_model_info *info);
+
+/* Element tables built on the device by the element kernel; copied to host arrays.
+ * Replaces get_element_stiffness_matrices / get_element_local2global_rot_matrices /
+ * get_element2dof_id_map (numpy_stiffness.py:503-513).  Any pointer may be NULL. */
+int cm_get_element_tables(cm_handle *h, double *Kg /*[nE*144]*/, double *R3 /*[nE*9]*/,
+                          int32_t *id_map /*[nE*12]*/);
+
+/* Static solver ordering (position -> node id), host array [n_nodes]. */
+int cm_get_node_order(const cm_handle *h, int32_t *order);
+
+/* Load cases, host pointers.  Replaces set_load / set_uniformly_distributed_loads /
+ * set_self_weight_load (numpy_stiffness.py:98-138); n_lc load cases are solved per subset.
+ *   nodal   [n_lc*6*n_nodes]  point loads already scattered to DOFs
+ *   w_udl   [n_lc*n_elems*3]  uniform line load (global axes) per element, used where has_udl
+ *   has_udl [n_lc*n_elems]    may be NULL (= none)
+ *   grav_on [n_lc]            self weight on/off; grav_dir [n_lc*3] (not normalised) */
+int cm_set_loadcases(cm_handle *h, int32_t n_lc, const double *nodal, const double *w_udl,
+                     const uint8_t *has_udl, const uint8_t *grav_on, const double *grav_dir);
+
+/* Lumped element loads of one load case as the solver uses them, host array [nE*12]
+ * (sum of UDL and self-weight parts, numpy_stiffness.py:401-430). */
+int cm_get_element_loads(cm_handle *h, int32_t lc, double *q);
+
+/* set_nodal_displacement_tol (numpy_stiffness.py:142-145). rot_tol is stored, unused. */
+int cm_set_tol(cm_handle *h, double trans_tol, double rot_tol);
+
+/* Output selection for cm_solve_many: device addresses, 0 = not wanted.
+ * B = subsets, L = load cases, nV/nE = nodes/elements. */
+typedef struct cm_solve_out {
+    uint64_t flag;        /* u8  [B*L]      success flag (numpy_stiffness.py:441)                 */
+    uint64_t status;      /* u8  [B*L]      CM_ST_*                                               */
+    uint64_t n_free;      /* i32 [B]                                                              */
+    uint64_t n_fixed;     /* i32 [B]                                                              */
+    uint64_t dof_map;     /* i32 [B*6nV]    the reference's id_map_RO (numpy_stiffness.py:193-208) */
+    uint64_t node_exists; /* u8  [B*nV]                                                           */
+    uint64_t U;           /* f64 [B*L*6nV]  nodal displacements, DOF order                        */
+    uint64_t Rf;          /* f64 [B*L*6nV]  fixity reactions at fixed DOFs, 0 elsewhere           */
+    uint64_t eR;          /* f64 [B*L*nE*12] element end forces, local axes; 0 rows when absent   */
+    uint64_t compliance;  /* f64 [B*L]                                                            */
+    uint64_t max_trans;   /* f64 [B*L]                                                            */
+    uint64_t max_rot;     /* f64 [B*L]                                                            */
+    uint64_t min_pivot;   /* f64 [B]        smallest LDL^T pivot of the scaled matrix             */
+} cm_solve_out;
+
+/* Factorisation kernel variant: 1 (default) = FP64 tensor-core MMA trailing updates,
+ * 0 = scalar validation variant of the same algorithm (slow; used by the parity tests to
+ * cross-check the MMA path). */
+int cm_set_variant(cm_handle *h, int32_t variant);
+
+/* Bytes of workspace needed to run `subsets_in_flight` subsets at once. cm_solve_many splits
+ * B into waves that fit the workspace it is given. */
+size_t cm_workspace_bytes(const cm_handle *h, int64_t subsets_in_flight);
+
+/* The hot path.  Replaces NumpyStiffness.solve (numpy_stiffness.py:228-397) for B element
+ * subsets at once.  masks_dev: u32 [B*mask_words], bit e%32 of word e/32 set = element e
+ * exists.  Everything is enqueued on `stream` (a cudaStream_t as integer, 0 = default
+ * stream); the call returns without synchronising. */
+int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *out,
+                  uint64_t workspace_dev, size_t workspace_bytes, uint64_t stream);
+
+/* Same, with HOST buffers: masks and every non-NULL output are host arrays (pinned or not).
+ * The call copies masks host->device, runs the kernels, copies the requested outputs back and
+ * returns when they are complete.  It manages its own device staging and workspace. */
+typedef struct cm_solve_out_host {
+    uint8_t *flag;
+    uint8_t *status;
+    int32_t *n_free;
+    int32_t *n_fixed;
+    int32_t *dof_map;
+    uint8_t *node_exists;
+    double *U;
+    double *Rf;
+    double *eR;
+    double *compliance;
+    double *max_trans;
+    double *max_rot;
+    double *min_pivot;
+} cm_solve_out_host;
+
+int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,
+                       const cm_solve_out_host *out);
+
+/* Counters since the last cm_reset_counters: kernels launched by this library, and device
+ * milliseconds (CUDA events on the launching stream) per stage of the last cm_solve_many*
+ * call when timing was enabled with cm_enable_timing(h, 1). stage: 0 dofmap+assembly,
+ * 1 factorisation(+forward), 2 back substitution + recovery. */
+int64_t cm_kernel_launches(const cm_handle *h);
+int cm_reset_counters(cm_handle *h);
+int cm_enable_timing(cm_handle *h, int32_t on);
+int cm_last_stage_ms(const cm_handle *h, double *ms /*[3]*/);
+
+/* Stand-alone element kernel for many elements (roofline measurement of the element kernel,
+ * SURVEY.md section 8d): device arrays, n elements; writes Kg [n*144], R3 [n*9]. */
+int cm_element_kernel_dev(uint64_t xyz_u /*[n*3]*/, uint64_t xyz_v /*[n*3]*/, uint64_t props /*[n*7]*/,
+                          uint64_t cr /*[n*6]*/, int64_t n, uint64_t Kg, uint64_t R3, uint64_t stream);
+
+const char *cm_last_error(void);
+const char *cm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONMECH_B200_H */
