@@ -66,6 +66,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     unsigned char *s_free = reinterpret_cast<unsigned char *>(s_mask + m.mask_words);   // [nV] free DOFs (0 if absent)
     unsigned char *s_exist = s_free + m.nV;                        // [nV]
     __shared__ int s_red[8];
+    __shared__ unsigned long long s_work;
     __shared__ double s_dred[K2_THREADS / 32];
 
     const int t = threadIdx.x, T = blockDim.x;
@@ -84,6 +85,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 
     for (int w = t; w < m.mask_words; w += T) s_mask[w] = gmask[w];
     if (t < 8) s_red[t] = 0;
+    if (t == 0) s_work = 0ull;
     __syncthreads();
 
     // ---- node existence, support status (numpy_stiffness.py:156-184)
@@ -115,6 +117,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     if (t == 0) {
         if (out.n_free) out.n_free[gs] = status == CM_ST_OK ? n_free : 0;
         if (out.n_fixed) out.n_fixed[gs] = status == CM_ST_OK ? n_fixed : 0;
+        if (out.profile_flops && status != CM_ST_OK) out.profile_flops[gs] = 0.0;
         info[CM_INFO_STATUS] = status;
         info[CM_INFO_NS] = status == CM_ST_OK ? n_free : 0;
         info[CM_INFO_NT] = status == CM_ST_OK ? (n_free + CM_TILE - 1) / CM_TILE : 0;
@@ -191,8 +194,12 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         int I0 = base / CM_TILE, I1 = (base + nf - 1) / CM_TILE;
         atomicMin(&s_kfirst[I0], cmin / CM_TILE);
         if (I1 != I0) atomicMin(&s_kfirst[I1], cmin / CM_TILE);
+        unsigned long long w = 0;      // algorithmic work: sum over rows of (row - first column)^2
+        for (int i = 0; i < nf; ++i) { unsigned long long hgt = (unsigned long long)(base + i - cmin); w += hgt * hgt; }
+        atomicAdd(&s_work, w);
     }
     __syncthreads();
+    if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
     for (int I = t; I < NT; I += T) kfirst_g[I] = s_kfirst[I];
 
     // ---- zero the tiles of the envelope (16-byte stores)

@@ -126,6 +126,8 @@ typedef struct cm_solve_out {
     uint64_t max_trans;   /* f64 [B*L]                                                            */
     uint64_t max_rot;     /* f64 [B*L]                                                            */
     uint64_t min_pivot;   /* f64 [B]        smallest LDL^T pivot of the scaled matrix             */
+    uint64_t profile_flops; /* f64 [B]      sum_j h_j^2 of the subset's K_mm envelope (algorithmic work  */
+                          /*                of the factorisation, one multiply-add counted as 2)  */
 } cm_solve_out;
 
 /* Factorisation kernel variant: 1 (default) = FP64 tensor-core MMA trailing updates,
@@ -161,6 +163,7 @@ typedef struct cm_solve_out_host {
     double *max_trans;
     double *max_rot;
     double *min_pivot;
+    double *profile_flops;
 } cm_solve_out_host;
 
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,

@@ -1,0 +1,319 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same inputs, and against the golden vectors frozen from the reference.
+
+Bar (BASELINE.json north_star): DOF maps, subset masks and success flags bit-exact; displacements
+and reactions within 1e-9 relative (inf-norm, translations/forces and rotations/moments
+separately)."""
+import random
+
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal, assert_almost_equal
+
+from golden_utils import Golden, golden_names, split_err, REL_TOL, MODELS
+from oracle.frame_oracle import FrameOracle, ST_OK, ST_ZERO_LOAD, ST_SINGULAR, ST_NO_SUPPORT
+
+pytestmark = pytest.mark.gpu
+
+ALL = ('flag', 'status', 'n_free', 'n_fixed', 'dof_map', 'node_exists', 'U', 'Rf', 'eR', 'compliance',
+       'max_trans', 'max_rot', 'min_pivot')
+WELL_POSED_PIVOT = 1e-8      # class W = reference min scaled pivot >= 1e-8
+
+
+def make_pair(model, loadcase, trans_tol=1e-3):
+    from conmech_b200 import StiffnessChecker
+    sc = StiffnessChecker(model, checker_engine='cuda')
+    sc.set_loads(loadcase)
+    sc.set_nodal_displacement_tol(trans_tol=trans_tol)
+    orc = FrameOracle(model)
+    orc.set_loads(loadcase)
+    orc.set_nodal_displacement_tol(trans_tol=trans_tol)
+    return sc, orc
+
+
+def check_against_oracle(eng, orc, subsets, r, lc=0, tag=''):
+    """Class W (well posed) -> exact flags/ints and 1e-9 values; class Z/M -> both False or counted."""
+    n_marginal = 0
+    for b, ids in enumerate(subsets):
+        o = orc.solve(ids)
+        ids2 = list(ids) or list(range(orc.nE))
+        st = int(r['status'][b, lc])
+        where = (tag, b)
+        if o.dof_map is not None:
+            assert int(r['n_free'][b]) == o.n_free, where
+            assert int(r['n_fixed'][b]) == o.n_fixed, where
+            assert_array_equal(r['dof_map'][b], o.dof_map, err_msg=str(where))
+        assert_array_equal(r['node_exists'][b].astype(bool), o.node_exists, err_msg=str(where))
+        if o.status in (ST_NO_SUPPORT, 2):
+            assert st == o.status and not r['flag'][b, lc], where
+            continue
+        if o.status == ST_ZERO_LOAD:
+            assert st == ST_ZERO_LOAD and bool(r['flag'][b, lc]) == o.success, where
+            assert not r['U'][b, lc].any()
+            continue
+        well_posed = o.status == ST_OK and o.min_pivot >= WELL_POSED_PIVOT
+        if not well_posed:
+            # singular / marginal in the reference: the flag must not claim success when the
+            # reference fails; values are rounding-dependent there
+            n_marginal += 1
+            if not o.success:
+                assert not r['flag'][b, lc], where
+            continue
+        assert st == ST_OK, (where, st, float(r['min_pivot'][b]))
+        assert bool(r['flag'][b, lc]) == o.success, (where, float(r['max_trans'][b, lc]), o.max_trans)
+        assert split_err(r['U'][b, lc], o.U) <= REL_TOL, where
+        assert split_err(r['Rf'][b, lc], o.R) <= REL_TOL, where
+        assert split_err(r['eR'][b, lc][ids2], o.eR[ids2]) <= REL_TOL, where
+        absent = np.setdiff1d(np.arange(orc.nE), ids2)
+        assert not r['eR'][b, lc][absent].any(), where
+        assert abs(r['max_trans'][b, lc] - o.max_trans) <= REL_TOL * o.max_trans, where
+        assert abs(r['compliance'][b, lc] - o.compliance) <= REL_TOL * abs(o.compliance), where
+    return n_marginal
+
+
+@pytest.mark.parametrize('variant', [1, 0], ids=['mma', 'scalar'])
+@pytest.mark.parametrize('name', golden_names())
+def test_golden_cases(name, variant):
+    g = Golden(name)
+    model = g.model()
+    sc, orc = make_pair(model, g.loadcase(model), g.meta['trans_tol'])
+    eng = sc._sc_ins
+    eng.set_factor_variant(variant)
+    subsets = [list(g.rec(i)['ids']) for i in range(g.n)]
+    r = eng.solve_many(subsets, want=ALL)
+    check_against_oracle(eng, orc, subsets, r, tag=name)
+    # and directly against the vectors frozen from the real reference
+    for b in range(g.n):
+        rec = g.rec(b)
+        assert bool(r['flag'][b, 0]) == bool(rec['flag']), (name, b)
+        if 'dof_map' in rec:
+            assert_array_equal(r['dof_map'][b], rec['dof_map'])
+        if 'U' in rec and np.isfinite(rec['U']).all() and np.abs(rec['U']).max() < 1e3 and 'joints__freeform' not in name:
+            assert split_err(r['U'][b, 0], rec['U']) <= REL_TOL, (name, b)
+            assert split_err(r['Rf'][b, 0], rec['R']) <= REL_TOL, (name, b)
+
+
+@pytest.mark.parametrize('name', ['tower_3D__self_weight', 'grid_5x5x5_joints__lc0', 'grid_4x3x4_diag__gravity',
+                                  'cantilever_beam_truss__loads', 'uniform_load_analytical_model__loads'])
+def test_element_tables(name):
+    """K1 against the oracle's element math and the reference's tables (<=1e-13)."""
+    g = Golden(name)
+    model = g.model()
+    sc, orc = make_pair(model, g.loadcase(model))
+    eng = sc._sc_ins
+    K = np.asarray(eng.get_element_stiffness_matrices())
+    R = np.asarray(eng.get_element_local2global_rot_matrices())
+    scale = np.abs(orc.K_G).max(axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(K - orc.K_G) / scale) <= 1e-13
+    assert np.max(np.abs(R - orc.R12)) <= 1e-15
+    assert_array_equal(eng.get_element2dof_id_map(), orc.id_map)
+    if g.extra('K_G') is not None:
+        assert np.max(np.abs(K - g.extra('K_G')) / scale) <= 1e-13
+    ids = list(range(orc.nE))
+    P = eng.get_lumped_nodal_loads(ids)
+    Po = orc.load_vector(ids)
+    assert np.max(np.abs(P - Po)) <= 1e-13 * max(1.0, np.abs(Po).max())
+
+
+def test_bfs_prefix_flags_config2():
+    """BASELINE config 2: every prefix of the construction sequence, tol 1e-3."""
+    for name, expect in (('tower_3D__bfs_prefixes', '000000000001110000000111'), ('topopt-100__bfs_prefixes', '1' * 132)):
+        g = Golden(name)
+        model = g.model()
+        sc, _ = make_pair(model, g.loadcase(model), 1e-3)
+        order = g.meta['order']
+        flags = sc.solve_many([order[:k] for k in range(1, len(order) + 1)])
+        assert ''.join('1' if f else '0' for f in flags) == expect
+        for b in range(g.n):
+            rec = g.rec(b)
+            assert flags[b] == bool(rec['flag'])
+
+
+def test_facade_solve_matches_reference_tests():
+    """The reference's own consistency test (tests/python/test_stiffness_checker.py:17-93): named
+    success / failure subsets, shuffled id order, dict results."""
+    from conmech_b200 import StiffnessChecker, LoadCase, GravityLoad
+    import os
+    path = os.path.join(MODELS, 'tower_3D.json')
+    sc = StiffnessChecker.from_json(path, checker_engine='cuda')
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    assert not sc.has_stored_result()
+    sc.set_nodal_displacement_tol(trans_tol=0.04)
+    ok_ids = [1, 12, 5, 10, 4, 11, 13, 3, 2, 0, 7]
+    for ids, expect in (([], True), (ok_ids, True), ([0, 4, 7, 8, 9], False)):
+        success = sc.solve(ids, eid_sanity_check=True)
+        assert success == expect
+        assert sc.has_stored_result()
+        s2, nD, fR, eR = sc.get_solved_results()
+        assert s2 == success
+        assert len(nD) == len(sc.get_element_connected_node_ids(existing_ids=ids))
+        assert len(eR) == (len(ids) or len(sc.elements))
+        for fn in sc.get_element_connected_node_ids(existing_ids=ids, fix_node_only=True):
+            assert_array_equal(nD[fn], np.zeros(6))
+        if expect:
+            assert sc.get_compliance() > 0.0
+        rng = random.Random(0)
+        for _ in range(5):
+            sh = list(ids)
+            rng.shuffle(sh)
+            assert sc.solve(sh) == success
+            _, nD2, fR2, eR2 = sc.get_solved_results()
+            for i in nD:
+                assert_almost_equal(nD[i], nD2[i])
+            for i in fR:
+                assert_almost_equal(fR[i], fR2[i])
+            for i in eR:
+                assert_almost_equal(eR[i][0], eR2[i][0])
+                assert_almost_equal(eR[i][1], eR2[i][1])
+    # no support in the subset -> False, no stored result (numpy_stiffness.py:238-240)
+    assert sc.solve([4, 5, 6, 7]) is False
+    assert not sc.has_stored_result()
+    assert_array_equal(sc.fix_element_ids, [0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14, 15])
+    with pytest.raises(ValueError):
+        sc._sc_ins.compute_dof_permutation([4, 5, 6, 7])
+    with pytest.raises(NotImplementedError):
+        StiffnessChecker.from_json(path, checker_engine='numpy')
+
+
+def test_equilibrium_invariants():
+    """Physics invariants the reference tests (test_stiffness_checker.py:191-365, 428-492):
+    K u = f + r, nodal equilibrium of element end forces, sum of vertical reactions = weight."""
+    g = Golden('topopt-100__self_weight+point_load')
+    model = g.model()
+    sc, orc = make_pair(model, g.loadcase(model))
+    eng = sc._sc_ins
+    ids = list(g.rec(1)['ids'])
+    r = eng.solve_many([ids], want=ALL)
+    U, R, E = r['U'][0, 0], r['Rf'][0, 0], r['eR'][0, 0]
+    K = eng.compute_full_stiffness_matrix(ids)
+    P = eng.get_lumped_nodal_loads(ids)
+    ex = np.repeat(r['node_exists'][0].astype(bool), 6)
+    assert np.max(np.abs(K.dot(U) - (P + R))[ex]) <= 1e-9 * np.abs(P).max()
+    # fR + load = - sum_e R^T eR  at every existing node
+    Rl = eng.get_element_local2global_rot_matrices()
+    acc = np.zeros_like(U)
+    for e in ids:
+        acc[eng.get_element2dof_id_map()[e]] += Rl[e].T.dot(E[e])
+    assert np.max(np.abs((R + P + acc)[ex])) <= 1e-8 * np.abs(P).max()
+    # gravity only: vertical reactions carry the weight
+    from conmech_b200 import LoadCase, GravityLoad
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    r = eng.solve_many([[]], want=('Rf', 'compliance'))
+    W = eng.get_gravity_nodal_loads([]).reshape(-1, 6)[:, 2].sum()
+    assert abs(r['Rf'][0, 0].reshape(-1, 6)[:, 2].sum() + W) <= 1e-9 * abs(W)
+    c1 = r['compliance'][0, 0]
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -2])))
+    c2 = eng.solve_many([[]], want=('compliance',))['compliance'][0, 0]
+    assert abs(c2 / c1 - 4.0) <= 1e-9            # compliance scales with g^2
+
+
+def test_edge_cases():
+    from conmech_b200 import StiffnessChecker, LoadCase, GravityLoad, PointLoad, pack_masks
+    g = Golden('tower_3D__self_weight')
+    model = g.model()
+    sc, orc = make_pair(model, LoadCase())          # no load at all
+    eng = sc._sc_ins
+    r = eng.solve_many([[], [0], [4, 5]], want=ALL)
+    assert list(r['status'][:, 0]) == [ST_ZERO_LOAD, ST_ZERO_LOAD, ST_NO_SUPPORT]
+    assert list(r['flag'][:, 0]) == [1, 1, 0]        # 0 < tol (numpy_stiffness.py:360-363)
+    assert not r['U'][0].any() and not r['Rf'][0].any()
+    # a load on a node that is absent from the subset still counts in ||P|| (Appendix B)
+    sc.set_loads(LoadCase(point_loads=[PointLoad([0, 0, -1.0], [0, 0, 0], 9)]))
+    orc.set_loads(LoadCase(point_loads=[PointLoad([0, 0, -1.0], [0, 0, 0], 9)]))
+    subsets = [[0], [0, 1, 2, 3], []]
+    r = eng.solve_many(subsets, want=ALL)
+    check_against_oracle(eng, orc, subsets, r, tag='absent-load')
+    assert r['status'][0, 0] == ST_OK and not r['U'][0, 0].any()
+    # masks given directly, duplicated ids collapse, out-of-range ids raise
+    m = pack_masks([[0, 0, 1, 2, 3]], len(model.elements))
+    r2 = eng.solve_many(m, want=('U',))
+    assert_array_equal(r2['U'][0], r['U'][1])
+    with pytest.raises(IndexError):
+        eng.solve_many([[99]])
+    # batch larger than one wave of the internal workspace still lines up
+    big = [subsets[b % 3] for b in range(300)]
+    rb = eng.solve_many(big, want=('max_trans',))
+    for b in range(300):
+        a, c = rb['max_trans'][b, 0], r['max_trans'][b % 3, 0]
+        assert a == c or (np.isnan(a) and np.isnan(c))
+
+
+def test_mechanism_detection():
+    """Exactly singular systems (zero diagonal after assembly, class Z of SURVEY Q16): pin-ended
+    members only -> rotational DOFs of free nodes have no stiffness; reference raises in SuperLU."""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(3, 3, 3)
+    for e in model.elements:
+        e.bending_stiff = False
+    sc, orc = make_pair(model, LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    r = sc._sc_ins.solve_many([[]], want=ALL)
+    o = orc.solve([])
+    assert o.status == ST_SINGULAR and not o.success
+    assert r['status'][0, 0] == ST_SINGULAR and not r['flag'][0, 0]
+    assert sc.solve([]) is False and not sc.has_stored_result()
+
+
+def test_config3_grid_batch():
+    """BASELINE config 3 shape: 1k-element grid, random connected subsets, vs the oracle; plus
+    run-to-run determinism (no atomics on floating-point data)."""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(7, 7, 8)
+    sc, orc = make_pair(model, LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    eng = sc._sc_ins
+    subsets = [syn.connected_subset(model, s) for s in range(1000, 1024)]
+    r = eng.solve_many(subsets, want=ALL)
+    check_against_oracle(eng, orc, subsets, r, tag='g1k')
+    r2 = eng.solve_many(subsets, want=ALL)
+    for k in ALL:
+        assert_array_equal(r[k], r2[k])
+
+
+def test_config3_full_size_properties():
+    """Full-size batch (4096 subsets of the 1k frame): properties that need no oracle -
+    vertical reactions balance the self weight of the existing elements, displacement at fixed
+    DOFs is zero, flags equal (max_trans < tol), device path == host path."""
+    import torch
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(7, 7, 8)
+    sc, orc = make_pair(model, LoadCase(gravity_load=GravityLoad([0, 0, -1])), trans_tol=5e-2)
+    eng = sc._sc_ins
+    B = 4096
+    subsets = [syn.connected_subset(model, s) for s in range(B)]
+    masks = syn.pack_masks(subsets, len(model.elements))
+    r = eng.solve_many(masks, want=('flag', 'status', 'U', 'Rf', 'max_trans', 'n_free'))
+    assert (r['status'] == ST_OK).all()
+    q = eng._element_loads(0)
+    for b in range(0, B, 64):
+        ids = subsets[b]
+        w = q[ids][:, [2, 8]].sum()
+        assert abs(r['Rf'][b, 0].reshape(-1, 6)[:, 2].sum() + w) <= 1e-9 * abs(w)
+    sup = np.array(list(model.supports.keys()))
+    assert not r['U'][:, 0].reshape(B, -1, 6)[:, sup].any()
+    assert_array_equal(r['flag'][:, 0].astype(bool), r['max_trans'][:, 0] < 5e-2)
+    assert 0 < r['flag'].sum() < B
+    dm = torch.from_numpy(masks.view(np.int32)).cuda()
+    rd = eng.solve_many_device(dm, want=('flag', 'max_trans', 'U'))
+    torch.cuda.synchronize()
+    assert_array_equal(rd['flag'].cpu().numpy(), r['flag'])
+    assert_array_equal(rd['max_trans'].cpu().numpy(), r['max_trans'])
+    assert_array_equal(rd['U'].cpu().numpy(), r['U'])
+
+
+def test_config4_multi_loadcase():
+    """BASELINE config 4: joints on horizontals, height-field subsets, four load cases solved
+    in ONE pass against the oracle solved once per (subset, load case)."""
+    from conmech_b200 import synthetic as syn, StiffnessChecker
+    dims = (5, 5, 5)
+    model = syn.grid_frame(*dims, joints=True)
+    lcs = syn.config4_loadcases(model)
+    sc = StiffnessChecker(model, checker_engine='cuda')
+    sc.set_load_cases(lcs)
+    eng = sc._sc_ins
+    subsets = [[]] + [syn.heightfield_subset(model, *dims, seed=s) for s in range(100, 112)]
+    r = eng.solve_many(subsets, want=ALL)
+    assert r['flag'].shape == (len(subsets), 4)
+    for li, lc in enumerate(lcs):
+        orc = FrameOracle(model)                    # fresh per load case (Q6)
+        orc.set_loads(lc)
+        n_m = check_against_oracle(eng, orc, subsets, r, lc=li, tag='cfg4-lc{}'.format(li))
+        assert n_m == 0

@@ -1,0 +1,117 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares, host logic (masks, model IO, synthetic workloads, subset sharding)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_loads_and_exports_header_symbols():
+    import __graft_entry__ as ge
+    ge.build()
+    from conmech_b200 import _capi
+    lib = _capi.load()
+    with open(os.path.join(REPO, 'include', 'conmech_b200.h')) as f:
+        header = f.read()
+    declared = set(re.findall(r'\b(cm_[a-z_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    assert declared == set(_capi.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b'sm_100a' in lib.cm_version()
+    # struct layouts the header promises
+    import ctypes as C
+    assert C.sizeof(_capi.SolveOut) == 14 * 8 and C.sizeof(_capi.SolveOutHost) == 14 * 8
+    assert C.sizeof(_capi.ModelDesc) == 16 + 6 * 8
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from conmech_b200 import StiffnessChecker, Model
+    from conmech_b200._capi import CmError
+    m = Model.from_json(os.path.join(REPO, 'tests', 'golden', 'models', 'tower_3D.json'))
+    with pytest.raises(CmError):
+        StiffnessChecker(m, checker_engine='cuda')
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(REPO, 'conmech_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(root, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_masks_roundtrip():
+    from conmech_b200 import pack_masks, ids_to_mask, mask_to_ids
+    rng = np.random.RandomState(0)
+    for nE in (1, 31, 32, 33, 931):
+        lists = [sorted(rng.choice(nE, size=rng.randint(1, nE + 1), replace=False).tolist()) for _ in range(7)]
+        m = pack_masks(lists, nE)
+        assert m.shape == (7, (nE + 31) // 32) and m.dtype == np.uint32
+        for b, ids in enumerate(lists):
+            assert_array_equal(mask_to_ids(m[b], nE), ids)
+            assert_array_equal(ids_to_mask(ids, nE), m[b])
+    full = pack_masks([[]], 40)
+    assert_array_equal(mask_to_ids(full[0], 40), np.arange(40))
+    with pytest.raises(IndexError):
+        pack_masks([[40]], 40)
+
+
+def test_model_io_roundtrip(models_dir):
+    from conmech_b200 import Model, LoadCase
+    for f in sorted(os.listdir(models_dir)):
+        if f.endswith('_loads.json') or f.endswith('_loadcase.json'):
+            lc = LoadCase.from_json(os.path.join(models_dir, f))
+            lc2 = LoadCase.from_data(json.loads(json.dumps(lc.to_data())))
+            assert len(lc2.point_loads) == len(lc.point_loads)
+            continue
+        m = Model.from_json(os.path.join(models_dir, f))
+        m2 = Model.from_data(json.loads(json.dumps(m.to_data())))
+        assert [n.point for n in m.nodes] == [n.point for n in m2.nodes]
+        assert [e.end_node_inds for e in m.elements] == [e.end_node_inds for e in m2.elements]
+        assert list(m.supports.keys()) == list(m2.supports.keys())
+        assert m.crosssec_id_from_etag == m2.crosssec_id_from_etag
+    mm = Model.from_json(os.path.join(models_dir, 'tower_3D.json'))
+    data = mm.to_data()
+    data['unit'] = 'millimeter'
+    scaled = Model.from_data(data)
+    assert np.allclose(np.array([n.point for n in scaled.nodes]) * 1e3, [n.point for n in mm.nodes])
+
+
+def test_synthetic_workloads_match_survey():
+    from conmech_b200 import synthetic as syn, Model
+    m = syn.grid_frame(7, 7, 8)
+    assert (len(m.nodes), len(m.elements), len(m.supports)) == (392, 931, 49)
+    assert len(syn.grid_frame(15, 15, 16).elements) == 9675
+    s0 = syn.connected_subset(m, 0)
+    assert s0 == syn.connected_subset(m, 0) and s0 == sorted(set(s0))
+    assert 0.19 * 931 <= len(s0) <= 0.91 * 931
+    fixed = set(m.supports)
+    seen, todo = set(), [e for e in s0 if set(m.elements[e].end_node_inds) & fixed]
+    inc = syn.node_incidence(m)
+    chosen = set(s0)
+    while todo:                               # connected to the ground by construction
+        e = todo.pop()
+        if e in seen:
+            continue
+        seen.add(e)
+        for v in m.elements[e].end_node_inds:
+            todo.extend(f for f in inc[v] if f in chosen and f not in seen)
+    assert seen == chosen
+    tower = Model.from_json(os.path.join(REPO, 'tests', 'golden', 'models', 'tower_3D.json'))
+    assert syn.bfs_sequence(tower) == [0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14, 15, 4, 7, 17, 22, 5, 19, 20, 6, 18, 21, 16, 23]
+    mj = syn.grid_frame(5, 5, 5, joints=True)
+    tags = {e.elem_tag for e in mj.elements}
+    assert tags == {'', 'hinge_a', 'spring', 'both'}
+    assert len(syn.config4_loadcases(mj)) == 4
+    hf = syn.heightfield_subset(mj, 5, 5, 5, seed=3)
+    assert hf == sorted(hf) and len(hf) > 0
