@@ -121,7 +121,7 @@ def run_reference(args):
         return
     from oracle import cpu_bench
     n_procs = os.cpu_count() or 1
-    per_step = args.cpu_sample or max(2 * n_procs, 32)
+    per_step = args.cpu_sample or 100 * n_procs                          # ~3 s per step
     import multiprocessing as mp
     ctx = mp.get_context('spawn')
     seeds_all = list(range((args.warmup + args.steps) * per_step))
@@ -163,7 +163,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_bench
         n_procs = os.cpu_count() or 1
-        n_sample = args.cpu_sample or max(4 * n_procs, 64)
+        n_sample = args.cpu_sample or min(args.batch, 400 * n_procs)      # ~10-15 s of CPU work
         rate, wall, _ = cpu_bench.time_oracle(GRID, range(n_sample), n_procs=n_procs, trans_tol=TRANS_TOL)
         rate1, wall1, _ = cpu_bench.time_oracle(GRID, range(min(n_sample, 48)), n_procs=1, trans_tol=TRANS_TOL)
         cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': n_procs, 'kind': 'port',
