@@ -29,7 +29,7 @@ struct cm_handle {
     // load tables
     double *d_q = nullptr, *d_pnodal = nullptr;
     double rot_tol = 0.0;
-    int variant = 1;                     // 1 = FP64 MMA factorisation, 0 = scalar validation variant
+    int variant = 2;                     // 2 = pipelined FP64 MMA (default), 1 = barrier MMA, 0 = scalar validation
     // counters / timing
     long long launches = 0;
     int timing = 0;
@@ -395,9 +395,17 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
     return (size_t)n * h->L.per_subset;
 }
 
-int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 1 FP64 MMA (default)
+int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 1 barrier MMA, 2 pipelined MMA (default)
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
     h->variant = variant;
+    return CM_OK;
+}
+
+int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (instrumented) counters
+    if (!h || !out16) return fail(CM_ERR_INVALID, "cm_debug_k3_phase_cycles: null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    CU(cm_factor_pipe_read_prof(reinterpret_cast<unsigned long long *>(out16)));
     return CM_OK;
 }
 
@@ -436,7 +444,10 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         if (h->timing) CU(cudaEventRecord(h->ev[0], st));
         CU(cm_launch_dofmap_assemble(h->m, h->L, ws, masks, first, count, od, st));
         if (h->timing) CU(cudaEventRecord(h->ev[1], st));
-        CU(cm_launch_factor(h->m, h->L, ws, count, h->variant, st));
+        if (h->variant >= 2 && cm_factor_pipe_supported(h->m))
+            CU(cm_launch_factor_pipe(h->m, h->L, ws, count, h->variant == 3 ? 1 : (h->variant == 4 ? 3 : 2), st));
+        else
+            CU(cm_launch_factor(h->m, h->L, ws, count, h->variant == 0 ? 0 : 1, st));
         if (h->timing) CU(cudaEventRecord(h->ev[2], st));
         CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
         h->launches += 3;

@@ -90,6 +90,10 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
                                       const cm_out_dev &out, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);
+bool cm_factor_pipe_supported(const cm_model_dev &m);
+cudaError_t cm_launch_factor_pipe(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+                                  int minb, cudaStream_t st);
+cudaError_t cm_factor_pipe_read_prof(unsigned long long *out16);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st);

@@ -235,7 +235,8 @@ class CudaStiffness(StiffnessBase):
         return (self._trans_tol, self._rot_tol)
 
     def set_factor_variant(self, variant):
-        """1 = FP64 tensor-core factorisation (default), 0 = scalar validation variant."""
+        """2 = pipelined FP64 tensor-core factorisation (default), 1 = block-barrier FP64 MMA kernel,
+        0 = scalar validation variant."""
         _capi.check(self._lib.cm_set_variant(self._handle, int(variant)))
 
     # ------------------------------------------------------------------ batched solves

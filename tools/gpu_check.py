@@ -20,7 +20,7 @@ ALL = ('flag', 'status', 'n_free', 'n_fixed', 'dof_map', 'node_exists', 'U', 'Rf
        'max_trans', 'max_rot', 'min_pivot')
 
 
-def compare(name, variants=(1, 0)):
+def compare(name, variants=(2, 3, 1)):
     g = Golden(name)
     model = g.model()
     lc = g.loadcase(model)
@@ -77,11 +77,11 @@ def timing():
     eng = sc._sc_ins
     print('G1k info', eng.info)
     t0 = time.time()
-    subsets = [syn.connected_subset(model, s) for s in range(1024)]
-    print('sampler: {:.2f} ms/subset'.format((time.time() - t0) / 1024 * 1e3))
+    subsets = [syn.connected_subset(model, s) for s in range(4096)]
+    print('sampler: {:.2f} ms/subset'.format((time.time() - t0) / 4096 * 1e3))
     masks = syn.pack_masks(subsets, len(model.elements))
     eng.enable_timing(True)
-    for var, nb in ((1, 1024), (0, 128)):
+    for var, nb in ((2, 1024), (3, 1024), (1, 1024), (2, 4096), (3, 4096), (1, 4096)):
         eng.set_factor_variant(var)
         for rep in range(2):
             t0 = time.time()

@@ -1,0 +1,38 @@
+"""Small driver for ncu captures: G1k frame, B subsets, one warm-up call and one measured call of
+the device path with the chosen factorisation variant."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from conmech_b200 import StiffnessChecker, LoadCase, GravityLoad, synthetic as syn      # noqa: E402
+
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+grid = tuple(int(x) for x in sys.argv[3].split('x')) if len(sys.argv) > 3 else (7, 7, 8)
+model = syn.grid_frame(*grid)
+sc = StiffnessChecker(model, checker_engine='cuda')
+sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+eng = sc._sc_ins
+eng.set_factor_variant(variant)
+masks = syn.pack_masks([syn.connected_subset(model, s) for s in range(B)], len(model.elements))
+dm = torch.from_numpy(masks.view(np.int32)).cuda()
+eng.enable_timing(True)
+for rep in range(2):
+    r = eng.solve_many_device(dm, want=('flag', 'status', 'max_trans', 'compliance', 'profile_flops'))
+    torch.cuda.synchronize()
+    ms = eng.last_stage_ms()
+fl = float(r['profile_flops'].sum().item())
+print('variant {} B={} stage ms {} | K3 {:.2f} TFLOP/s algorithmic'.format(variant, B, ms, fl / ms[1] / 1e9))
+if variant == 4:
+    import ctypes as C
+    out = np.zeros(16, dtype=np.uint64)
+    eng._lib.cm_debug_k3_phase_cycles(eng._handle, out.ctypes.data_as(C.c_void_p))      # clear warm-up counts? (both calls accumulate)
+    names = ['wait_operand', 'mma_update', 'transpose', 'wait_diag', 'trsm', 'store_publish', 'lookahead', 'diag_mma',
+             'ldlt', 'rhs_busy', 'rhs_wait', 'row_warp_total']
+    tot = float(out[11])
+    for n, v in zip(names, out[:12]):
+        print('  {:14s} {:14d} cycles  {:6.2f}% of row-warp time'.format(n, int(v), 100.0 * float(v) / tot))
