@@ -29,7 +29,7 @@ struct cm_handle {
     // load tables
     double *d_q = nullptr, *d_pnodal = nullptr;
     double rot_tol = 0.0;
-    int variant = 2;                     // 2 = pipelined FP64 MMA (default), 1 = barrier MMA, 0 = scalar validation
+    int variant = 2;                     // 2/3 = FP64 tensor-core kernel with 4/8-warp CTAs (2 default), 4/5 = same, instrumented, 0 = scalar validation
     // counters / timing
     long long launches = 0;
     int timing = 0;
@@ -329,6 +329,7 @@ static void make_layout(cm_handle *h) {
     L.off_x = o;      o = al(o + (size_t)n_lc * L.n_pad * sizeof(double));
     L.off_p = o;      o = al(o + (size_t)n_lc * 6 * m.nV * sizeof(double));
     L.off_kfirst = o; o = al(o + (size_t)m.n_tile_rows_max * sizeof(int));
+    L.off_minv = o;   o = al(o + (size_t)m.n_tile_rows_max * CM_TILE_ELEMS * sizeof(double));
     L.off_info = o;   o = al(o + CM_INFO_INTS * sizeof(int));
     L.per_subset = o;
 }
@@ -395,8 +396,9 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
     return (size_t)n * h->L.per_subset;
 }
 
-int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 1 barrier MMA, 2 pipelined MMA (default)
+int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
+    if (variant != 0 && (variant < 2 || variant > 5)) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0, 2, 3, 4 or 5");
     h->variant = variant;
     return CM_OK;
 }
@@ -405,7 +407,7 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
     if (!h || !out16) return fail(CM_ERR_INVALID, "cm_debug_k3_phase_cycles: null argument");
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
-    CU(cm_factor_pipe_read_prof(reinterpret_cast<unsigned long long *>(out16)));
+    CU(cm_factor_col_read_prof(reinterpret_cast<unsigned long long *>(out16)));
     return CM_OK;
 }
 
@@ -444,10 +446,10 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         if (h->timing) CU(cudaEventRecord(h->ev[0], st));
         CU(cm_launch_dofmap_assemble(h->m, h->L, ws, masks, first, count, od, st));
         if (h->timing) CU(cudaEventRecord(h->ev[1], st));
-        if (h->variant >= 2 && cm_factor_pipe_supported(h->m))
-            CU(cm_launch_factor_pipe(h->m, h->L, ws, count, h->variant == 3 ? 1 : (h->variant == 4 ? 3 : 2), st));
+        if (h->variant == 0)
+            CU(cm_launch_factor(h->m, h->L, ws, count, 0, st));
         else
-            CU(cm_launch_factor(h->m, h->L, ws, count, h->variant == 0 ? 0 : 1, st));
+            CU(cm_launch_factor_col(h->m, h->L, ws, count, (h->variant & 1) ? 8 : 4, h->variant >= 4 ? 1 : 0, st));
         if (h->timing) CU(cudaEventRecord(h->ev[2], st));
         CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
         h->launches += 3;

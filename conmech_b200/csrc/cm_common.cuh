@@ -22,11 +22,15 @@
 #define CM_INFO_ZERO_LOAD 4        // bit lc set: ||P_lc|| <= eps
 #define CM_INFO_JACOBI 5           // 1: Jacobi scaling applied, 0: identity (a |k_ii| <= eps)
 
-// Element (r,k) of a 32x32 tile.  Rows are contiguous (k fastest) and the eight 4-double groups
-// of a row are XOR-swizzled with the row index, so that the warp-wide 8-rows x 4-doubles
-// fragment reads of the FP64 MMA are bank-conflict free once a tile sits in shared memory.
+// Element (r,k) of a 32x32 tile, "fragment-major" order: [k/4][(r%8)*4 + k%4][r/8].
+// For the FP64 MMA m8n8k4 (lane = 4*g + t) the four A (or B) fragments of k-step ks that a lane
+// needs - rows g, 8+g, 16+g, 24+g at k = 4*ks + t - are the 4 consecutive doubles at
+// ks*128 + lane*4, so a warp fetches one k-step of an operand tile as one contiguous 1 KB run of
+// 32-byte vector loads; accumulator fragments (rows ri*8+g, columns cj*8 + 2t, 2t+1, ri = 0..3)
+// are 8 consecutive doubles per (lane, cj).  The same storage therefore serves as MMA operand
+// and as accumulator without any shared-memory transposition.
 __host__ __device__ __forceinline__ int cm_tile_off(int r, int k) {
-    return (r << 5) + ((((k >> 2) ^ (r & 7))) << 2) + (k & 3);
+    return ((k >> 2) << 7) + ((((r & 7) << 2) + (k & 3)) << 2) + (r >> 3);
 }
 
 // Model tables on the device (all sizes fixed at cm_create).
@@ -65,6 +69,7 @@ struct cm_ws_layout {
     size_t off_x;          // double [n_lc*n_pad] rhs -> forward solution -> solution
     size_t off_p;          // double [n_lc*6nV] full load vector, DOF order
     size_t off_kfirst;     // int    [n_tile_rows_max] first tile column in the envelope
+    size_t off_minv;       // double [n_tile_rows_max*1024] M_J = D_J^-1 L_JJ^-1 per diagonal tile (tile layout)
     size_t off_info;       // int    [CM_INFO_INTS]
     int n_pad;             // n_tile_rows_max*32
 };
@@ -90,10 +95,9 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
                                       const cm_out_dev &out, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);
-bool cm_factor_pipe_supported(const cm_model_dev &m);
-cudaError_t cm_launch_factor_pipe(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
-                                  int minb, cudaStream_t st);
-cudaError_t cm_factor_pipe_read_prof(unsigned long long *out16);
+cudaError_t cm_launch_factor_col(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+                                 int nwarps, int prof, cudaStream_t st);
+cudaError_t cm_factor_col_read_prof(unsigned long long *out16);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st);

@@ -1,0 +1,148 @@
+// Warp-level building blocks on 32x32 fp64 tiles in the fragment-major layout of cm_tile_off()
+// (cm_common.cuh), shared by the factorisation and substitution kernels.
+#pragma once
+#include "cm_common.cuh"
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragment ownership (lane = 4*g + t):
+//   a = A[g][t],  b = B[t][g],  c0,c1 = C[g][2t], C[g][2t+1].
+// (tcgen05 has no f64 kind; mma.sync m8n8k4 is the FP64 tensor path on sm_100a.)
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ const double *cm_tile_ptr(const double *tiles, int bt, int I, int K) {
+    return tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS;
+}
+__device__ __forceinline__ double *cm_tile_ptr(double *tiles, int bt, int I, int K) {
+    return tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS;
+}
+
+// 32-byte accesses as two 16-byte vector instructions; p must be 32-byte aligned.  (The single
+// 256-bit forms ld/st.global.v4.f64 exist on sm_100a, but ptxas 12.9 was seen to drop three of the
+// four components of such stores in one instantiation of the factorisation kernel, so they are
+// not used.)
+__device__ __forceinline__ void ldg4(double (&v)[4], const double *p) {
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg4(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
+    asm volatile("st.global.v2.f64 [%0+16], {%1,%2};" :: "l"(p), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void lds4(double (&v)[4], const double *p) {
+    const double2 x = reinterpret_cast<const double2 *>(p)[0];
+    const double2 y = reinterpret_cast<const double2 *>(p)[1];
+    v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+}
+
+// Accumulator fragments of one warp: a 32x32 tile as 4x4 MMA atoms; c[cj][e][ri] is the element
+// at row ri*8 + lane/4, column cj*8 + (lane%4)*2 + e.  In tile storage the 8 values of one cj are
+// the 8 consecutive doubles at cbase(lane) + cj*256.
+struct TileAcc { double c[4][2][4]; };
+
+__device__ __forceinline__ int acc_cbase(int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    return ((t >> 1) << 7) + (((g << 2) + ((t & 1) << 1)) << 2);
+}
+
+__device__ __forceinline__ void acc_zero(TileAcc &a) {
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) a.c[cj][e][ri] = 0.0;
+}
+
+__device__ __forceinline__ void acc_load(TileAcc &a, const double *T, int lane) {
+    const double *p = T + acc_cbase(lane);
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        ldg4(a.c[cj][0], p + cj * 256);
+        ldg4(a.c[cj][1], p + cj * 256 + 4);
+    }
+}
+
+__device__ __forceinline__ void acc_store(const TileAcc &a, double *T, int lane) {
+    double *p = T + acc_cbase(lane);
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        stg4(p + cj * 256, a.c[cj][0][0], a.c[cj][0][1], a.c[cj][0][2], a.c[cj][0][3]);
+        stg4(p + cj * 256 + 4, a.c[cj][1][0], a.c[cj][1][1], a.c[cj][1][2], a.c[cj][1][3]);
+    }
+}
+
+// 16 (or, LOWER: the 10 on and below the block diagonal) MMAs of one k-step
+template <bool LOWER>
+__device__ __forceinline__ void frag_mma(TileAcc &acc, const double (&a)[4], const double (&b)[4]) {
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+        for (int cj = 0; cj < 4; ++cj)
+            if (!LOWER || cj <= ri) dmma_m8n8k4(acc.c[cj][0][ri], acc.c[cj][1][ri], a[ri], b[cj]);
+}
+
+// acc -= sum over nsteps k-steps (4 columns each) of  A[:, k] * d[k] * B[:, k]^T, where the operand
+// tiles of consecutive block columns are contiguous in memory (one tile row of the block band), so
+// the whole sum is one linear stream: A and B advance 128 doubles per k-step, d advances 4.
+// nsteps is a multiple of 8.  Software pipelined by hand: the fragments of step q+1 are in flight
+// while the MMAs of step q issue.  SYRK: A == B (diagonal tile; only the lower atoms are computed).
+template <bool SYRK>
+__device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__restrict__ A,
+                                                  const double *__restrict__ B, const double *__restrict__ d,
+                                                  int nsteps, int lane) {
+    const double *pa = A + lane * 4;
+    const double *pb = B + lane * 4;
+    const double *pd = d + (lane & 3);
+    double a0[4], b0[4], a1[4], b1[4], d0, d1;
+    ldg4(a0, pa);
+    if (!SYRK) ldg4(b0, pb);
+    d0 = pd[0];
+    for (int q = 0; q < nsteps; q += 2) {
+        ldg4(a1, pa + 128);
+        if (!SYRK) ldg4(b1, pb + 128);
+        d1 = pd[4];
+        {
+            const double nd = -d0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b0[i] = (SYRK ? a0[i] : b0[i]) * nd;
+            frag_mma<SYRK>(acc, a0, b0);
+        }
+        pa += 256; pb += 256; pd += 8;
+        if (q + 2 < nsteps) {
+            ldg4(a0, pa);
+            if (!SYRK) ldg4(b0, pb);
+            d0 = pd[0];
+        }
+        {
+            const double nd = -d1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b1[i] = (SYRK ? a1[i] : b1[i]) * nd;
+            frag_mma<SYRK>(acc, a1, b1);
+        }
+    }
+}
+
+// acc = A * Ms^T for one 32x32 tile A in global memory and Ms in shared memory, both in tile
+// layout (used as L(I,J) = acc(I,J) * (D_J^-1 L_JJ^-1)^T, the triangular solve as a product).
+__device__ __forceinline__ void acc_mul_smem(TileAcc &acc, const double *__restrict__ A,
+                                             const double *__restrict__ Ms, int lane) {
+    const double *pa = A + lane * 4;
+    const double *pb = Ms + lane * 4;
+    double a0[4], b0[4], a1[4], b1[4];
+    ldg4(a0, pa);
+    lds4(b0, pb);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+        ldg4(a1, pa + 128);
+        lds4(b1, pb + 128);
+        frag_mma<false>(acc, a0, b0);
+        pa += 256; pb += 256;
+        if (q + 2 < 8) {
+            ldg4(a0, pa);
+            lds4(b0, pb);
+        }
+        frag_mma<false>(acc, a1, b1);
+    }
+}

@@ -5,7 +5,7 @@
 // Reference: numpy_stiffness.py:353-359 (solve, unscale, compliance), :366-372 (reactions),
 // :386-391 (element reactions, sign flipped: quirk Q4), :438-441 / :457-464 (criterion:
 // max_v ||u_v[0:3]||_2 < trans_tol, strict, NaN -> False).  One CTA per subset.
-#include "cm_common.cuh"
+#include "cm_frag.cuh"
 
 namespace {
 
@@ -15,8 +15,22 @@ constexpr int K4_WARPS = K4_THREADS / 32;
 __device__ __forceinline__ double thr(double k) { return (fabs(k) > CM_EPS) ? k : 0.0; }
 __device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (mask[e >> 5] >> (e & 31)) & 1u; }
 
-__device__ __forceinline__ const double *tile_ptr(const double *tiles, int bt, int I, int K) {
-    return tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS;
+// colsum[ks] (valid on lanes 0..3, column 4*ks + lane) = sum_r T[r][4*ks + lane] * w[r] for a tile in
+// fragment-major layout; w4 holds w[i*8 + lane/4], i = 0..3.  One 32-byte load per lane and k-step.
+__device__ __forceinline__ void tile_tmatvec(const double *__restrict__ T, const double (&w4)[4], double (&cs)[8], int lane) {
+    const double *p = T + lane * 4;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v[4];
+        ldg4(v, p + q * 128);
+        cs[q] = v[0] * w4[0] + v[1] * w4[1] + v[2] * w4[2] + v[3] * w4[3];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 4);
+        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
+        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
+    }
 }
 
 // NaN-propagating max (np.max semantics)
@@ -51,7 +65,6 @@ __device__ double block_nanmax(double v, double *s_red) {
 __global__ void __launch_bounds__(K4_THREADS)
 k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
                  cm_out_dev out) {
-    __shared__ double s_part[K4_WARPS][32];
     __shared__ double s_red[K4_WARPS];
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -65,6 +78,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
     const int *sidx = reinterpret_cast<const int *>(slab + L.off_sidx);
     const double *dinv = reinterpret_cast<const double *>(slab + L.off_dinv);
     const double *dpiv = reinterpret_cast<const double *>(slab + L.off_dpiv);
+    const double *minv = reinterpret_cast<const double *>(slab + L.off_minv);
     double *X = reinterpret_cast<double *>(slab + L.off_x);
     const double *P = reinterpret_cast<const double *>(slab + L.off_p);
     const uint32_t *mask = masks + (size_t)gs * m.mask_words;
@@ -102,33 +116,62 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             for (int r = t; r < NT * CM_TILE; r += K4_THREADS) Xl[r] = 0.0;
             __syncthreads();
         } else {
-            // ---- back substitution L^T x = D^-1 y, block column by block column from the end
-            for (int J = NT - 1; J >= 0; --J) {
-                const int Iend = min(J + bt - 1, NT - 1);
-                double part = 0.0;
-                for (int I = J + 1 + warp; I <= Iend; I += K4_WARPS) {
-                    if (kfirst[I] > J) continue;
-                    const double *Lij = tile_ptr(tiles, bt, I, J);
-                    const double *xI = Xl + I * CM_TILE;
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) part += Lij[cm_tile_off(r, lane)] * xI[r];
-                }
-                s_part[warp][lane] = part;
-                __syncthreads();
-                if (warp == 0) {
-                    double s = Xl[J * CM_TILE + lane] / dpiv[J * CM_TILE + lane];
+            // ---- back substitution L^T x = D^-1 y, row-oriented: once x_I is known every tile
+            // (I,J) of block row I (contiguous in memory) subtracts L(I,J)^T x_I from the pending
+            // sum of block J; the warp that owns tile (I,I-1) then finishes x_{I-1} =
+            // M^T (d .* s) with M = D^-1 L_JJ^-1 left by the factorisation.  One barrier per row.
+            for (int r = t; r < NT * CM_TILE; r += K4_THREADS) Xl[r] = Xl[r] / dpiv[r];
+            __syncthreads();
+            const int g = lane >> 2;
+            if (warp == 0) {
+                const int I = NT - 1;
+                double w4[4], cs[8];
 #pragma unroll
-                    for (int w = 0; w < K4_WARPS; ++w) s -= s_part[w][lane];
-                    const double *Ljj = tile_ptr(tiles, bt, J, J);
+                for (int i = 0; i < 4; ++i) w4[i] = dpiv[I * CM_TILE + i * 8 + g] * Xl[I * CM_TILE + i * 8 + g];
+                tile_tmatvec(minv + (size_t)I * CM_TILE_ELEMS, w4, cs, lane);
+                __syncwarp();
+                if (lane < 4)
 #pragma unroll
-                    for (int c = 31; c > 0; --c) {
-                        const double xc = __shfl_sync(0xffffffffu, s, c);
-                        if (lane < c) s -= Ljj[cm_tile_off(c, lane)] * xc;
-                    }
-                    Xl[J * CM_TILE + lane] = s;
-                }
-                __syncthreads();
+                    for (int q = 0; q < 8; ++q) Xl[I * CM_TILE + q * 4 + lane] = cs[q];
             }
+            for (int I = NT - 1; I > 0; --I) {
+                __syncthreads();
+                const int kf = kfirst[I];
+                double x4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x4[i] = Xl[I * CM_TILE + i * 8 + g];
+                for (int J = I - 1 - warp; J >= kf; J -= K4_WARPS) {
+                    double cs[8];
+                    tile_tmatvec(cm_tile_ptr(tiles, bt, I, J), x4, cs, lane);
+                    if (lane < 4)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + q * 4 + lane] -= cs[q];
+                    if (J == I - 1) {
+                        __syncwarp();
+                        double w4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) w4[i] = dpiv[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
+                        tile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
+                        __syncwarp();
+                        if (lane < 4)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + q * 4 + lane] = cs[q];
+                    }
+                }
+                if (kf > I - 1 && warp == 0) {
+                    // row I has no tile left of the diagonal: block I-1 is complete without it
+                    const int J = I - 1;
+                    double w4[4], cs[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w4[i] = dpiv[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
+                    tile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
+                    __syncwarp();
+                    if (lane < 4)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + q * 4 + lane] = cs[q];
+                }
+            }
+            __syncthreads();
         }
 
         // ---- displacements in DOF order (U = D x on free DOFs, 0 elsewhere), compliance

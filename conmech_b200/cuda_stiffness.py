@@ -235,7 +235,7 @@ class CudaStiffness(StiffnessBase):
         return (self._trans_tol, self._rot_tol)
 
     def set_factor_variant(self, variant):
-        """2 = pipelined FP64 tensor-core factorisation (default), 1 = block-barrier FP64 MMA kernel,
+        """2 = FP64 tensor-core factorisation (default), 4 = the same kernel with phase cycle counters,
         0 = scalar validation variant."""
         _capi.check(self._lib.cm_set_variant(self._handle, int(variant)))
 

@@ -130,15 +130,14 @@ typedef struct cm_solve_out {
                           /*                of the factorisation, one multiply-add counted as 2)  */
 } cm_solve_out;
 
-/* Factorisation kernel variant: 2 (default) = pipelined FP64 tensor-core MMA kernel (row-owner
- * warps, flag synchronised; used when the band fits its shared-memory ring, else 1),
- * 1 = block-column FP64 MMA kernel with block barriers, 0 = scalar validation variant of the
- * same algorithm (slow; used by the parity tests to cross-check the MMA paths). */
+/* Factorisation kernel variant: 2 (default) = FP64 tensor-core block-band LDL^T
+ * (csrc/k3_factor_col.cu) with 4-warp CTAs, 3 = the same with 8-warp CTAs, 4 / 5 = those two
+ * instrumented with per-phase cycle counters, 0 = scalar validation variant of the same
+ * algorithm (slow; used by the parity tests to cross-check the tensor-core path). */
 int cm_set_variant(cm_handle *h, int32_t variant);
 
-/* Development aid: variant 4 runs an instrumented build of the pipelined factorisation that
- * accumulates clock64() cycles per phase over all row warps; this reads and clears the 16
- * counters (slot meanings in csrc/k3_factor_pipe.cu). */
+/* Development aid: after a solve with variant 4 or 5, reads and clears the 16 phase counters
+ * (clock64 cycles summed over CTAs; slot meanings in csrc/k3_factor_col.cu). */
 int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16);
 
 /* Bytes of workspace needed to run `subsets_in_flight` subsets at once. cm_solve_many splits
