@@ -294,7 +294,7 @@ def main():
     k3_ms_per_launch = stage_ms[1] / n_waves
     flops_per_launch = flops_batch * (min(B, wave) / B)
     achieved = flops_per_launch / (k3_ms_per_launch * 1e-3) / 1e12
-    roofline = {'kernel': 'k3_factor (block-band LDL^T, FP64 mma.sync m8n8k4)', 'bound': 'tensor',
+    roofline = {'kernel': 'k3_factor_flow (block-band LDL^T, FP64 DMMA m8n8k4, dataflow rows)', 'bound': 'tensor',
                 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
                 'traffic': None,
                 'peak_source': 'cuBLAS DGEMM 8192^3 fp64 measured live in this run (MEASURED_PEAKS.json has no '

@@ -23,7 +23,7 @@ SOURCES = [
     ('k1_element.cu', ['-fmad=false']),
     ('k2_dofmap_assemble.cu', []),
     ('k3_factor.cu', []),
-    ('k3_factor_col.cu', []),
+    ('k3_factor_flow.cu', []),
     ('k4_solve_recover.cu', []),
 ]
 

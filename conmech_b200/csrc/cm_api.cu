@@ -29,7 +29,7 @@ struct cm_handle {
     // load tables
     double *d_q = nullptr, *d_pnodal = nullptr;
     double rot_tol = 0.0;
-    int variant = 2;                     // 2/3 = FP64 tensor-core kernel with 4/8-warp CTAs (2 default), 4/5 = same, instrumented, 0 = scalar validation
+    int variant = 2;                     // 2/3 = FP64 tensor-core dataflow kernel with 4/8-warp CTAs (2 default), 4/5 = same, instrumented, 0 = scalar validation
     // counters / timing
     long long launches = 0;
     int timing = 0;
@@ -407,7 +407,7 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
     if (!h || !out16) return fail(CM_ERR_INVALID, "cm_debug_k3_phase_cycles: null argument");
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
-    CU(cm_factor_col_read_prof(reinterpret_cast<unsigned long long *>(out16)));
+    CU(cm_factor_flow_read_prof(reinterpret_cast<unsigned long long *>(out16)));
     return CM_OK;
 }
 
@@ -449,7 +449,7 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         if (h->variant == 0)
             CU(cm_launch_factor(h->m, h->L, ws, count, 0, st));
         else
-            CU(cm_launch_factor_col(h->m, h->L, ws, count, (h->variant & 1) ? 8 : 4, h->variant >= 4 ? 1 : 0, st));
+            CU(cm_launch_factor_flow(h->m, h->L, ws, count, (h->variant & 1) ? 8 : 4, h->variant >= 4 ? 1 : 0, st));
         if (h->timing) CU(cudaEventRecord(h->ev[2], st));
         CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
         h->launches += 3;

@@ -95,9 +95,9 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
                                       const cm_out_dev &out, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);
-cudaError_t cm_launch_factor_col(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
-                                 int nwarps, int prof, cudaStream_t st);
-cudaError_t cm_factor_col_read_prof(unsigned long long *out16);
+cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+                                  int nwarps, int prof, cudaStream_t st);
+cudaError_t cm_factor_flow_read_prof(unsigned long long *out16);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st);

@@ -1,4 +1,4 @@
-// K3, scalar validation variant - the same block-band LDL^T as k3_factor_col.cu (pivot rules,
+// K3, scalar validation variant - the same block-band LDL^T as k3_factor_flow.cu (pivot rules,
 // forward substitution, M_J = D_J^-1 L_JJ^-1 output) with plain FP64 FMAs, true triangular solves
 // and element-wise tile accesses.  Slow on purpose; the parity tests use it to cross-check the
 // tensor-core kernel (cm_set_variant(h, 0)).

@@ -1,0 +1,429 @@
+// K3 (default) - batched fp64 LDL^T of the Jacobi-scaled K_mm in block-band tile storage on the
+// FP64 tensor cores, with pivot-based mechanism detection and the forward substitution fused in.
+//
+// Replaces the reference's SuperLU factorisation + definiteness test + first triangular solve
+// (numpy_stiffness.py:299-336, :353).  The reference factors with diagonal pivots only
+// (diag_pivot_thresh=0, SymmetricMode), raises on an exactly zero pivot (:301-319) and rejects any
+// pivot <= -1e-14 (:326-336); the same rules are applied here to the pivots d_j of the LDL^T.
+// Off-diagonal tiles are solved as a product with M_J = D_J^-1 L_JJ^-1 (one more tensor-core tile
+// product instead of a scalar triangular solve).  Tiles are stored fragment-major (cm_tile_off), so
+// accumulators and operands move with vector loads/stores straight between global memory (L1/L2
+// resident window) and MMA registers.  No block-wide barrier on the hot loop:
+//
+// One CTA per subset, NW "row" warps.  Warp w owns tile rows I = w, w+NW, ... and walks each row
+// left to right: tile (I,J) accumulates A(I,J) - sum_K L(I,K) D_K L(J,K)^T as one linear operand
+// stream, is solved against M_J, and the row ends with its diagonal tile (SYRK stream, LDL^T,
+// inverse) and the forward substitution of the row.  The only synchronisation is one progress
+// counter per tile row in shared memory: prog[J] = number of finished tile columns of row J
+// (J+1 once its diagonal factor and M_J are published).  Term K of tile (I,J) may run once
+// prog[J] > K; the solve once prog[J] == J+1.  Rows therefore advance as a staggered wavefront, the
+// serial diagonal factorisations of consecutive rows overlap with the other rows' tensor-core work,
+// and every warp always has a long stream of independent MMAs queued.  The critical path per row
+// is  M_{I-1} -> solve of tile (I,I-1) -> newest SYRK term -> LDL^T + inverse of tile (I,I);  all
+// older terms of those two tiles are accumulated before the warp starts waiting (look-ahead).
+#include "cm_frag.cuh"
+#include <cstdlib>
+
+namespace {
+
+constexpr int DS = 34;                          // row stride of the diagonal scratch matrices (doubles)
+constexpr int DSCR = 2 * 32 * DS + 2 * 32;      // CTA scratch of the diagonal factorisation: two 32x32
+                                                // matrices, a column, the reciprocal pivots.  One copy
+                                                // per CTA: the diagonal factorisations of a subset form
+                                                // a dependency chain, so only one is ever in progress.
+
+// instrumented build: cycles per activity, summed over all row warps (slots: 0 wait for an update
+// operand, 1 update streams, 2 wait for M_J, 3 solve product, 4 diagonal-tile updates, 5 wait for the
+// previous diagonal factor, 6 diagonal factor, 7 wait for the forward chain, 8 forward substitution,
+// 9 total)
+__device__ unsigned long long g_flow_prof[16];
+#define FP_T0(pc) long long _t0 = (pc) ? clock64() : 0
+#define FP_ADD(pc, slot) do { if (pc) { long long _n = clock64(); if ((threadIdx.x & 31) == 0) (pc)[slot] += _n - _t0; _t0 = _n; } } while (0)
+
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);      // seed: relative error <= 2^-23
+    x = fma(x, e, x);                // 2^-46
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);             // below one ulp
+}
+
+__device__ __forceinline__ int wait_prog_gt(volatile int *prog, int J, int K) {
+    int p = prog[J];
+    while (p <= K) { __nanosleep(40); p = prog[J]; }
+    __threadfence_block();
+    return p;
+}
+
+__device__ __forceinline__ double dneg(double x) {       // sign flip on the integer pipe
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+
+// Blocked LDL^T of the lower triangle of tile T (global, tile layout) by one warp, then
+// M = D^-1 L^-1, written to Mg (global, tile layout); pivots to dg.  8-column panels are eliminated
+// with one matrix row per lane (the pivot column travels through shared memory); the trailing
+// update and the block-wise inverse (X = L^-1: X_ii by substitution, X_ij = -X_ii sum_k L_ik X_kj)
+// run as 8x8x4 FP64 MMAs on fragments read from the shared scratch matrices.  The serial chain is
+// 32 pivots of ~100 cycles plus a dozen short MMA stages, and the warp issues ~4x fewer FP64
+// instructions than an unblocked elimination - this routine is the critical path of every tile row.
+// A pivot that violates the reference's rules (exact zero raises in SuperLU: numpy_stiffness.py:
+// 301-319; <= -1e-14 is rejected: :326-336; NaN fails both) sets *s_fail and is replaced by 1.
+__device__ __noinline__ void diag_factor_blk(const double *T, double *Mg, double *dg, double *scr, int lane,
+                                             int *s_fail, double *s_minpiv_w) {
+    double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v[4];
+        ldg4(v, T + q * 128 + lane * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sA[(8 * i + g) * DS + 4 * q + t] = v[i];
+    }
+    __syncwarp();
+    int fail = 0;
+    double minpiv = *s_minpiv_w;
+    double dmine = 1.0, rmine = 1.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 8 * b;
+        double p[8], pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(sA + lane * DS + c0 + k);
+            p[k] = v.x; p[k + 1] = v.y;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            s_col[lane] = p[c];
+            __syncwarp();
+            double d = s_col[c0 + c];
+            if (!(d > -CM_EPS) || d == 0.0) { fail = 1; d = 1.0; }
+            minpiv = fmin(minpiv, d);
+            const double rinv = fast_rcp(d);
+            if (lane == c0 + c) { dmine = d; rmine = rinv; }
+            pk[c] = p[c];                        // (L D)[lane][c0+c]
+            const double l = p[c] * rinv;        // L[lane][c0+c] for lane > c0+c (unused otherwise)
+            p[c] = l;
+#pragma unroll
+            for (int k = c + 1; k < 8; ++k) p[k] -= l * s_col[c0 + k];
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            *reinterpret_cast<double2 *>(sA + lane * DS + c0 + k) = make_double2(p[k], p[k + 1]);
+            *reinterpret_cast<double2 *>(sB + lane * DS + c0 + k) = make_double2(pk[k], pk[k + 1]);
+        }
+        __syncwarp();
+        if (b < 3) {
+            // trailing blocks (ri,cj), b < cj <= ri:  A -= (L D)(ri,b) L(cj,b)^T
+#pragma unroll
+            for (int ri = b + 1; ri < 4; ++ri)
+#pragma unroll
+                for (int cj = b + 1; cj <= ri; ++cj) {
+                    double2 cc = *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t);
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2)
+                        dmma_m8n8k4(cc.x, cc.y, dneg(sB[(8 * ri + g) * DS + c0 + 4 * s2 + t]),
+                                    sA[(8 * cj + g) * DS + c0 + 4 * s2 + t]);
+                    *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t) = cc;
+                }
+            __syncwarp();
+        }
+    }
+    dg[lane] = dmine;
+    s_rinv[lane] = rmine;
+    if (lane == 0) { *s_minpiv_w = minpiv; if (fail) *s_fail = 1; }
+    // ---- X = L^-1.  Diagonal blocks: lane 8*bb + j owns column j of X_bb (substitution on e_j)
+    {
+        const int bb = lane >> 3, j = lane & 7;
+        const double *Lb = sA + (8 * bb) * DS + 8 * bb;
+        double x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r) x[r] -= Lb[r * DS + c] * x[c];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sB[(8 * bb + r) * DS + 8 * bb + j] = x[r];
+    }
+    __syncwarp();
+    // off-diagonal blocks by distance d from the diagonal: T_ij = sum_{k=j}^{i-1} L_ik X_kj is parked in
+    // the unused upper block (j,i) of sA, then X_ij = -X_ii T_ij
+#pragma unroll
+    for (int d = 1; d < 4; ++d) {
+#pragma unroll
+        for (int i = d; i < 4; ++i) {
+            const int j = i - d;
+            double c0v = 0.0, c1v = 0.0;
+#pragma unroll
+            for (int k = j; k < i; ++k)
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2)
+                    dmma_m8n8k4(c0v, c1v, sA[(8 * i + g) * DS + 8 * k + 4 * s2 + t],
+                                sB[(8 * k + 4 * s2 + t) * DS + 8 * j + g]);
+            *reinterpret_cast<double2 *>(sA + (8 * j + g) * DS + 8 * i + 2 * t) = make_double2(c0v, c1v);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = d; i < 4; ++i) {
+            const int j = i - d;
+            double c0v = 0.0, c1v = 0.0;
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+                dmma_m8n8k4(c0v, c1v, dneg(sB[(8 * i + g) * DS + 8 * i + 4 * s2 + t]),
+                            sA[(8 * j + 4 * s2 + t) * DS + 8 * i + g]);
+            *reinterpret_cast<double2 *>(sB + (8 * i + g) * DS + 8 * j + 2 * t) = make_double2(c0v, c1v);
+        }
+        __syncwarp();
+    }
+    // ---- M = D^-1 X to global memory, tile layout (blocks above the diagonal are zero)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            v[i] = ((q >> 1) <= i) ? sB[(8 * i + g) * DS + 4 * q + t] * s_rinv[8 * i + g] : 0.0;
+        stg4(Mg + q * 128 + lane * 4, v[0], v[1], v[2], v[3]);
+    }
+    __syncwarp();
+}
+
+// acc = A * M^T for 32x32 tiles A and M in global memory, tile layout
+__device__ __forceinline__ void acc_mul_glob(TileAcc &acc, const double *__restrict__ A,
+                                             const double *__restrict__ M, int lane) {
+    const double *pa = A + lane * 4;
+    const double *pb = M + lane * 4;
+    double a0[4], b0[4], a1[4], b1[4];
+    ldg4(a0, pa);
+    ldg4(b0, pb);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+        ldg4(a1, pa + 128);
+        ldg4(b1, pb + 128);
+        frag_mma<false>(acc, a0, b0);
+        pa += 256; pb += 256;
+        if (q + 2 < 8) {
+            ldg4(a0, pa);
+            ldg4(b0, pb);
+        }
+        frag_mma<false>(acc, a1, b1);
+    }
+}
+
+// tile (I,J), J < I: all update terms as they become available, then the solve against M_J
+__device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, const double *dpiv, const int *kfirst,
+                                          volatile int *prog, int bt, int I, int J, int kfI, int lane,
+                                          long long *pc) {
+    double *T = cm_tile_ptr(tiles, bt, I, J);
+    int K = max(kfI, kfirst[J]);
+    FP_T0(pc);
+    if (K < J) {
+        TileAcc acc;
+        acc_load(acc, T, lane);
+        while (K < J) {
+            const int Kend = min(wait_prog_gt(prog, J, K), J);
+            FP_ADD(pc, 0);
+            acc_update_stream<false>(acc, cm_tile_ptr(tiles, bt, I, K), cm_tile_ptr(tiles, bt, J, K),
+                                     dpiv + K * CM_TILE, (Kend - K) * 8, lane);
+            K = Kend;
+            FP_ADD(pc, 1);
+        }
+        acc_store(acc, T, lane);
+        __syncwarp();
+        FP_ADD(pc, 1);
+    }
+    wait_prog_gt(prog, J, J);                     // M_J published
+    FP_ADD(pc, 2);
+    TileAcc r;
+    acc_zero(r);
+    acc_mul_glob(r, T, minv + (size_t)J * CM_TILE_ELEMS, lane);
+    acc_store(r, T, lane);
+    FP_ADD(pc, 3);
+}
+
+// diagonal tile (I,I) -= sum_{K in [K0,K1)} L(I,K) D_K L(I,K)^T  (own row, already final)
+__device__ __noinline__ void diag_update(double *tiles, const double *dpiv, int bt, int I, int K0, int K1, int lane) {
+    double *T = cm_tile_ptr(tiles, bt, I, I);
+    TileAcc acc;
+    acc_load(acc, T, lane);
+    acc_update_stream<true>(acc, cm_tile_ptr(tiles, bt, I, K0), nullptr, dpiv + K0 * CM_TILE, (K1 - K0) * 8, lane);
+    acc_store(acc, T, lane);
+}
+
+// forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - sum_K L(J,K) y_K)
+__device__ __noinline__ void forward_row_w(const double *tiles, const double *minv, const double *dpiv, double *X,
+                                           double *s_r, int n_pad, int n_lc, int zero_bits, int bt, int J, int kfJ,
+                                           int lane) {
+    const int g = lane >> 2, tt = lane & 3;
+    const double *Mj = minv + (size_t)J * CM_TILE_ELEMS + lane * 4;
+    for (int lc = 0; lc < n_lc; ++lc) {
+        if ((zero_bits >> lc) & 1) continue;
+        double *Xl = X + (size_t)lc * n_pad;
+        double part[4] = {0.0, 0.0, 0.0, 0.0};
+        const double *Ljk = cm_tile_ptr(tiles, bt, J, kfJ) + lane * 4;
+        const double *yk = Xl + kfJ * CM_TILE + tt;
+        const int nst = (J - kfJ) * 8;
+#pragma unroll 4
+        for (int q = 0; q < nst; ++q) {
+            double v[4];
+            ldg4(v, Ljk + q * 128);
+            const double y = yk[q * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) part[i] += v[i] * y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1);
+            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2);
+        }
+        if (tt == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s_r[i * 8 + g] = Xl[J * CM_TILE + i * 8 + g] - part[i];
+        }
+        __syncwarp();
+        double zp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double v[4];
+            ldg4(v, Mj + q * 128);
+            const double rr = s_r[q * 4 + tt];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zp[i] += v[i] * rr;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 1);
+            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 2);
+        }
+        if (tt == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Xl[J * CM_TILE + i * 8 + g] = dpiv[J * CM_TILE + i * 8 + g] * zp[i];
+        }
+        __syncwarp();
+    }
+}
+
+template <int NW, bool PROF>
+__global__ void __launch_bounds__(NW * 32, 16 / NW)
+k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
+    extern __shared__ __align__(16) double smem[];
+    double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
+    double *s_rhs = s_scr + DSCR;                                    // [NW][32] forward substitution scratch
+    double *s_minpiv = s_rhs + NW * 32;                              // [NW]
+    int *s_prog = reinterpret_cast<int *>(s_minpiv + NW);            // [n_tile_rows_max] factor progress
+    int *s_yprog = s_prog + m.n_tile_rows_max;                       // rows forward-substituted
+    int *s_fail = s_yprog + 1;
+    __shared__ long long s_pc[PROF ? NW : 1][10];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    char *slab = ws + (size_t)blockIdx.x * L.per_subset;
+    int *info = reinterpret_cast<int *>(slab + L.off_info);
+    if (info[CM_INFO_STATUS] != CM_ST_OK) return;
+    const int NT = info[CM_INFO_NT];
+    double *tiles = reinterpret_cast<double *>(slab + L.off_tiles);
+    const int *kfirst = reinterpret_cast<const int *>(slab + L.off_kfirst);
+    double *dpiv = reinterpret_cast<double *>(slab + L.off_dpiv);
+    double *minv = reinterpret_cast<double *>(slab + L.off_minv);
+    double *X = reinterpret_cast<double *>(slab + L.off_x);
+    const int bt = m.band_tiles;
+    const int n_lc = m.n_lc;
+    const int zero_bits = info[CM_INFO_ZERO_LOAD];
+    volatile int *prog = s_prog;
+    volatile int *yprog = s_yprog;
+
+    for (int I = t; I < NT; I += NW * 32) s_prog[I] = kfirst[I];
+    if (t == 0) { *s_yprog = 0; *s_fail = 0; }
+    if (t < NW) s_minpiv[t] = __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+
+    long long *pc = PROF ? s_pc[warp] : nullptr;
+    if (PROF && lane == 0) for (int i = 0; i < 10; ++i) pc[i] = 0;
+    const long long tstart = PROF ? clock64() : 0;
+    for (int I = warp; I < NT; I += NW) {
+        const int kfI = kfirst[I];
+        for (int J = kfI; J < I; ++J) {
+            if (J == I - 1 && I - 2 >= kfI) {    // look-ahead: diagonal terms that do not need row I-1
+                FP_T0(pc);
+                diag_update(tiles, dpiv, bt, I, kfI, I - 1, lane);
+                FP_ADD(pc, 4);
+            }
+            offdiag_tile(tiles, minv, dpiv, kfirst, prog, bt, I, J, kfI, lane, pc);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) prog[I] = J + 1;
+        }
+        FP_T0(pc);
+        if (I > kfI) {                           // newest diagonal term (or all of them without look-ahead)
+            const int K0 = (I - 2 >= kfI) ? I - 1 : kfI;
+            diag_update(tiles, dpiv, bt, I, K0, I, lane);
+        }
+        __syncwarp();
+        FP_ADD(pc, 4);
+        if (I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
+        FP_ADD(pc, 5);
+        diag_factor_blk(cm_tile_ptr(tiles, bt, I, I), minv + (size_t)I * CM_TILE_ELEMS, dpiv + I * CM_TILE, s_scr, lane,
+                        s_fail, s_minpiv + warp);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) prog[I] = I + 1;
+        FP_ADD(pc, 6);
+        // forward substitution of row I once rows < I are done (they finish one chain step earlier)
+        {
+            int y = *yprog;
+            while (y < I) { __nanosleep(40); y = *yprog; }
+            __threadfence_block();
+        }
+        FP_ADD(pc, 7);
+        forward_row_w(tiles, minv, dpiv, X, s_rhs + warp * 32, L.n_pad, n_lc, zero_bits, bt, I, kfI, lane);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *yprog = I + 1;
+        FP_ADD(pc, 8);
+    }
+    if (PROF && lane == 0) {
+        pc[9] = clock64() - tstart;
+        for (int i = 0; i < 10; ++i) atomicAdd(&g_flow_prof[i], (unsigned long long)pc[i]);
+    }
+    __syncthreads();
+    if (t == 0) {
+        double mp = s_minpiv[0];
+        for (int w = 1; w < NW; ++w) mp = fmin(mp, s_minpiv[w]);
+        if (*s_fail) info[CM_INFO_STATUS] = CM_ST_SINGULAR;
+        dpiv[L.n_pad] = mp;            // slot after the pivots
+    }
+}
+
+size_t flow_smem(const cm_model_dev &m, int nw) {
+    return (size_t)(DSCR + nw * 32 + nw) * sizeof(double) + (size_t)(m.n_tile_rows_max + 4) * sizeof(int);
+}
+
+}  // namespace
+
+template <int NW, bool PROF>
+static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
+    static size_t configured = 0;
+    const size_t smem = flow_smem(m, NW);
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k3_factor_flow<NW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k3_factor_flow<NW, PROF><<<count, NW * 32, smem, st>>>(m, L, ws);
+    return cudaGetLastError();
+}
+
+cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+                                  int nwarps, int prof, cudaStream_t st) {
+    if (nwarps == 8) return prof ? launch_flow<8, true>(m, L, ws, count, st) : launch_flow<8, false>(m, L, ws, count, st);
+    return prof ? launch_flow<4, true>(m, L, ws, count, st) : launch_flow<4, false>(m, L, ws, count, st);
+}
+
+// read (and clear) the activity counters of the instrumented build
+cudaError_t cm_factor_flow_read_prof(unsigned long long *out16) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_flow_prof, 16 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(g_flow_prof, z, sizeof(z));
+}

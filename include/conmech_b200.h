@@ -130,14 +130,15 @@ typedef struct cm_solve_out {
                           /*                of the factorisation, one multiply-add counted as 2)  */
 } cm_solve_out;
 
-/* Factorisation kernel variant: 2 (default) = FP64 tensor-core block-band LDL^T
- * (csrc/k3_factor_col.cu) with 4-warp CTAs, 3 = the same with 8-warp CTAs, 4 / 5 = those two
- * instrumented with per-phase cycle counters, 0 = scalar validation variant of the same
- * algorithm (slow; used by the parity tests to cross-check the tensor-core path). */
+/* Factorisation kernel variant: 2 (default) = FP64 tensor-core block-band LDL^T, dataflow
+ * kernel (csrc/k3_factor_flow.cu) with 4-warp CTAs, 3 = the same with 8-warp CTAs, 4 / 5 = those
+ * two instrumented with per-activity cycle counters, 0 = scalar validation variant of the same
+ * algorithm (csrc/k3_factor.cu; slow, used by the parity tests to cross-check the tensor-core
+ * path). */
 int cm_set_variant(cm_handle *h, int32_t variant);
 
-/* Development aid: after a solve with variant 4 or 5, reads and clears the 16 phase counters
- * (clock64 cycles summed over CTAs; slot meanings in csrc/k3_factor_col.cu). */
+/* Development aid: after a solve with variant 4 or 5, reads and clears the 16 activity counters
+ * (clock64 cycles summed over all row warps; slot meanings in csrc/k3_factor_flow.cu). */
 int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16);
 
 /* Bytes of workspace needed to run `subsets_in_flight` subsets at once. cm_solve_many splits

@@ -115,3 +115,54 @@ def test_synthetic_workloads_match_survey():
     assert len(syn.config4_loadcases(mj)) == 4
     hf = syn.heightfield_subset(mj, 5, 5, 5, seed=3)
     assert hf == sorted(hf) and len(hf) > 0
+
+
+# ---------------------------------------------------------------- multi-rank sharding (gloo, CPU)
+def test_shard_range_partitions():
+    from conmech_b200.sharding import shard_range
+    for n in (0, 1, 7, 8, 100000, 12345):
+        for world in (1, 2, 3, 8):
+            edges = [shard_range(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+class _FakeEngine(object):
+    """Stands in for CudaStiffness on a CPU box: deterministic per-subset outputs from the masks."""
+    def solve_many(self, masks, want):
+        pop = np.unpackbits(np.ascontiguousarray(masks).view(np.uint8), axis=1).sum(axis=1)
+        res = {'flag': (pop % 2 == 0).astype(np.uint8).reshape(-1, 1), 'status': np.zeros((len(masks), 1), np.uint8),
+               'max_trans': pop.astype(np.float64).reshape(-1, 1) * 1e-4,
+               'compliance': pop.astype(np.float64).reshape(-1, 1) * 0.5}
+        return {k: res[k] for k in want}
+
+
+def _sharded_worker(rank, world, port, B, ret):
+    import torch.distributed as dist
+    from conmech_b200.sharding import solve_many_sharded
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{}'.format(port), rank=rank, world_size=world)
+    rng = np.random.RandomState(0)
+    masks = rng.randint(0, 2 ** 32, size=(B, 30), dtype=np.uint64).astype(np.uint32)
+    out = solve_many_sharded(_FakeEngine(), masks)
+    ret[rank] = {k: v.copy() for k, v in out.items()}
+    dist.destroy_process_group()
+
+
+def test_solve_many_sharded_gloo_world2():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    B, world = 37, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, port, B, ret), nprocs=world, join=True)
+    rng = np.random.RandomState(0)
+    masks = rng.randint(0, 2 ** 32, size=(B, 30), dtype=np.uint64).astype(np.uint32)
+    ref = _FakeEngine().solve_many(masks, ('flag', 'status', 'max_trans', 'compliance'))
+    for r in range(world):
+        for k, v in ref.items():
+            assert np.array_equal(ret[r][k], v), (r, k)

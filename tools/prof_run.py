@@ -27,11 +27,12 @@ for rep in range(2):
     ms = eng.last_stage_ms()
 fl = float(r['profile_flops'].sum().item())
 print('variant {} B={} stage ms {} | K3 {:.2f} TFLOP/s algorithmic | status {} flags {}'.format(variant, B, ms, fl / ms[1] / 1e9, np.bincount(r['status'].cpu().numpy().ravel()), int(r['flag'].sum().item())))
-if variant >= 4:
+if variant in (4, 5):
     import ctypes as C
     out = np.zeros(16, dtype=np.uint64)
-    eng._lib.cm_debug_k3_phase_cycles(eng._handle, out.ctypes.data_as(C.c_void_p))      # clear warm-up counts? (both calls accumulate)
-    names = ['late', 'diag|lookahead', 'trsm', 'diag_factor_alone']
-    tot = float(out[0] + out[1] + out[2])
-    for n, v in zip(names, out[:4]):
-        print('  {:18s} {:14d} cycles  {:6.2f}% of CTA time'.format(n, int(v), 100.0 * float(v) / tot))
+    eng._lib.cm_debug_k3_phase_cycles(eng._handle, out.ctypes.data_as(C.c_void_p))
+    names = ['wait_operand', 'update_streams', 'wait_M', 'solve_product', 'diag_updates', 'wait_prev_diag',
+             'diag_factor', 'wait_fwd_chain', 'forward_subst', 'total']
+    tot = float(out[9])
+    for n, v in zip(names, out[:len(names)]):
+        print('  {:18s} {:14d} cycles  {:6.2f}%'.format(n, int(v), 100.0 * float(v) / tot))
