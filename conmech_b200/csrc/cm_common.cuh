@@ -70,6 +70,8 @@ struct cm_ws_layout {
     size_t off_p;          // double [n_lc*6nV] full load vector, DOF order
     size_t off_kfirst;     // int    [n_tile_rows_max] first tile column in the envelope
     size_t off_minv;       // double [n_tile_rows_max*1024] M_J = D_J^-1 L_JJ^-1 per diagonal tile (tile layout)
+    size_t off_kcol;       // int    [n_tile_rows_max] first nonzero column of the tile row, in k-steps of 4
+                           //        (rounded down to even): columns left of it are zero in A and in L
     size_t off_info;       // int    [CM_INFO_INTS]
     int n_pad;             // n_tile_rows_max*32
 };
@@ -96,7 +98,7 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
-                                  int nwarps, int prof, cudaStream_t st);
+                                  int config, int prof, cudaStream_t st);
 cudaError_t cm_factor_flow_read_prof(unsigned long long *out16);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, long long first, int count,

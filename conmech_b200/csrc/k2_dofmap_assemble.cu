@@ -61,7 +61,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     int *s_base = reinterpret_cast<int *>(smem_raw);             // [nV] first solver row of node
     int *s_tmp = s_base + m.nV;                                    // [nV] scan input / scratch
     int *s_kfirst = s_tmp + m.nV;                                  // [n_tile_rows_max]
-    int *s_scan = s_kfirst + m.n_tile_rows_max;                    // [K2_THREADS+1]
+    int *s_kcol = s_kfirst + m.n_tile_rows_max;                    // [n_tile_rows_max] first column / 4
+    int *s_scan = s_kcol + m.n_tile_rows_max;                      // [K2_THREADS+1]
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_scan + K2_THREADS + 1);   // [mask_words]
     unsigned char *s_free = reinterpret_cast<unsigned char *>(s_mask + m.mask_words);   // [nV] free DOFs (0 if absent)
     unsigned char *s_exist = s_free + m.nV;                        // [nV]
@@ -79,6 +80,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     double *X = reinterpret_cast<double *>(slab + L.off_x);
     double *P = reinterpret_cast<double *>(slab + L.off_p);
     int *kfirst_g = reinterpret_cast<int *>(slab + L.off_kfirst);
+    int *kcol_g = reinterpret_cast<int *>(slab + L.off_kcol);
     int *info = reinterpret_cast<int *>(slab + L.off_info);
     const uint32_t *gmask = masks + (size_t)gs * m.mask_words;
     const int nV = m.nV;
@@ -175,7 +177,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     for (int p = t; p < nV; p += T) s_base[m.order[p]] = s_tmp[p];
     const int ns = n_free;
     const int NT = (ns + CM_TILE - 1) / CM_TILE;
-    for (int I = t; I < NT; I += T) s_kfirst[I] = I;
+    for (int I = t; I < NT; I += T) { s_kfirst[I] = I; s_kcol[I] = 8 * I; }
     __syncthreads();
     for (int v = t; v < nV; v += T) {
         int base = s_base[v];
@@ -193,14 +195,15 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         }
         int I0 = base / CM_TILE, I1 = (base + nf - 1) / CM_TILE;
         atomicMin(&s_kfirst[I0], cmin / CM_TILE);
-        if (I1 != I0) atomicMin(&s_kfirst[I1], cmin / CM_TILE);
+        atomicMin(&s_kcol[I0], cmin / 4);
+        if (I1 != I0) { atomicMin(&s_kfirst[I1], cmin / CM_TILE); atomicMin(&s_kcol[I1], cmin / 4); }
         unsigned long long w = 0;      // algorithmic work: sum over rows of (row - first column)^2
         for (int i = 0; i < nf; ++i) { unsigned long long hgt = (unsigned long long)(base + i - cmin); w += hgt * hgt; }
         atomicAdd(&s_work, w);
     }
     __syncthreads();
     if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
-    for (int I = t; I < NT; I += T) kfirst_g[I] = s_kfirst[I];
+    for (int I = t; I < NT; I += T) { kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1; }
 
     // ---- zero the tiles of the envelope (16-byte stores)
     {
@@ -351,7 +354,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,
                                       const cm_out_dev &out, cudaStream_t st) {
-    size_t smem = (size_t)(2 * m.nV + m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV + 16;
+    size_t smem = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV + 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k2_dofmap_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -190,16 +190,16 @@ __device__ __noinline__ void diag_factor_blk(const double *T, double *Mg, double
     __syncwarp();
 }
 
-// acc = A * M^T for 32x32 tiles A and M in global memory, tile layout
+// acc = A * M^T for 32x32 tiles A and M in global memory, tile layout; the columns of A left of
+// k-step q0 (even) are zero and skipped
 __device__ __forceinline__ void acc_mul_glob(TileAcc &acc, const double *__restrict__ A,
-                                             const double *__restrict__ M, int lane) {
-    const double *pa = A + lane * 4;
-    const double *pb = M + lane * 4;
+                                             const double *__restrict__ M, int q0, int lane) {
+    const double *pa = A + q0 * 128 + lane * 4;
+    const double *pb = M + q0 * 128 + lane * 4;
     double a0[4], b0[4], a1[4], b1[4];
     ldg4(a0, pa);
     ldg4(b0, pb);
-#pragma unroll
-    for (int q = 0; q < 8; q += 2) {
+    for (int q = q0; q < 8; q += 2) {
         ldg4(a1, pa + 128);
         ldg4(b1, pb + 128);
         frag_mma<false>(acc, a0, b0);
@@ -213,11 +213,14 @@ __device__ __forceinline__ void acc_mul_glob(TileAcc &acc, const double *__restr
 }
 
 // tile (I,J), J < I: all update terms as they become available, then the solve against M_J
-__device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, const double *dpiv, const int *kfirst,
-                                          volatile int *prog, int bt, int I, int J, int kfI, int lane,
+template <int DEPTH>
+__device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, const double *dpiv, const int *kcol,
+                                          volatile int *prog, int bt, int I, int J, int kcI, int lane,
                                           long long *pc) {
     double *T = cm_tile_ptr(tiles, bt, I, J);
-    int K = max(kfI, kfirst[J]);
+    // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
+    int qs = max(kcI, kcol[J]);
+    int K = qs >> 3;
     FP_T0(pc);
     if (K < J) {
         TileAcc acc;
@@ -225,9 +228,14 @@ __device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, con
         while (K < J) {
             const int Kend = min(wait_prog_gt(prog, J, K), J);
             FP_ADD(pc, 0);
-            acc_update_stream<false>(acc, cm_tile_ptr(tiles, bt, I, K), cm_tile_ptr(tiles, bt, J, K),
-                                     dpiv + K * CM_TILE, (Kend - K) * 8, lane);
+            const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
+            const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
+            if (DEPTH == 2)
+                acc_update_stream_d2<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
+            else
+                acc_update_stream<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
             K = Kend;
+            qs = K * 8;
             FP_ADD(pc, 1);
         }
         acc_store(acc, T, lane);
@@ -238,23 +246,29 @@ __device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, con
     FP_ADD(pc, 2);
     TileAcc r;
     acc_zero(r);
-    acc_mul_glob(r, T, minv + (size_t)J * CM_TILE_ELEMS, lane);
+    const int q0 = max(kcI - 8 * J, 0);            // leading zero columns of the row's first tile
+    acc_mul_glob(r, T, minv + (size_t)J * CM_TILE_ELEMS, q0, lane);
     acc_store(r, T, lane);
     FP_ADD(pc, 3);
 }
 
-// diagonal tile (I,I) -= sum_{K in [K0,K1)} L(I,K) D_K L(I,K)^T  (own row, already final)
-__device__ __noinline__ void diag_update(double *tiles, const double *dpiv, int bt, int I, int K0, int K1, int lane) {
+// diagonal tile (I,I) -= sum over k-steps [q0, q1) of the own (final) row:  L(I,k) d_k L(I,k)^T
+template <int DEPTH>
+__device__ __noinline__ void diag_update(double *tiles, const double *dpiv, int bt, int I, int q0, int q1, int lane) {
     double *T = cm_tile_ptr(tiles, bt, I, I);
+    const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)q0 * 128;
     TileAcc acc;
     acc_load(acc, T, lane);
-    acc_update_stream<true>(acc, cm_tile_ptr(tiles, bt, I, K0), nullptr, dpiv + K0 * CM_TILE, (K1 - K0) * 8, lane);
+    if (DEPTH == 2)
+        acc_update_stream_d2<true>(acc, A, nullptr, dpiv + q0 * 4, q1 - q0, lane);
+    else
+        acc_update_stream<true>(acc, A, nullptr, dpiv + q0 * 4, q1 - q0, lane);
     acc_store(acc, T, lane);
 }
 
 // forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - sum_K L(J,K) y_K)
 __device__ __noinline__ void forward_row_w(const double *tiles, const double *minv, const double *dpiv, double *X,
-                                           double *s_r, int n_pad, int n_lc, int zero_bits, int bt, int J, int kfJ,
+                                           double *s_r, int n_pad, int n_lc, int zero_bits, int bt, int J, int kcJ,
                                            int lane) {
     const int g = lane >> 2, tt = lane & 3;
     const double *Mj = minv + (size_t)J * CM_TILE_ELEMS + lane * 4;
@@ -262,9 +276,9 @@ __device__ __noinline__ void forward_row_w(const double *tiles, const double *mi
         if ((zero_bits >> lc) & 1) continue;
         double *Xl = X + (size_t)lc * n_pad;
         double part[4] = {0.0, 0.0, 0.0, 0.0};
-        const double *Ljk = cm_tile_ptr(tiles, bt, J, kfJ) + lane * 4;
-        const double *yk = Xl + kfJ * CM_TILE + tt;
-        const int nst = (J - kfJ) * 8;
+        const double *Ljk = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)kcJ * 128 + lane * 4;
+        const double *yk = Xl + kcJ * 4 + tt;
+        const int nst = J * 8 - kcJ;
 #pragma unroll 4
         for (int q = 0; q < nst; ++q) {
             double v[4];
@@ -305,8 +319,8 @@ __device__ __noinline__ void forward_row_w(const double *tiles, const double *mi
     }
 }
 
-template <int NW, bool PROF>
-__global__ void __launch_bounds__(NW * 32, 16 / NW)
+template <int NW, bool PROF, int MINB, int DEPTH>
+__global__ void __launch_bounds__(NW * 32, MINB)
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
@@ -324,6 +338,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     const int NT = info[CM_INFO_NT];
     double *tiles = reinterpret_cast<double *>(slab + L.off_tiles);
     const int *kfirst = reinterpret_cast<const int *>(slab + L.off_kfirst);
+    const int *kcol = reinterpret_cast<const int *>(slab + L.off_kcol);
     double *dpiv = reinterpret_cast<double *>(slab + L.off_dpiv);
     double *minv = reinterpret_cast<double *>(slab + L.off_minv);
     double *X = reinterpret_cast<double *>(slab + L.off_x);
@@ -343,21 +358,22 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     const long long tstart = PROF ? clock64() : 0;
     for (int I = warp; I < NT; I += NW) {
         const int kfI = kfirst[I];
+        const int kcI = kcol[I];                 // first nonzero column of the row in k-steps (even), kcI / 8 == kfI
         for (int J = kfI; J < I; ++J) {
             if (J == I - 1 && I - 2 >= kfI) {    // look-ahead: diagonal terms that do not need row I-1
                 FP_T0(pc);
-                diag_update(tiles, dpiv, bt, I, kfI, I - 1, lane);
+                diag_update<DEPTH>(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            offdiag_tile(tiles, minv, dpiv, kfirst, prog, bt, I, J, kfI, lane, pc);
+            offdiag_tile<DEPTH>(tiles, minv, dpiv, kcol, prog, bt, I, J, kcI, lane, pc);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
         }
         FP_T0(pc);
         if (I > kfI) {                           // newest diagonal term (or all of them without look-ahead)
-            const int K0 = (I - 2 >= kfI) ? I - 1 : kfI;
-            diag_update(tiles, dpiv, bt, I, K0, I, lane);
+            const int q0 = (I - 2 >= kfI) ? 8 * (I - 1) : kcI;
+            diag_update<DEPTH>(tiles, dpiv, bt, I, q0, 8 * I, lane);
         }
         __syncwarp();
         FP_ADD(pc, 4);
@@ -376,7 +392,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
             __threadfence_block();
         }
         FP_ADD(pc, 7);
-        forward_row_w(tiles, minv, dpiv, X, s_rhs + warp * 32, L.n_pad, n_lc, zero_bits, bt, I, kfI, lane);
+        forward_row_w(tiles, minv, dpiv, X, s_rhs + warp * 32, L.n_pad, n_lc, zero_bits, bt, I, kcI, lane);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *yprog = I + 1;
@@ -401,23 +417,27 @@ size_t flow_smem(const cm_model_dev &m, int nw) {
 
 }  // namespace
 
-template <int NW, bool PROF>
+template <int NW, bool PROF, int MINB, int DEPTH>
 static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
     static size_t configured = 0;
     const size_t smem = flow_smem(m, NW);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k3_factor_flow<NW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3_factor_flow<NW, PROF, MINB, DEPTH>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k3_factor_flow<NW, PROF><<<count, NW * 32, smem, st>>>(m, L, ws);
+    k3_factor_flow<NW, PROF, MINB, DEPTH><<<count, NW * 32, smem, st>>>(m, L, ws);
     return cudaGetLastError();
 }
 
+// config: 0 = 4 warps x 4 CTAs/SM, 1 = 8 warps x 2 CTAs/SM, 2 = 4 warps x 3 CTAs/SM with the deeper
+// operand prefetch (more registers per thread)
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
-                                  int nwarps, int prof, cudaStream_t st) {
-    if (nwarps == 8) return prof ? launch_flow<8, true>(m, L, ws, count, st) : launch_flow<8, false>(m, L, ws, count, st);
-    return prof ? launch_flow<4, true>(m, L, ws, count, st) : launch_flow<4, false>(m, L, ws, count, st);
+                                  int config, int prof, cudaStream_t st) {
+    if (config == 1) return prof ? launch_flow<8, true, 2, 1>(m, L, ws, count, st) : launch_flow<8, false, 2, 1>(m, L, ws, count, st);
+    if (config == 2) return launch_flow<4, false, 3, 2>(m, L, ws, count, st);
+    return prof ? launch_flow<4, true, 4, 1>(m, L, ws, count, st) : launch_flow<4, false, 4, 1>(m, L, ws, count, st);
 }
 
 // read (and clear) the activity counters of the instrumented build
