@@ -158,19 +158,16 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
 
-    # ---- CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process
+    # ---- CPU baseline (rank 0, N=1 only) in a child process of its own, before the GPU work starts
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_bench
-        n_procs = os.cpu_count() or 1
-        n_sample = args.cpu_sample or min(args.batch, 400 * n_procs)      # ~10-15 s of CPU work
-        rate, wall, _ = cpu_bench.time_oracle(GRID, range(n_sample), n_procs=n_procs, trans_tol=TRANS_TOL)
-        rate1, wall1, _ = cpu_bench.time_oracle(GRID, range(min(n_sample, 48)), n_procs=1, trans_tol=TRANS_TOL)
-        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': n_procs, 'kind': 'port',
-                        'sample': 'first {} subsets of the same workload on {} processes ({:.1f} s); '
-                                  'single process: {:.1f} solves/s; {}'.format(
-                                      n_sample, n_procs, wall, rate1, cpu_bench.cpu_model_name()),
-                        'single_core_value': rate1}
+        r = subprocess.run([sys.executable, '-m', 'oracle.cpu_bench', str(GRID[0]), str(GRID[1]), str(GRID[2]),
+                            str(TRANS_TOL), str(args.batch), str(args.cpu_sample)],
+                           cwd=REPO, capture_output=True, text=True)
+        if r.returncode == 0 and r.stdout.strip():
+            cpu_baseline = json.loads(r.stdout.strip().splitlines()[-1])
+        else:
+            sys.stderr.write('cpu baseline failed: ' + r.stderr[-2000:] + '\n')
 
     import numpy as np
     import torch

@@ -399,7 +399,7 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
 
 int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
-    if (variant != 0 && (variant < 2 || variant > 6)) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0 or 2..6");
+    if (variant != 0 && (variant < 2 || variant > 5)) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0, 2, 3, 4 or 5");
     h->variant = variant;
     return CM_OK;
 }
@@ -450,8 +450,7 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         if (h->variant == 0)
             CU(cm_launch_factor(h->m, h->L, ws, count, 0, st));
         else
-            CU(cm_launch_factor_flow(h->m, h->L, ws, count, h->variant == 6 ? 2 : (h->variant & 1),
-                                     (h->variant == 4 || h->variant == 5) ? 1 : 0, st));
+            CU(cm_launch_factor_flow(h->m, h->L, ws, count, h->variant & 1, h->variant >= 4 ? 1 : 0, st));
         if (h->timing) CU(cudaEventRecord(h->ev[2], st));
         CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
         h->launches += 3;

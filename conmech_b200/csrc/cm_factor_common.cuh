@@ -1,0 +1,217 @@
+// Pieces shared by the factorisation kernels (k3_factor_flow.cu, k3_factor_pair.cu): the blocked
+// diagonal-tile factorisation, the forward substitution of one block row, progress-flag waits.
+#pragma once
+#include "cm_frag.cuh"
+
+namespace {
+
+constexpr int DS = 34;                          // row stride of the diagonal scratch matrices (doubles)
+constexpr int DSCR = 2 * 32 * DS + 2 * 32;      // CTA scratch of the diagonal factorisation: two 32x32
+                                                // matrices, a column, the reciprocal pivots.  One copy
+                                                // per CTA: the diagonal factorisations of a subset form
+                                                // a dependency chain, so only one is ever in progress.
+
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);      // seed: relative error <= 2^-23
+    x = fma(x, e, x);                // 2^-46
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);             // below one ulp
+}
+
+__device__ __forceinline__ int wait_prog_gt(volatile int *prog, int J, int K) {
+    int p = prog[J];
+    while (p <= K) { __nanosleep(40); p = prog[J]; }
+    __threadfence_block();
+    return p;
+}
+
+__device__ __forceinline__ double dneg(double x) {       // sign flip on the integer pipe
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+
+// Blocked LDL^T of the lower triangle of tile T (global, tile layout) by one warp, then
+// M = D^-1 L^-1, written to Mg (global, tile layout); pivots to dg.  8-column panels are eliminated
+// with one matrix row per lane (the pivot column travels through shared memory); the trailing
+// update and the block-wise inverse (X = L^-1: X_ii by substitution, X_ij = -X_ii sum_k L_ik X_kj)
+// run as 8x8x4 FP64 MMAs on fragments read from the shared scratch matrices.  The serial chain is
+// 32 pivots of ~100 cycles plus a dozen short MMA stages, and the warp issues ~4x fewer FP64
+// instructions than an unblocked elimination - this routine is the critical path of every tile row.
+// A pivot that violates the reference's rules (exact zero raises in SuperLU: numpy_stiffness.py:
+// 301-319; <= -1e-14 is rejected: :326-336; NaN fails both) sets *s_fail and is replaced by 1.
+__device__ __noinline__ void diag_factor_blk(const double *T, double *Mg, double *dg, double *scr, int lane,
+                                             int *s_fail, double *s_minpiv_w) {
+    double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v[4];
+        ldg4(v, T + q * 128 + lane * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sA[(8 * i + g) * DS + 4 * q + t] = v[i];
+    }
+    __syncwarp();
+    int fail = 0;
+    double minpiv = *s_minpiv_w;
+    double dmine = 1.0, rmine = 1.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 8 * b;
+        double p[8], pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(sA + lane * DS + c0 + k);
+            p[k] = v.x; p[k + 1] = v.y;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            s_col[lane] = p[c];
+            __syncwarp();
+            double d = s_col[c0 + c];
+            if (!(d > -CM_EPS) || d == 0.0) { fail = 1; d = 1.0; }
+            minpiv = fmin(minpiv, d);
+            const double rinv = fast_rcp(d);
+            if (lane == c0 + c) { dmine = d; rmine = rinv; }
+            pk[c] = p[c];                        // (L D)[lane][c0+c]
+            const double l = p[c] * rinv;        // L[lane][c0+c] for lane > c0+c (unused otherwise)
+            p[c] = l;
+#pragma unroll
+            for (int k = c + 1; k < 8; ++k) p[k] -= l * s_col[c0 + k];
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            *reinterpret_cast<double2 *>(sA + lane * DS + c0 + k) = make_double2(p[k], p[k + 1]);
+            *reinterpret_cast<double2 *>(sB + lane * DS + c0 + k) = make_double2(pk[k], pk[k + 1]);
+        }
+        __syncwarp();
+        if (b < 3) {
+            // trailing blocks (ri,cj), b < cj <= ri:  A -= (L D)(ri,b) L(cj,b)^T
+#pragma unroll
+            for (int ri = b + 1; ri < 4; ++ri)
+#pragma unroll
+                for (int cj = b + 1; cj <= ri; ++cj) {
+                    double2 cc = *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t);
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2)
+                        dmma_m8n8k4(cc.x, cc.y, dneg(sB[(8 * ri + g) * DS + c0 + 4 * s2 + t]),
+                                    sA[(8 * cj + g) * DS + c0 + 4 * s2 + t]);
+                    *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t) = cc;
+                }
+            __syncwarp();
+        }
+    }
+    dg[lane] = dmine;
+    s_rinv[lane] = rmine;
+    if (lane == 0) { *s_minpiv_w = minpiv; if (fail) *s_fail = 1; }
+    // ---- X = L^-1.  Diagonal blocks: lane 8*bb + j owns column j of X_bb (substitution on e_j)
+    {
+        const int bb = lane >> 3, j = lane & 7;
+        const double *Lb = sA + (8 * bb) * DS + 8 * bb;
+        double x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r) x[r] -= Lb[r * DS + c] * x[c];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sB[(8 * bb + r) * DS + 8 * bb + j] = x[r];
+    }
+    __syncwarp();
+    // off-diagonal blocks by distance d from the diagonal: T_ij = sum_{k=j}^{i-1} L_ik X_kj is parked in
+    // the unused upper block (j,i) of sA, then X_ij = -X_ii T_ij
+#pragma unroll
+    for (int d = 1; d < 4; ++d) {
+#pragma unroll
+        for (int i = d; i < 4; ++i) {
+            const int j = i - d;
+            double c0v = 0.0, c1v = 0.0;
+#pragma unroll
+            for (int k = j; k < i; ++k)
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2)
+                    dmma_m8n8k4(c0v, c1v, sA[(8 * i + g) * DS + 8 * k + 4 * s2 + t],
+                                sB[(8 * k + 4 * s2 + t) * DS + 8 * j + g]);
+            *reinterpret_cast<double2 *>(sA + (8 * j + g) * DS + 8 * i + 2 * t) = make_double2(c0v, c1v);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = d; i < 4; ++i) {
+            const int j = i - d;
+            double c0v = 0.0, c1v = 0.0;
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+                dmma_m8n8k4(c0v, c1v, dneg(sB[(8 * i + g) * DS + 8 * i + 4 * s2 + t]),
+                            sA[(8 * j + 4 * s2 + t) * DS + 8 * i + g]);
+            *reinterpret_cast<double2 *>(sB + (8 * i + g) * DS + 8 * j + 2 * t) = make_double2(c0v, c1v);
+        }
+        __syncwarp();
+    }
+    // ---- M = D^-1 X to global memory, tile layout (blocks above the diagonal are zero)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            v[i] = ((q >> 1) <= i) ? sB[(8 * i + g) * DS + 4 * q + t] * s_rinv[8 * i + g] : 0.0;
+        stg4(Mg + q * 128 + lane * 4, v[0], v[1], v[2], v[3]);
+    }
+    __syncwarp();
+}
+
+// forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - sum_K L(J,K) y_K)
+__device__ __noinline__ void forward_row_w(const double *tiles, const double *minv, const double *dpiv, double *X,
+                                           double *s_r, int n_pad, int n_lc, int zero_bits, int bt, int J, int kcJ,
+                                           int lane) {
+    const int g = lane >> 2, tt = lane & 3;
+    const double *Mj = minv + (size_t)J * CM_TILE_ELEMS + lane * 4;
+    for (int lc = 0; lc < n_lc; ++lc) {
+        if ((zero_bits >> lc) & 1) continue;
+        double *Xl = X + (size_t)lc * n_pad;
+        double part[4] = {0.0, 0.0, 0.0, 0.0};
+        const double *Ljk = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)kcJ * 128 + lane * 4;
+        const double *yk = Xl + kcJ * 4 + tt;
+        const int nst = J * 8 - kcJ;
+#pragma unroll 4
+        for (int q = 0; q < nst; ++q) {
+            double v[4];
+            ldg4(v, Ljk + q * 128);
+            const double y = yk[q * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) part[i] += v[i] * y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1);
+            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2);
+        }
+        if (tt == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s_r[i * 8 + g] = Xl[J * CM_TILE + i * 8 + g] - part[i];
+        }
+        __syncwarp();
+        double zp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double v[4];
+            ldg4(v, Mj + q * 128);
+            const double rr = s_r[q * 4 + tt];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zp[i] += v[i] * rr;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 1);
+            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 2);
+        }
+        if (tt == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Xl[J * CM_TILE + i * 8 + g] = dpiv[J * CM_TILE + i * 8 + g] * zp[i];
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace

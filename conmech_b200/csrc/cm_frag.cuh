@@ -124,50 +124,6 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
     }
 }
 
-// Same stream with the fragments of TWO k-steps in flight ahead of the MMAs (three register
-// stages, ~50 more registers): for kernels compiled with a larger register budget, where fewer
-// resident warps have to cover the L2 / DRAM latency of the operand stream themselves.
-template <bool SYRK>
-struct FragStage { double a[4], b[4], d; };
-
-template <bool SYRK>
-__device__ __forceinline__ void stage_load(FragStage<SYRK> &s, const double *pa, const double *pb, const double *pd, int q) {
-    ldg4(s.a, pa + q * 128);
-    if (!SYRK) ldg4(s.b, pb + q * 128);
-    s.d = pd[q * 4];
-}
-template <bool SYRK>
-__device__ __forceinline__ void stage_mma(TileAcc &acc, FragStage<SYRK> &s) {
-    const double nd = -s.d;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s.b[i] = (SYRK ? s.a[i] : s.b[i]) * nd;
-    frag_mma<SYRK>(acc, s.a, s.b);
-}
-
-template <bool SYRK>
-__device__ __forceinline__ void acc_update_stream_d2(TileAcc &acc, const double *__restrict__ A,
-                                                     const double *__restrict__ B, const double *__restrict__ d,
-                                                     int nsteps, int lane) {
-    const double *pa = A + lane * 4;
-    const double *pb = B + lane * 4;
-    const double *pd = d + (lane & 3);
-    FragStage<SYRK> s0, s1, s2;
-    stage_load(s0, pa, pb, pd, 0);
-    if (nsteps > 1) stage_load(s1, pa, pb, pd, 1);
-    for (int q = 0; q < nsteps; q += 3) {
-        if (q + 2 < nsteps) stage_load(s2, pa, pb, pd, q + 2);
-        stage_mma(acc, s0);
-        if (q + 1 < nsteps) {
-            if (q + 3 < nsteps) stage_load(s0, pa, pb, pd, q + 3);
-            stage_mma(acc, s1);
-        }
-        if (q + 2 < nsteps) {
-            if (q + 4 < nsteps) stage_load(s1, pa, pb, pd, q + 4);
-            stage_mma(acc, s2);
-        }
-    }
-}
-
 // acc = A * Ms^T for one 32x32 tile A in global memory and Ms in shared memory, both in tile
 // layout (used as L(I,J) = acc(I,J) * (D_J^-1 L_JJ^-1)^T, the triangular solve as a product).
 __device__ __forceinline__ void acc_mul_smem(TileAcc &acc, const double *__restrict__ A,

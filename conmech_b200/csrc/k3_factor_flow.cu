@@ -21,174 +21,19 @@
 // and every warp always has a long stream of independent MMAs queued.  The critical path per row
 // is  M_{I-1} -> solve of tile (I,I-1) -> newest SYRK term -> LDL^T + inverse of tile (I,I);  all
 // older terms of those two tiles are accumulated before the warp starts waiting (look-ahead).
-#include "cm_frag.cuh"
-#include <cstdlib>
+#include "cm_factor_common.cuh"
 
 namespace {
 
-constexpr int DS = 34;                          // row stride of the diagonal scratch matrices (doubles)
-constexpr int DSCR = 2 * 32 * DS + 2 * 32;      // CTA scratch of the diagonal factorisation: two 32x32
-                                                // matrices, a column, the reciprocal pivots.  One copy
-                                                // per CTA: the diagonal factorisations of a subset form
-                                                // a dependency chain, so only one is ever in progress.
 
 // instrumented build: cycles per activity, summed over all row warps (slots: 0 wait for an update
 // operand, 1 update streams, 2 wait for M_J, 3 solve product, 4 diagonal-tile updates, 5 wait for the
 // previous diagonal factor, 6 diagonal factor, 7 wait for the forward chain, 8 forward substitution,
-// 9 total)
+// 9 total, 10 solve product of the chain tile (I,I-1), 11 newest diagonal term, 12 gap between the
+// publication of M_{I-1} and the owner of row I noticing it)
 __device__ unsigned long long g_flow_prof[16];
 #define FP_T0(pc) long long _t0 = (pc) ? clock64() : 0
 #define FP_ADD(pc, slot) do { if (pc) { long long _n = clock64(); if ((threadIdx.x & 31) == 0) (pc)[slot] += _n - _t0; _t0 = _n; } } while (0)
-
-__device__ __forceinline__ double fast_rcp(double d) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-    double e = fma(-d, x, 1.0);      // seed: relative error <= 2^-23
-    x = fma(x, e, x);                // 2^-46
-    e = fma(-d, x, 1.0);
-    return fma(x, e, x);             // below one ulp
-}
-
-__device__ __forceinline__ int wait_prog_gt(volatile int *prog, int J, int K) {
-    int p = prog[J];
-    while (p <= K) { __nanosleep(40); p = prog[J]; }
-    __threadfence_block();
-    return p;
-}
-
-__device__ __forceinline__ double dneg(double x) {       // sign flip on the integer pipe
-    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
-}
-
-// Blocked LDL^T of the lower triangle of tile T (global, tile layout) by one warp, then
-// M = D^-1 L^-1, written to Mg (global, tile layout); pivots to dg.  8-column panels are eliminated
-// with one matrix row per lane (the pivot column travels through shared memory); the trailing
-// update and the block-wise inverse (X = L^-1: X_ii by substitution, X_ij = -X_ii sum_k L_ik X_kj)
-// run as 8x8x4 FP64 MMAs on fragments read from the shared scratch matrices.  The serial chain is
-// 32 pivots of ~100 cycles plus a dozen short MMA stages, and the warp issues ~4x fewer FP64
-// instructions than an unblocked elimination - this routine is the critical path of every tile row.
-// A pivot that violates the reference's rules (exact zero raises in SuperLU: numpy_stiffness.py:
-// 301-319; <= -1e-14 is rejected: :326-336; NaN fails both) sets *s_fail and is replaced by 1.
-__device__ __noinline__ void diag_factor_blk(const double *T, double *Mg, double *dg, double *scr, int lane,
-                                             int *s_fail, double *s_minpiv_w) {
-    double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        double v[4];
-        ldg4(v, T + q * 128 + lane * 4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sA[(8 * i + g) * DS + 4 * q + t] = v[i];
-    }
-    __syncwarp();
-    int fail = 0;
-    double minpiv = *s_minpiv_w;
-    double dmine = 1.0, rmine = 1.0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int c0 = 8 * b;
-        double p[8], pk[8];
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            const double2 v = *reinterpret_cast<const double2 *>(sA + lane * DS + c0 + k);
-            p[k] = v.x; p[k + 1] = v.y;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            s_col[lane] = p[c];
-            __syncwarp();
-            double d = s_col[c0 + c];
-            if (!(d > -CM_EPS) || d == 0.0) { fail = 1; d = 1.0; }
-            minpiv = fmin(minpiv, d);
-            const double rinv = fast_rcp(d);
-            if (lane == c0 + c) { dmine = d; rmine = rinv; }
-            pk[c] = p[c];                        // (L D)[lane][c0+c]
-            const double l = p[c] * rinv;        // L[lane][c0+c] for lane > c0+c (unused otherwise)
-            p[c] = l;
-#pragma unroll
-            for (int k = c + 1; k < 8; ++k) p[k] -= l * s_col[c0 + k];
-            __syncwarp();
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            *reinterpret_cast<double2 *>(sA + lane * DS + c0 + k) = make_double2(p[k], p[k + 1]);
-            *reinterpret_cast<double2 *>(sB + lane * DS + c0 + k) = make_double2(pk[k], pk[k + 1]);
-        }
-        __syncwarp();
-        if (b < 3) {
-            // trailing blocks (ri,cj), b < cj <= ri:  A -= (L D)(ri,b) L(cj,b)^T
-#pragma unroll
-            for (int ri = b + 1; ri < 4; ++ri)
-#pragma unroll
-                for (int cj = b + 1; cj <= ri; ++cj) {
-                    double2 cc = *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t);
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2)
-                        dmma_m8n8k4(cc.x, cc.y, dneg(sB[(8 * ri + g) * DS + c0 + 4 * s2 + t]),
-                                    sA[(8 * cj + g) * DS + c0 + 4 * s2 + t]);
-                    *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t) = cc;
-                }
-            __syncwarp();
-        }
-    }
-    dg[lane] = dmine;
-    s_rinv[lane] = rmine;
-    if (lane == 0) { *s_minpiv_w = minpiv; if (fail) *s_fail = 1; }
-    // ---- X = L^-1.  Diagonal blocks: lane 8*bb + j owns column j of X_bb (substitution on e_j)
-    {
-        const int bb = lane >> 3, j = lane & 7;
-        const double *Lb = sA + (8 * bb) * DS + 8 * bb;
-        double x[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) x[r] = (r == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int c = 0; c < 7; ++c)
-#pragma unroll
-            for (int r = c + 1; r < 8; ++r) x[r] -= Lb[r * DS + c] * x[c];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) sB[(8 * bb + r) * DS + 8 * bb + j] = x[r];
-    }
-    __syncwarp();
-    // off-diagonal blocks by distance d from the diagonal: T_ij = sum_{k=j}^{i-1} L_ik X_kj is parked in
-    // the unused upper block (j,i) of sA, then X_ij = -X_ii T_ij
-#pragma unroll
-    for (int d = 1; d < 4; ++d) {
-#pragma unroll
-        for (int i = d; i < 4; ++i) {
-            const int j = i - d;
-            double c0v = 0.0, c1v = 0.0;
-#pragma unroll
-            for (int k = j; k < i; ++k)
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2)
-                    dmma_m8n8k4(c0v, c1v, sA[(8 * i + g) * DS + 8 * k + 4 * s2 + t],
-                                sB[(8 * k + 4 * s2 + t) * DS + 8 * j + g]);
-            *reinterpret_cast<double2 *>(sA + (8 * j + g) * DS + 8 * i + 2 * t) = make_double2(c0v, c1v);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = d; i < 4; ++i) {
-            const int j = i - d;
-            double c0v = 0.0, c1v = 0.0;
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2)
-                dmma_m8n8k4(c0v, c1v, dneg(sB[(8 * i + g) * DS + 8 * i + 4 * s2 + t]),
-                            sA[(8 * j + 4 * s2 + t) * DS + 8 * i + g]);
-            *reinterpret_cast<double2 *>(sB + (8 * i + g) * DS + 8 * j + 2 * t) = make_double2(c0v, c1v);
-        }
-        __syncwarp();
-    }
-    // ---- M = D^-1 X to global memory, tile layout (blocks above the diagonal are zero)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        double v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            v[i] = ((q >> 1) <= i) ? sB[(8 * i + g) * DS + 4 * q + t] * s_rinv[8 * i + g] : 0.0;
-        stg4(Mg + q * 128 + lane * 4, v[0], v[1], v[2], v[3]);
-    }
-    __syncwarp();
-}
 
 // acc = A * M^T for 32x32 tiles A and M in global memory, tile layout; the columns of A left of
 // k-step q0 (even) are zero and skipped
@@ -213,10 +58,9 @@ __device__ __forceinline__ void acc_mul_glob(TileAcc &acc, const double *__restr
 }
 
 // tile (I,J), J < I: all update terms as they become available, then the solve against M_J
-template <int DEPTH>
 __device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, const double *dpiv, const int *kcol,
                                           volatile int *prog, int bt, int I, int J, int kcI, int lane,
-                                          long long *pc) {
+                                          long long *pc, volatile long long *tpub) {
     double *T = cm_tile_ptr(tiles, bt, I, J);
     // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
     int qs = max(kcI, kcol[J]);
@@ -230,10 +74,7 @@ __device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, con
             FP_ADD(pc, 0);
             const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
             const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
-            if (DEPTH == 2)
-                acc_update_stream_d2<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
-            else
-                acc_update_stream<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
+            acc_update_stream<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
             K = Kend;
             qs = K * 8;
             FP_ADD(pc, 1);
@@ -244,83 +85,27 @@ __device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, con
     }
     wait_prog_gt(prog, J, J);                     // M_J published
     FP_ADD(pc, 2);
+    if (pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *tpub;     // reaction gap on the chain
     TileAcc r;
     acc_zero(r);
     const int q0 = max(kcI - 8 * J, 0);            // leading zero columns of the row's first tile
     acc_mul_glob(r, T, minv + (size_t)J * CM_TILE_ELEMS, q0, lane);
     acc_store(r, T, lane);
-    FP_ADD(pc, 3);
+    if (pc && J == I - 1) FP_ADD(pc, 10); else FP_ADD(pc, 3);
 }
 
 // diagonal tile (I,I) -= sum over k-steps [q0, q1) of the own (final) row:  L(I,k) d_k L(I,k)^T
-template <int DEPTH>
 __device__ __noinline__ void diag_update(double *tiles, const double *dpiv, int bt, int I, int q0, int q1, int lane) {
     double *T = cm_tile_ptr(tiles, bt, I, I);
     const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)q0 * 128;
     TileAcc acc;
     acc_load(acc, T, lane);
-    if (DEPTH == 2)
-        acc_update_stream_d2<true>(acc, A, nullptr, dpiv + q0 * 4, q1 - q0, lane);
-    else
-        acc_update_stream<true>(acc, A, nullptr, dpiv + q0 * 4, q1 - q0, lane);
+    acc_update_stream<true>(acc, A, nullptr, dpiv + q0 * 4, q1 - q0, lane);
     acc_store(acc, T, lane);
 }
 
-// forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - sum_K L(J,K) y_K)
-__device__ __noinline__ void forward_row_w(const double *tiles, const double *minv, const double *dpiv, double *X,
-                                           double *s_r, int n_pad, int n_lc, int zero_bits, int bt, int J, int kcJ,
-                                           int lane) {
-    const int g = lane >> 2, tt = lane & 3;
-    const double *Mj = minv + (size_t)J * CM_TILE_ELEMS + lane * 4;
-    for (int lc = 0; lc < n_lc; ++lc) {
-        if ((zero_bits >> lc) & 1) continue;
-        double *Xl = X + (size_t)lc * n_pad;
-        double part[4] = {0.0, 0.0, 0.0, 0.0};
-        const double *Ljk = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)kcJ * 128 + lane * 4;
-        const double *yk = Xl + kcJ * 4 + tt;
-        const int nst = J * 8 - kcJ;
-#pragma unroll 4
-        for (int q = 0; q < nst; ++q) {
-            double v[4];
-            ldg4(v, Ljk + q * 128);
-            const double y = yk[q * 4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) part[i] += v[i] * y;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1);
-            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2);
-        }
-        if (tt == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s_r[i * 8 + g] = Xl[J * CM_TILE + i * 8 + g] - part[i];
-        }
-        __syncwarp();
-        double zp[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            double v[4];
-            ldg4(v, Mj + q * 128);
-            const double rr = s_r[q * 4 + tt];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) zp[i] += v[i] * rr;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 1);
-            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 2);
-        }
-        if (tt == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) Xl[J * CM_TILE + i * 8 + g] = dpiv[J * CM_TILE + i * 8 + g] * zp[i];
-        }
-        __syncwarp();
-    }
-}
-
-template <int NW, bool PROF, int MINB, int DEPTH>
-__global__ void __launch_bounds__(NW * 32, MINB)
+template <int NW, bool PROF>
+__global__ void __launch_bounds__(NW * 32, 16 / NW)
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
@@ -329,7 +114,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     int *s_prog = reinterpret_cast<int *>(s_minpiv + NW);            // [n_tile_rows_max] factor progress
     int *s_yprog = s_prog + m.n_tile_rows_max;                       // rows forward-substituted
     int *s_fail = s_yprog + 1;
-    __shared__ long long s_pc[PROF ? NW : 1][10];
+    __shared__ long long s_pc[PROF ? NW : 1][16];
+    __shared__ long long s_tpub;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     char *slab = ws + (size_t)blockIdx.x * L.per_subset;
@@ -354,7 +140,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     __syncthreads();
 
     long long *pc = PROF ? s_pc[warp] : nullptr;
-    if (PROF && lane == 0) for (int i = 0; i < 10; ++i) pc[i] = 0;
+    if (PROF && lane == 0) for (int i = 0; i < 16; ++i) pc[i] = 0;
     const long long tstart = PROF ? clock64() : 0;
     for (int I = warp; I < NT; I += NW) {
         const int kfI = kfirst[I];
@@ -362,10 +148,10 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         for (int J = kfI; J < I; ++J) {
             if (J == I - 1 && I - 2 >= kfI) {    // look-ahead: diagonal terms that do not need row I-1
                 FP_T0(pc);
-                diag_update<DEPTH>(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
+                diag_update(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            offdiag_tile<DEPTH>(tiles, minv, dpiv, kcol, prog, bt, I, J, kcI, lane, pc);
+            offdiag_tile(tiles, minv, dpiv, kcol, prog, bt, I, J, kcI, lane, pc, &s_tpub);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
@@ -373,17 +159,17 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         FP_T0(pc);
         if (I > kfI) {                           // newest diagonal term (or all of them without look-ahead)
             const int q0 = (I - 2 >= kfI) ? 8 * (I - 1) : kcI;
-            diag_update<DEPTH>(tiles, dpiv, bt, I, q0, 8 * I, lane);
+            diag_update(tiles, dpiv, bt, I, q0, 8 * I, lane);
         }
         __syncwarp();
-        FP_ADD(pc, 4);
+        FP_ADD(pc, 11);
         if (I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
         FP_ADD(pc, 5);
         diag_factor_blk(cm_tile_ptr(tiles, bt, I, I), minv + (size_t)I * CM_TILE_ELEMS, dpiv + I * CM_TILE, s_scr, lane,
                         s_fail, s_minpiv + warp);
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) prog[I] = I + 1;
+        if (lane == 0) { if (PROF) s_tpub = clock64(); prog[I] = I + 1; }
         FP_ADD(pc, 6);
         // forward substitution of row I once rows < I are done (they finish one chain step earlier)
         {
@@ -400,7 +186,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     }
     if (PROF && lane == 0) {
         pc[9] = clock64() - tstart;
-        for (int i = 0; i < 10; ++i) atomicAdd(&g_flow_prof[i], (unsigned long long)pc[i]);
+        for (int i = 0; i < 16; ++i) atomicAdd(&g_flow_prof[i], (unsigned long long)pc[i]);
     }
     __syncthreads();
     if (t == 0) {
@@ -417,27 +203,24 @@ size_t flow_smem(const cm_model_dev &m, int nw) {
 
 }  // namespace
 
-template <int NW, bool PROF, int MINB, int DEPTH>
+template <int NW, bool PROF>
 static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
     static size_t configured = 0;
     const size_t smem = flow_smem(m, NW);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k3_factor_flow<NW, PROF, MINB, DEPTH>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3_factor_flow<NW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k3_factor_flow<NW, PROF, MINB, DEPTH><<<count, NW * 32, smem, st>>>(m, L, ws);
+    k3_factor_flow<NW, PROF><<<count, NW * 32, smem, st>>>(m, L, ws);
     return cudaGetLastError();
 }
 
-// config: 0 = 4 warps x 4 CTAs/SM, 1 = 8 warps x 2 CTAs/SM, 2 = 4 warps x 3 CTAs/SM with the deeper
-// operand prefetch (more registers per thread)
+// config: 0 = 4 warps x 4 CTAs/SM (default), 1 = 8 warps x 2 CTAs/SM
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                                   int config, int prof, cudaStream_t st) {
-    if (config == 1) return prof ? launch_flow<8, true, 2, 1>(m, L, ws, count, st) : launch_flow<8, false, 2, 1>(m, L, ws, count, st);
-    if (config == 2) return launch_flow<4, false, 3, 2>(m, L, ws, count, st);
-    return prof ? launch_flow<4, true, 4, 1>(m, L, ws, count, st) : launch_flow<4, false, 4, 1>(m, L, ws, count, st);
+    if (config == 1) return prof ? launch_flow<8, true>(m, L, ws, count, st) : launch_flow<8, false>(m, L, ws, count, st);
+    return prof ? launch_flow<4, true>(m, L, ws, count, st) : launch_flow<4, false>(m, L, ws, count, st);
 }
 
 // read (and clear) the activity counters of the instrumented build

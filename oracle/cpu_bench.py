@@ -70,3 +70,24 @@ def cpu_model_name():
     except OSError:
         pass
     return 'unknown'
+
+
+def baseline_record(grid, trans_tol, batch, sample=0):
+    """The ``cpu_baseline`` object of bench.py: the oracle on all host cores over a bounded sample."""
+    n_procs = os.cpu_count() or 1
+    n_sample = sample or min(batch, 400 * n_procs)          # ~10-15 s of CPU work
+    rate, wall, _ = time_oracle(grid, range(n_sample), n_procs=n_procs, trans_tol=trans_tol)
+    rate1, wall1, _ = time_oracle(grid, range(min(n_sample, 48)), n_procs=1, trans_tol=trans_tol)
+    return {'value': rate, 'unit': 'solves/s', 'cores': n_procs, 'kind': 'port',
+            'sample': 'first {} subsets of the same workload on {} processes ({:.1f} s); '
+                      'single process: {:.1f} solves/s; {}'.format(n_sample, n_procs, wall, rate1, cpu_model_name()),
+            'single_core_value': rate1}
+
+
+if __name__ == '__main__':
+    # python -m oracle.cpu_bench nx ny nz trans_tol batch sample  ->  one JSON line (used by bench.py in a
+    # child process so that the CPU run shares no state - threads, allocator - with the GPU process)
+    import json
+    import sys
+    a = sys.argv[1:]
+    print(json.dumps(baseline_record((int(a[0]), int(a[1]), int(a[2])), float(a[3]), int(a[4]), int(a[5]))))

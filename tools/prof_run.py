@@ -32,7 +32,7 @@ if variant in (4, 5):
     out = np.zeros(16, dtype=np.uint64)
     eng._lib.cm_debug_k3_phase_cycles(eng._handle, out.ctypes.data_as(C.c_void_p))
     names = ['wait_operand', 'update_streams', 'wait_M', 'solve_product', 'diag_updates', 'wait_prev_diag',
-             'diag_factor', 'wait_fwd_chain', 'forward_subst', 'total']
+             'diag_factor', 'wait_fwd_chain', 'forward_subst', 'total', 'chain_solve', 'chain_last_syrk', 'chain_gap']
     tot = float(out[9])
     for n, v in zip(names, out[:len(names)]):
         print('  {:18s} {:14d} cycles  {:6.2f}%'.format(n, int(v), 100.0 * float(v) / tot))
