@@ -219,6 +219,30 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     std::vector<int> pos(nV);
     for (int p = 0; p < nV; ++p) pos[h->order[p]] = p;
 
+    // lower pairs of every node (static: the solver order does not depend on the subset)
+    std::vector<int> lp_ptr(nV + 1, 0), lp_node, lp_eptr(1, 0), lp_elem;
+    std::vector<unsigned char> lp_end;
+    for (int a = 0; a < nV; ++a) {
+        std::vector<std::pair<int, int>> inc;     // (neighbour, incidence slot) of a's incident elements
+        for (int p = ne_ptr[a]; p < ne_ptr[a + 1]; ++p) {
+            int e = ne_elem[p];
+            int c = d->conn[2 * e + (ne_end[p] ? 0 : 1)];
+            if (pos[c] < pos[a]) inc.push_back({c, p});
+        }
+        std::stable_sort(inc.begin(), inc.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+            return x.first < y.first; });        // per neighbour, elements stay in ascending id
+        for (size_t k = 0; k < inc.size(); ++k) {
+            if (k == 0 || inc[k].first != inc[k - 1].first) {
+                if (k) lp_eptr.push_back((int)lp_elem.size());
+                lp_node.push_back(inc[k].first);
+            }
+            lp_elem.push_back(ne_elem[inc[k].second]);
+            lp_end.push_back(ne_end[inc[k].second]);
+        }
+        if (!inc.empty()) lp_eptr.push_back((int)lp_elem.size());
+        lp_ptr[a + 1] = (int)lp_node.size();
+    }
+
     m.n_tile_rows_max = std::max(1, (n_free_full + CM_TILE - 1) / CM_TILE);
     m.band_tiles = (halfbw + CM_TILE - 1) / CM_TILE + 1;
     if (m.band_tiles > m.n_tile_rows_max) m.band_tiles = m.n_tile_rows_max;
@@ -235,7 +259,8 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
 
     int rc;
     double *xyz, *props, *cr; int *conn, *d_ne_ptr, *d_ne_elem, *d_sup_node, *d_node_sup, *d_order, *d_pos;
-    unsigned char *d_ne_end, *d_sup_cond;
+    int *d_lp_ptr, *d_lp_node, *d_lp_eptr, *d_lp_elem;
+    unsigned char *d_ne_end, *d_sup_cond, *d_lp_end;
 #define UP(expr) do { rc = (expr); if (rc != CM_OK) { cm_destroy(h); return rc; } } while (0)
     UP(dev_upload(h, d->xyz, (size_t)3 * nV, &xyz));
     UP(dev_upload(h, d->conn, (size_t)2 * nE, &conn));
@@ -249,6 +274,11 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     UP(dev_upload(h, node_sup.data(), (size_t)nV, &d_node_sup));
     UP(dev_upload(h, h->order.data(), (size_t)nV, &d_order));
     UP(dev_upload(h, pos.data(), (size_t)nV, &d_pos));
+    UP(dev_upload(h, lp_ptr.data(), lp_ptr.size(), &d_lp_ptr));
+    UP(dev_upload(h, lp_node.data(), lp_node.size(), &d_lp_node));
+    UP(dev_upload(h, lp_eptr.data(), lp_eptr.size(), &d_lp_eptr));
+    UP(dev_upload(h, lp_elem.data(), lp_elem.size(), &d_lp_elem));
+    UP(dev_upload(h, lp_end.data(), lp_end.size(), &d_lp_end));
     UP(dev_upload<double>(h, nullptr, (size_t)144 * nE, &m.Kg));
     UP(dev_upload<double>(h, nullptr, (size_t)9 * nE, &m.R3));
     UP(dev_upload<double>(h, nullptr, (size_t)nE, &m.elen));
@@ -257,6 +287,7 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     m.ne_ptr = d_ne_ptr; m.ne_elem = d_ne_elem; m.ne_end = d_ne_end;
     m.sup_node = d_sup_node; m.sup_cond = d_sup_cond; m.node_sup = d_node_sup;
     m.order = d_order; m.pos = d_pos;
+    m.lp_ptr = d_lp_ptr; m.lp_node = d_lp_node; m.lp_eptr = d_lp_eptr; m.lp_elem = d_lp_elem; m.lp_end = d_lp_end;
     m.q = nullptr; m.pnodal = nullptr;
 
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -331,6 +362,7 @@ static void make_layout(cm_handle *h) {
     L.off_kfirst = o; o = al(o + (size_t)m.n_tile_rows_max * sizeof(int));
     L.off_minv = o;   o = al(o + (size_t)m.n_tile_rows_max * CM_TILE_ELEMS * sizeof(double));
     L.off_kcol = o;   o = al(o + (size_t)m.n_tile_rows_max * sizeof(int));
+    L.off_aflag = o;  o = al(o + (size_t)m.n_tile_rows_max * m.band_tiles);
     L.off_info = o;   o = al(o + CM_INFO_INTS * sizeof(int));
     L.per_subset = o;
 }

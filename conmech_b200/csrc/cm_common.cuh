@@ -52,6 +52,13 @@ struct cm_model_dev {
     const int *sup_node;   // [nS]
     const unsigned char *sup_cond; // [nS*6]
     const int *node_sup;   // [nV] support index or -1
+    // "lower pairs": for node a the distinct neighbours c that precede it in the solver order, and
+    // per pair the elements joining them (ascending ids) with the end at which a sits
+    const int *lp_ptr;     // [nV+1]
+    const int *lp_node;    // [n_pairs]
+    const int *lp_eptr;    // [n_pairs+1]
+    const int *lp_elem;    // [<= nE]
+    const unsigned char *lp_end;   // [<= nE]
     const int *order;      // [nV] solver position -> node
     const int *pos;        // [nV] node -> solver position
     const double *q;       // [n_lc*nE*12] lumped element loads
@@ -70,6 +77,8 @@ struct cm_ws_layout {
     size_t off_p;          // double [n_lc*6nV] full load vector, DOF order
     size_t off_kfirst;     // int    [n_tile_rows_max] first tile column in the envelope
     size_t off_minv;       // double [n_tile_rows_max*1024] M_J = D_J^-1 L_JJ^-1 per diagonal tile (tile layout)
+    size_t off_aflag;      // uchar  [n_tile_rows_max*band_tiles] 1: the tile holds entries of K_mm (assembled by K2);
+                           //        0: structurally empty before fill-in, its storage is NOT initialised
     size_t off_kcol;       // int    [n_tile_rows_max] first nonzero column of the tile row, in k-steps of 4
                            //        (rounded down to even): columns left of it are zero in A and in L
     size_t off_info;       // int    [CM_INFO_INTS]

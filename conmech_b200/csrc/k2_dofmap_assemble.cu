@@ -66,6 +66,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_scan + K2_THREADS + 1);   // [mask_words]
     unsigned char *s_free = reinterpret_cast<unsigned char *>(s_mask + m.mask_words);   // [nV] free DOFs (0 if absent)
     unsigned char *s_exist = s_free + m.nV;                        // [nV]
+    unsigned char *s_aflag = s_exist + m.nV;                       // [n_tile_rows_max*band_tiles] tile holds K_mm entries
     __shared__ int s_red[8];
     __shared__ unsigned long long s_work;
     __shared__ double s_dred[K2_THREADS / 32];
@@ -81,6 +82,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     double *P = reinterpret_cast<double *>(slab + L.off_p);
     int *kfirst_g = reinterpret_cast<int *>(slab + L.off_kfirst);
     int *kcol_g = reinterpret_cast<int *>(slab + L.off_kcol);
+    unsigned char *aflag_g = reinterpret_cast<unsigned char *>(slab + L.off_aflag);
     int *info = reinterpret_cast<int *>(slab + L.off_info);
     const uint32_t *gmask = masks + (size_t)gs * m.mask_words;
     const int nV = m.nV;
@@ -178,6 +180,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     const int ns = n_free;
     const int NT = (ns + CM_TILE - 1) / CM_TILE;
     for (int I = t; I < NT; I += T) { s_kfirst[I] = I; s_kcol[I] = 8 * I; }
+    for (int i = t; i < NT * m.band_tiles; i += T) s_aflag[i] = 0;
     __syncthreads();
     for (int v = t; v < nV; v += T) {
         int base = s_base[v];
@@ -187,13 +190,29 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         int nf = s_free[v];
         if (nf == 0) continue;
         int cmin = base;
+        const int I0 = base / CM_TILE, I1 = (base + nf - 1) / CM_TILE;
+        const int btf = m.band_tiles;
+        // tiles that receive entries of K_mm: the node's own diagonal block and the blocks towards
+        // neighbours that come earlier in the solver order
+        s_aflag[I0 * btf + btf - 1] = 1;
+        if (I1 != I0) { s_aflag[I1 * btf + btf - 1] = 1; s_aflag[I1 * btf + btf - 2] = 1; }
         for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
             int e = m.ne_elem[p];
             if (!elem_on(s_mask, e)) continue;
             int c = m.conn[2 * e + (m.ne_end[p] ? 0 : 1)];
-            if (s_free[c]) cmin = min(cmin, s_base[c]);
+            if (!s_free[c]) continue;
+            const int bc = s_base[c];
+            cmin = min(cmin, bc);
+            if (bc < base) {
+                const int K0 = bc / CM_TILE, K1 = (bc + s_free[c] - 1) / CM_TILE;
+                s_aflag[I0 * btf + (K0 - I0 + btf - 1)] = 1;
+                if (K1 <= I0) s_aflag[I0 * btf + (K1 - I0 + btf - 1)] = 1;
+                if (I1 != I0) {
+                    s_aflag[I1 * btf + (K0 - I1 + btf - 1)] = 1;
+                    s_aflag[I1 * btf + (K1 - I1 + btf - 1)] = 1;
+                }
+            }
         }
-        int I0 = base / CM_TILE, I1 = (base + nf - 1) / CM_TILE;
         atomicMin(&s_kfirst[I0], cmin / CM_TILE);
         atomicMin(&s_kcol[I0], cmin / 4);
         if (I1 != I0) { atomicMin(&s_kfirst[I1], cmin / CM_TILE); atomicMin(&s_kcol[I1], cmin / 4); }
@@ -204,18 +223,19 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     __syncthreads();
     if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
     for (int I = t; I < NT; I += T) { kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1; }
+    for (int i = t; i < NT * m.band_tiles; i += T) aflag_g[i] = s_aflag[i];
 
-    // ---- zero the tiles of the envelope (16-byte stores)
+    // ---- zero the tiles that will receive entries (16-byte stores); structurally empty tiles of the
+    // envelope are left untouched - the factorisation starts their accumulators from zero
     {
         const int bt = m.band_tiles;
         double2 z2 = make_double2(0.0, 0.0);
-        for (int I = 0; I < NT; ++I) {
-            int kf = s_kfirst[I];
-            int ntile = I - kf + 1;
-            double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)I * bt + (kf - I + bt - 1)) * CM_TILE_ELEMS);
-            int n2 = ntile * (CM_TILE_ELEMS / 2);
-            for (int i = t; i < n2; i += T) dst[i] = z2;
-        }
+        for (int I = 0; I < NT; ++I)
+            for (int K = s_kfirst[I]; K <= I; ++K) {
+                if (!s_aflag[I * bt + (K - I + bt - 1)]) continue;
+                double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS);
+                for (int i = t; i < CM_TILE_ELEMS / 2; i += T) dst[i] = z2;
+            }
     }
 
     // ---- diagonal of K_mm and the Jacobi scale (numpy_stiffness.py:283-290)
@@ -246,7 +266,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     if (t == 0) info[CM_INFO_JACOBI] = jacobi;
     __syncthreads();
 
-    // ---- gather assembly, one warp per node row block
+    // ---- gather assembly, one warp per node: the 6x6 diagonal block (lower triangle) and one 6x6
+    // block per lower pair (a,c) - 36 entries each, all entries of the node spread over the lanes.
+    // An entry sums its contributing element entries in ascending element id.
     {
         const int bt = m.band_tiles;
         const int lane = t & 31, warp = t >> 5, nw = T >> 5;
@@ -254,53 +276,44 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             if (s_free[a] == 0) continue;
             const int base_a = s_base[a];
             const int p0 = m.ne_ptr[a], p1 = m.ne_ptr[a + 1];
-            // diagonal node block, lower triangle
-            for (int idx = lane; idx < 36; idx += 32) {
-                int i = idx / 6, j = idx - 6 * i;
-                if (j > i) continue;
-                int r = node_row(m, a, i, base_a), c = node_row(m, a, j, base_a);
-                if (r < 0 || c < 0) continue;
+            const int q0 = m.lp_ptr[a];
+            const int total = 36 * (1 + m.lp_ptr[a + 1] - q0);
+            for (int idx = lane; idx < total; idx += 32) {
+                const int blk = idx / 36, ij = idx - 36 * blk;
+                const int i = ij / 6, j = ij - 6 * i;
+                const int r = node_row(m, a, i, base_a);
+                if (r < 0) continue;
+                int cc;
                 double s = 0.0;
-                for (int p = p0; p < p1; ++p) {
-                    int e = m.ne_elem[p];
-                    if (!elem_on(s_mask, e)) continue;
-                    int o = 6 * m.ne_end[p];
-                    s += thr(m.Kg[(size_t)e * 144 + (o + i) * 12 + o + j]);
-                }
-                s = (dinv[r] * s) * dinv[c];
-                int I = r >> 5, K = c >> 5;
-                tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, c & 31)] = s;
-            }
-            // off-diagonal node blocks (a,c) with c before a in the solver order
-            for (int p = p0; p < p1; ++p) {
-                int e = m.ne_elem[p];
-                if (!elem_on(s_mask, e)) continue;
-                int enda = m.ne_end[p];
-                int c = m.conn[2 * e + (enda ? 0 : 1)];
-                if (s_free[c] == 0 || s_base[c] > base_a) continue;
-                bool dup = false;            // an earlier existing element joins the same pair
-                for (int p2 = p0; p2 < p; ++p2) {
-                    int e2 = m.ne_elem[p2];
-                    if (elem_on(s_mask, e2) && m.conn[2 * e2 + (m.ne_end[p2] ? 0 : 1)] == c) dup = true;
-                }
-                if (dup) continue;
-                const int base_c = s_base[c];
-                for (int idx = lane; idx < 36; idx += 32) {
-                    int i = idx / 6, j = idx - 6 * i;
-                    int r = node_row(m, a, i, base_a), cc = node_row(m, c, j, base_c);
-                    if (r < 0 || cc < 0) continue;
-                    double s = 0.0;
-                    for (int p2 = p; p2 < p1; ++p2) {
-                        int e2 = m.ne_elem[p2];
-                        if (!elem_on(s_mask, e2)) continue;
-                        int ea2 = m.ne_end[p2];
-                        if (m.conn[2 * e2 + (ea2 ? 0 : 1)] != c) continue;
-                        s += thr(m.Kg[(size_t)e2 * 144 + (6 * ea2 + i) * 12 + 6 * (1 - ea2) + j]);
+                if (blk == 0) {
+                    if (j > i) continue;
+                    cc = node_row(m, a, j, base_a);
+                    if (cc < 0) continue;
+                    for (int p = p0; p < p1; ++p) {
+                        const int e = m.ne_elem[p];
+                        if (!elem_on(s_mask, e)) continue;
+                        const int o = 6 * m.ne_end[p];
+                        s += thr(m.Kg[(size_t)e * 144 + (o + i) * 12 + o + j]);
                     }
-                    s = (dinv[r] * s) * dinv[cc];
-                    int I = r >> 5, K = cc >> 5;
-                    tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = s;
+                } else {
+                    const int q = q0 + blk - 1;
+                    const int c = m.lp_node[q];
+                    if (s_free[c] == 0) continue;
+                    cc = node_row(m, c, j, s_base[c]);
+                    if (cc < 0) continue;
+                    bool any = false;
+                    for (int pe = m.lp_eptr[q]; pe < m.lp_eptr[q + 1]; ++pe) {
+                        const int e = m.lp_elem[pe];
+                        if (!elem_on(s_mask, e)) continue;
+                        const int ea = m.lp_end[pe];
+                        s += thr(m.Kg[(size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea) + j]);
+                        any = true;
+                    }
+                    if (!any) continue;          // no existing element joins the pair: the tile may be unassembled
                 }
+                s = (dinv[r] * s) * dinv[cc];
+                const int I = r >> 5, K = cc >> 5;
+                tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = s;
             }
         }
         // unit diagonal on the padding rows of the last tile
@@ -354,7 +367,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,
                                       const cm_out_dev &out, cudaStream_t st) {
-    size_t smem = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV + 16;
+    size_t smem = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
+                  (size_t)m.n_tile_rows_max * m.band_tiles + 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k2_dofmap_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -33,6 +33,7 @@ k3_factor_scalar(cm_model_dev m, cm_ws_layout L, char *ws) {
     const int *kfirst = reinterpret_cast<const int *>(slab + L.off_kfirst);
     double *dpiv = reinterpret_cast<double *>(slab + L.off_dpiv);
     double *minv = reinterpret_cast<double *>(slab + L.off_minv);
+    const unsigned char *aflag = reinterpret_cast<const unsigned char *>(slab + L.off_aflag);
     double *X = reinterpret_cast<double *>(slab + L.off_x);
     const int bt = m.band_tiles;
     const int n_lc = m.n_lc;
@@ -51,8 +52,9 @@ k3_factor_scalar(cm_model_dev m, cm_ws_layout L, char *ws) {
             double acc[32];             // row `lane` of tile (I,J)
             if (active) {
                 const double *A = cm_tile_ptr(tiles, bt, I, J);
+                const bool has_a = aflag[I * bt + (J - I + bt - 1)] != 0;     // else the storage is not initialised
 #pragma unroll
-                for (int k = 0; k < 32; ++k) acc[k] = A[cm_tile_off(lane, k)];
+                for (int k = 0; k < 32; ++k) acc[k] = has_a ? A[cm_tile_off(lane, k)] : 0.0;
                 for (int K = max(kfirst[I], kfJ); K < J; ++K) {
                     const double *Lik = cm_tile_ptr(tiles, bt, I, K);
                     const double *Ljk = cm_tile_ptr(tiles, bt, J, K);

@@ -36,39 +36,50 @@ __device__ unsigned long long g_flow_prof[16];
 #define FP_ADD(pc, slot) do { if (pc) { long long _n = clock64(); if ((threadIdx.x & 31) == 0) (pc)[slot] += _n - _t0; _t0 = _n; } } while (0)
 
 // acc = A * M^T for 32x32 tiles A and M in global memory, tile layout; the columns of A left of
-// k-step q0 (even) are zero and skipped
+// k-step q0 (even) are zero and skipped.  M is lower triangular, so k-step q only reaches the
+// output column blocks cj >= q/2: 80 MMAs instead of 128.
 __device__ __forceinline__ void acc_mul_glob(TileAcc &acc, const double *__restrict__ A,
                                              const double *__restrict__ M, int q0, int lane) {
-    const double *pa = A + q0 * 128 + lane * 4;
-    const double *pb = M + q0 * 128 + lane * 4;
-    double a0[4], b0[4], a1[4], b1[4];
-    ldg4(a0, pa);
-    ldg4(b0, pb);
-    for (int q = q0; q < 8; q += 2) {
-        ldg4(a1, pa + 128);
-        ldg4(b1, pb + 128);
-        frag_mma<false>(acc, a0, b0);
-        pa += 256; pb += 256;
-        if (q + 2 < 8) {
-            ldg4(a0, pa);
-            ldg4(b0, pb);
+    const double *pa = A + lane * 4;
+    const double *pb = M + lane * 4;
+    double a[2][4], b[2][4];
+    ldg4(a[0], pa + q0 * 128);
+    ldg4(b[0], pb + q0 * 128);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (q < q0) continue;
+        const int cur = q & 1;
+        if (q + 1 < 8) {
+            ldg4(a[cur ^ 1], pa + (q + 1) * 128);
+            ldg4(b[cur ^ 1], pb + (q + 1) * 128);
         }
-        frag_mma<false>(acc, a1, b1);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < 4; ++cj)
+                if (cj >= (q >> 1)) dmma_m8n8k4(acc.c[cj][0][ri], acc.c[cj][1][ri], a[cur][ri], b[cur][cj]);
     }
 }
 
 // tile (I,J), J < I: all update terms as they become available, then the solve against M_J
 __device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, const double *dpiv, const int *kcol,
-                                          volatile int *prog, int bt, int I, int J, int kcI, int lane,
-                                          long long *pc, volatile long long *tpub) {
+                                          const unsigned char *aflag, volatile int *prog, int bt, int I, int J,
+                                          int kcI, int lane, long long *pc, volatile long long *tpub) {
     double *T = cm_tile_ptr(tiles, bt, I, J);
+    const bool has_a = aflag[I * bt + (J - I + bt - 1)] != 0;      // K2 assembled entries into this tile
     // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
     int qs = max(kcI, kcol[J]);
     int K = qs >> 3;
     FP_T0(pc);
+    if (K >= J && !has_a) {                       // no entries and no fill-in: the tile of L is zero
+        TileAcc z;
+        acc_zero(z);
+        acc_store(z, T, lane);
+        return;
+    }
     if (K < J) {
         TileAcc acc;
-        acc_load(acc, T, lane);
+        if (has_a) acc_load(acc, T, lane); else acc_zero(acc);
         while (K < J) {
             const int Kend = min(wait_prog_gt(prog, J, K), J);
             FP_ADD(pc, 0);
@@ -125,6 +136,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     double *tiles = reinterpret_cast<double *>(slab + L.off_tiles);
     const int *kfirst = reinterpret_cast<const int *>(slab + L.off_kfirst);
     const int *kcol = reinterpret_cast<const int *>(slab + L.off_kcol);
+    const unsigned char *aflag = reinterpret_cast<const unsigned char *>(slab + L.off_aflag);
     double *dpiv = reinterpret_cast<double *>(slab + L.off_dpiv);
     double *minv = reinterpret_cast<double *>(slab + L.off_minv);
     double *X = reinterpret_cast<double *>(slab + L.off_x);
@@ -151,7 +163,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
                 diag_update(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            offdiag_tile(tiles, minv, dpiv, kcol, prog, bt, I, J, kcI, lane, pc, &s_tpub);
+            offdiag_tile(tiles, minv, dpiv, kcol, aflag, prog, bt, I, J, kcI, lane, pc, &s_tpub);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
