@@ -317,3 +317,16 @@ def test_config4_multi_loadcase():
         orc.set_loads(lc)
         n_m = check_against_oracle(eng, orc, subsets, r, lc=li, tag='cfg4-lc{}'.format(li))
         assert n_m == 0
+
+
+def test_config5_large_frame():
+    """BASELINE config 5: ~10k-element grid (15x15x16: 9675 elements, 20 250 free DOFs, band of 35
+    tiles, 633 tile rows) - a factorisation-bound case; two subsets against the oracle."""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(15, 15, 16)
+    sc, orc = make_pair(model, LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    eng = sc._sc_ins
+    assert eng.info['n_free_full'] == 20250
+    subsets = [syn.connected_subset(model, 3, lo=0.5, hi=0.6), []]
+    r = eng.solve_many(subsets, want=ALL)
+    check_against_oracle(eng, orc, subsets, r, tag='g10k')
