@@ -10,5 +10,6 @@ from .stiffness_base import StiffnessBase
 from .cuda_stiffness import CudaStiffness
 from .stiffness_checker import StiffnessChecker
 from .masks import pack_masks, ids_to_mask, mask_to_ids
+from .sharding import shard_range, solve_many_sharded
 
 __version__ = '0.1.0'

@@ -84,6 +84,21 @@ class StiffnessChecker(object):
             return flags, {k: r[k][:, 0].copy() for k in ('status', 'max_trans', 'compliance')}
         return flags
 
+    def solve_sequence(self, order, return_details=False):
+        """Stiffness check of EVERY prefix of a construction sequence in one batched pass: flag k
+        is ``solve(order[:k+1])``.  This is the loop the sequencing planners around the reference
+        run one solve at a time (README.rst:39-42, examples/notebook_demo/demo.ipynb); here the
+        prefix masks are built vectorised (cumulative OR) and solved together."""
+        order = np.asarray(list(order), dtype=np.int64)
+        nE = len(self.model.elements)
+        if order.size and (order.min() < 0 or order.max() >= nE):
+            raise IndexError('element id not within range!')
+        W = (nE + 31) // 32
+        words = np.zeros((len(order), W), dtype=np.uint32)
+        words[np.arange(len(order)), order >> 5] = np.uint32(1) << (order & 31).astype(np.uint32)
+        masks = np.bitwise_or.accumulate(words, axis=0)
+        return self.solve_many(masks, return_details=return_details)
+
     # ---------------------------------------------------------------- loads
     def set_loads(self, loadcase):
         """reference ``stiffness_checker.py:188-218``."""
@@ -251,6 +266,22 @@ class StiffnessChecker(object):
             json.dump(self.result_data, f, indent=4 if formatted_json else None)
 
     # ---------------------------------------------------------------- graph queries
+    def set_output_json(self, do_output=True, output_dir=None, file_name=None):
+        """DEPRECATED in the reference (``stiffness_checker.py:589-603``); use ``write_result_to_json``."""
+        raise NotImplementedError('deprecated in the reference; use write_result_to_json(file_path)')
+
+    def get_element_local_node_id(self, element_id, point):
+        """0 / 1 if ``point`` is end 0 / end 1 of the element, else None.  (The reference's
+        version, ``stiffness_checker.py:678-692``, calls an undefined ``norm``; this one compares
+        coordinates within 1e-9.)"""
+        u, v = self.elements[element_id]
+        p = np.asarray(point, dtype=float)
+        if np.linalg.norm(p - np.asarray(self.node_points[u])) < 1e-9:
+            return 0
+        if np.linalg.norm(p - np.asarray(self.node_points[v])) < 1e-9:
+            return 1
+        return None
+
     def get_node_neighbors(self, return_e_id=False):
         nb = defaultdict(set)
         for e_id, e in enumerate(self.elements):

@@ -330,3 +330,35 @@ def test_config5_large_frame():
     subsets = [syn.connected_subset(model, 3, lo=0.5, hi=0.6), []]
     r = eng.solve_many(subsets, want=ALL)
     check_against_oracle(eng, orc, subsets, r, tag='g10k')
+
+
+def test_solve_sequence_and_from_data():
+    """Next-row callers: every prefix of a construction sequence in one call, and the
+    one-call JSON-data entry point (reference utils.py:6-64) against the reference's stored result."""
+    import json
+    from conmech_b200 import StiffnessChecker, LoadCase, GravityLoad, synthetic as syn
+    from conmech_b200.utils import solve_linear_elastic_from_data
+    g = Golden('tower_3D__bfs_prefixes')
+    model = g.model()
+    sc = StiffnessChecker(model, checker_engine='cuda')
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    sc.set_nodal_displacement_tol(trans_tol=1e-3)
+    order = syn.bfs_sequence(model)
+    flags = sc.solve_sequence(order)
+    assert ''.join('1' if f else '0' for f in flags) == '000000000001110000000111'
+    assert flags == sc.solve_many([order[:k] for k in range(1, len(order) + 1)])
+    # cantilever_beam_truss: model + load case as data -> result dictionary like the reference's,
+    # checked against the result file an older release of the reference stored with the example
+    import os
+    g2 = Golden('cantilever_beam_truss__loads')
+    with open(os.path.join(MODELS, 'cantilever_beam_truss.json')) as f:
+        mdata = json.load(f)
+    with open(os.path.join(MODELS, 'cantilever_beam_truss_loadcase.json')) as f:
+        ldata = json.load(f)
+    rd = solve_linear_elastic_from_data(mdata, ldata, verbose=False)
+    assert rd['solve_success'] is True
+    assert abs(rd['elastic_energy'] - float(g2.extra('stored_compliance'))) <= 1e-9 * float(g2.extra('stored_compliance'))
+    assert abs(rd['max_trans'] - float(g2.extra('stored_max_trans'))) <= 1e-9 * float(g2.extra('stored_max_trans'))
+    U = g2.extra('stored_U').reshape(-1, 6)
+    for nid, nd in rd['nodal_displacement'].items():
+        assert np.max(np.abs(np.array(nd) - U[nid])) <= 1e-9 * np.abs(U).max()
