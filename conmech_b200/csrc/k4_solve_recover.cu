@@ -135,6 +135,12 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     for (int q = 0; q < 8; ++q) Xl[I * CM_TILE + q * 4 + lane] = cs[q];
             }
             for (int I = NT - 1; I > 0; --I) {
+                // M_{I-1} is needed at the end of this row's chain: start its DRAM read now
+                if (warp == 0) {
+                    const double *Mn = minv + (size_t)(I - 1) * CM_TILE_ELEMS;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + lane * 16));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + 512 + lane * 16));
+                }
                 __syncthreads();
                 const int kf = kfirst[I];
                 double x4[4];
