@@ -29,7 +29,8 @@ struct cm_handle {
     // load tables
     double *d_q = nullptr, *d_pnodal = nullptr;
     double rot_tol = 0.0;
-    int variant = 2;                     // 2/3 = FP64 tensor-core dataflow kernel with 4/8-warp CTAs (2 default), 4/5 = same, instrumented, 0 = scalar validation
+    int variant = 1;                     // 1 = FP64 tensor-core dataflow kernel, CTA size chosen per launch (default); 2/3/6 = the same with 4/8/16-warp CTAs;
+                                         // 4/5 = 4/8-warp CTAs instrumented; 0 = scalar validation
     // counters / timing
     long long launches = 0;
     int timing = 0;
@@ -431,7 +432,7 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
 
 int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
-    if (variant != 0 && (variant < 2 || variant > 5)) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0, 2, 3, 4 or 5");
+    if (variant < 0 || variant > 6) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..6");
     h->variant = variant;
     return CM_OK;
 }
@@ -482,7 +483,11 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         if (h->variant == 0)
             CU(cm_launch_factor(h->m, h->L, ws, count, 0, st));
         else
-            CU(cm_launch_factor_flow(h->m, h->L, ws, count, h->variant & 1, h->variant >= 4 ? 1 : 0, st));
+        {
+            // variant -> CTA configuration of the dataflow kernel (0 automatic, 1: 8 warps, 2: 4 warps, 3: 16 warps)
+            const int cfg = h->variant == 1 ? 0 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2));
+            CU(cm_launch_factor_flow(h->m, h->L, ws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, st));
+        }
         if (h->timing) CU(cudaEventRecord(h->ev[2], st));
         CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
         h->launches += 3;

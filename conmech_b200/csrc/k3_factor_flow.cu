@@ -116,7 +116,7 @@ __device__ __noinline__ void diag_update(double *tiles, const double *dpiv, int 
 }
 
 template <int NW, bool PROF>
-__global__ void __launch_bounds__(NW * 32, 16 / NW)
+__global__ void __launch_bounds__(NW * 32, NW <= 16 ? 16 / NW : 1)
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
@@ -228,10 +228,26 @@ static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, cha
     return cudaGetLastError();
 }
 
-// config: 0 = 4 warps x 4 CTAs/SM (default), 1 = 8 warps x 2 CTAs/SM
+// config: 0 = automatic, 1 = 8 warps x 2 CTAs/SM, 2 = 4 warps x 4 CTAs/SM, 3 = 16 warps x 1 CTA/SM.
+// Automatic: four small CTAs per SM hide the serial chain of a subset behind other subsets and are
+// best whenever the launch fills the GPU; a launch with few subsets of a wide band (the 10k-element
+// frames) instead needs its parallelism INSIDE the subset - more tile rows in flight per CTA.
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                                   int config, int prof, cudaStream_t st) {
+    if (config == 0) {
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (n_sm <= 0) n_sm = 148;
+        }
+        config = 2;
+        if (count <= 2 * n_sm && m.band_tiles > 8) config = 1;
+        if (count <= n_sm && m.band_tiles > 16) config = 3;
+    }
     if (config == 1) return prof ? launch_flow<8, true>(m, L, ws, count, st) : launch_flow<8, false>(m, L, ws, count, st);
+    if (config == 3) return launch_flow<16, false>(m, L, ws, count, st);
     return prof ? launch_flow<4, true>(m, L, ws, count, st) : launch_flow<4, false>(m, L, ws, count, st);
 }
 

@@ -235,8 +235,9 @@ class CudaStiffness(StiffnessBase):
         return (self._trans_tol, self._rot_tol)
 
     def set_factor_variant(self, variant):
-        """2 = FP64 tensor-core factorisation with 4-warp CTAs (default), 3 = 8-warp CTAs, 4 / 5 = the
-        same two with activity cycle counters, 0 = scalar validation variant."""
+        """1 = FP64 tensor-core factorisation, CTA size chosen per launch (default); 2 / 3 / 6 = pinned to
+        4 / 8 / 16-warp CTAs; 4 / 5 = 4 / 8-warp CTAs with activity cycle counters; 0 = scalar
+        validation variant."""
         _capi.check(self._lib.cm_set_variant(self._handle, int(variant)))
 
     # ------------------------------------------------------------------ batched solves

@@ -130,11 +130,12 @@ typedef struct cm_solve_out {
                           /*                of the factorisation, one multiply-add counted as 2)  */
 } cm_solve_out;
 
-/* Factorisation kernel variant: 2 (default) = FP64 tensor-core block-band LDL^T, dataflow
- * kernel (csrc/k3_factor_flow.cu) with 4-warp CTAs, 3 = the same with 8-warp CTAs, 4 / 5 = those
- * two instrumented with per-activity cycle counters, 0 = scalar validation variant of the same
- * algorithm (csrc/k3_factor.cu; slow, used by the parity tests to cross-check the tensor-core
- * path). */
+/* Factorisation kernel variant: 1 (default) = FP64 tensor-core block-band LDL^T, dataflow
+ * kernel (csrc/k3_factor_flow.cu), CTA size chosen per launch (4 warps x 4 CTAs/SM when the
+ * launch fills the GPU, 8 or 16 warps per subset for few subsets of a wide band); 2 / 3 / 6 = the
+ * same kernel pinned to 4 / 8 / 16-warp CTAs; 4 / 5 = 4 / 8-warp CTAs instrumented with
+ * per-activity cycle counters; 0 = scalar validation variant of the same algorithm
+ * (csrc/k3_factor.cu; slow, used by the parity tests to cross-check the tensor-core path). */
 int cm_set_variant(cm_handle *h, int32_t variant);
 
 /* Development aid: after a solve with variant 4 or 5, reads and clears the 16 activity counters

@@ -71,7 +71,7 @@ def check_against_oracle(eng, orc, subsets, r, lc=0, tag=''):
     return n_marginal
 
 
-@pytest.mark.parametrize('variant', [2, 0], ids=['mma', 'scalar'])
+@pytest.mark.parametrize('variant', [1, 2, 6, 0], ids=['auto', 'w4', 'w16', 'scalar'])
 @pytest.mark.parametrize('name', golden_names())
 def test_golden_cases(name, variant):
     g = Golden(name)

@@ -15,6 +15,8 @@ masks = syn.pack_masks([syn.connected_subset(model, s) for s in range(B)], len(m
 print('sampler {:.1f} s'.format(time.time() - t0))
 dm = torch.from_numpy(masks.view(np.int32)).cuda()
 eng.enable_timing(True)
+if len(sys.argv) > 2:
+    eng.set_factor_variant(int(sys.argv[2]))
 for rep in range(2):
     r = eng.solve_many_device(dm, want=('flag', 'status', 'max_trans', 'profile_flops'), max_in_flight=B)
     torch.cuda.synchronize()

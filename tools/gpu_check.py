@@ -20,7 +20,7 @@ ALL = ('flag', 'status', 'n_free', 'n_fixed', 'dof_map', 'node_exists', 'U', 'Rf
        'max_trans', 'max_rot', 'min_pivot')
 
 
-def compare(name, variants=(2, 3, 0)):
+def compare(name, variants=(1, 6, 0)):
     g = Golden(name)
     model = g.model()
     lc = g.loadcase(model)
