@@ -533,12 +533,15 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
         h->stage_bytes = off;
     }
     // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
-    size_t freeb = 0, totalb = 0;
-    CU(cudaMemGetInfo(&freeb, &totalb));
+    // (the driver is only asked about free memory when the workspace has to grow)
     const size_t per = h->L.per_subset;
     size_t want = std::min<size_t>(Bn, 4096) * per;
-    size_t cap = (freeb + h->ws_bytes) / 2;
-    if (want > cap) want = std::max(per, cap / per * per);
+    if (want > h->ws_bytes) {
+        size_t freeb = 0, totalb = 0;
+        CU(cudaMemGetInfo(&freeb, &totalb));
+        size_t cap = (freeb + h->ws_bytes) / 2;
+        if (want > cap) want = std::max(per, cap / per * per);
+    }
     if (want > h->ws_bytes) {
         if (h->wsbuf) cudaFree(h->wsbuf);
         h->wsbuf = nullptr; h->ws_bytes = 0;
