@@ -264,9 +264,14 @@ def main():
         eng.solve_many(host_np[k % n_batches], want=want, out=out_host)
     barrier()
     t0 = time.perf_counter()
+    step_times = []
     for k in range(args.steps):
+        ts = time.perf_counter()
         eng.solve_many(host_np[(args.warmup + k) % n_batches], want=want, out=out_host)
+        step_times.append(time.perf_counter() - ts)
     e2e_s = time.perf_counter() - t0
+    if os.environ.get('CM_BENCH_DEBUG'):
+        sys.stderr.write('rank {} e2e step ms {}\n'.format(rank, ['{:.1f}'.format(1e3 * x) for x in step_times]))
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
