@@ -395,6 +395,7 @@ class CudaStiffness(StiffnessBase):
 
     # ---- procedural data
     def _element_loads(self, lc=0):
+        self._push_loads()
         q = np.zeros((self.nE, 12))
         _capi.check(self._lib.cm_get_element_loads(self._handle, lc, _ptr(q)))
         return q

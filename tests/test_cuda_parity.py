@@ -362,3 +362,37 @@ def test_solve_sequence_and_from_data():
     U = g2.extra('stored_U').reshape(-1, 6)
     for nid, nd in rd['nodal_displacement'].items():
         assert np.max(np.abs(np.array(nd) - U[nid])) <= 1e-9 * np.abs(U).max()
+
+
+def test_config3_100k_subsets_properties():
+    """BASELINE config 3 at its FULL size - 100 000 random connected subsets of the 1k-element frame -
+    through properties that need no oracle: every subset solves (status OK), the vertical support
+    reactions balance the self weight of exactly the existing elements (1e-9 relative), flags equal
+    (max_trans < tol), compliance is positive; plus the oracle on a sample of the same batch."""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(7, 7, 8)
+    tol = 5e-2
+    sc, orc = make_pair(model, LoadCase(gravity_load=GravityLoad([0, 0, -1])), trans_tol=tol)
+    eng = sc._sc_ins
+    nE = len(model.elements)
+    B, chunk = 100000, 5000
+    q = eng._element_loads(0)
+    wz = q[:, 2] + q[:, 8]                                    # vertical lumped self weight per element
+    n_true = 0
+    for c0 in range(0, B, chunk):
+        subsets = [syn.connected_subset(model, s) for s in range(c0, c0 + chunk)]
+        masks = syn.pack_masks(subsets, nE)
+        r = eng.solve_many(masks, want=('flag', 'status', 'Rf', 'max_trans', 'compliance'))
+        assert (r['status'] == ST_OK).all()
+        bits = np.unpackbits(masks.view(np.uint8), axis=1, bitorder='little')[:, :nE].astype(np.float64)
+        weight = bits @ wz
+        rz = r['Rf'][:, 0].reshape(chunk, -1, 6)[:, :, 2].sum(axis=1)
+        assert np.max(np.abs(rz + weight) / np.abs(weight)) <= 1e-9
+        assert_array_equal(r['flag'][:, 0].astype(bool), r['max_trans'][:, 0] < tol)
+        assert (r['compliance'] > 0).all()
+        n_true += int(r['flag'].sum())
+        if c0 == 0:
+            sample = list(range(0, chunk, chunk // 16))
+            rs = eng.solve_many([subsets[b] for b in sample], want=ALL)
+            check_against_oracle(eng, orc, [subsets[b] for b in sample], rs, tag='g1k-100k-sample')
+    assert 0 < n_true < B
