@@ -33,6 +33,16 @@ __host__ __device__ __forceinline__ int cm_tile_off(int r, int k) {
     return ((k >> 2) << 7) + ((((r & 7) << 2) + (k & 3)) << 2) + (r >> 3);
 }
 
+// Element (r,k) of a lower-triangular M_J = D_J^-1 L_JJ^-1 tile, "Mq" order: [r/8][k/8][lane][k%2]
+// with lane = 4*(r%8) + (k%8)/2.  As the B operand of the solve product L(I,J) = acc * M_J^T taken
+// straight from accumulator registers (k-slot t of k-step (cj,e) <-> column 8cj + 2t + e, which is
+// where the accumulator fragment of that lane already sits), the two fragments a lane needs for
+// output block r/8 and k-block cj are one 16-byte vector; blocks above the diagonal are never
+// stored or read.  tools/frag_emulator.py checks these maps lane by lane.
+__host__ __device__ __forceinline__ int cm_mtile_off(int r, int k) {
+    return ((r >> 3) << 8) + ((k >> 3) << 6) + ((((r & 7) << 2) + ((k & 7) >> 1)) << 1) + (k & 1);
+}
+
 // Model tables on the device (all sizes fixed at cm_create).
 struct cm_model_dev {
     int nV, nE, nS, n_lc;
@@ -76,7 +86,7 @@ struct cm_ws_layout {
     size_t off_x;          // double [n_lc*n_pad] rhs -> forward solution -> solution
     size_t off_p;          // double [n_lc*6nV] full load vector, DOF order
     size_t off_kfirst;     // int    [n_tile_rows_max] first tile column in the envelope
-    size_t off_minv;       // double [n_tile_rows_max*1024] M_J = D_J^-1 L_JJ^-1 per diagonal tile (tile layout)
+    size_t off_minv;       // double [n_tile_rows_max*1024] M_J = D_J^-1 L_JJ^-1 per diagonal tile (cm_mtile_off layout)
     size_t off_aflag;      // uchar  [n_tile_rows_max*band_tiles] 1: the tile holds entries of K_mm (assembled by K2);
                            //        0: structurally empty before fill-in, its storage is NOT initialised
     size_t off_kcol;       // int    [n_tile_rows_max] first nonzero column of the tile row, in k-steps of 4

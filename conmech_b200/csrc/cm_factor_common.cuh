@@ -40,16 +40,20 @@ __device__ __forceinline__ double dneg(double x) {       // sign flip on the int
 // instructions than an unblocked elimination - this routine is the critical path of every tile row.
 // A pivot that violates the reference's rules (exact zero raises in SuperLU: numpy_stiffness.py:
 // 301-319; <= -1e-14 is rejected: :326-336; NaN fails both) sets *s_fail and is replaced by 1.
-__device__ __noinline__ void diag_factor_blk(const double *T, double *Mg, double *dg, double *scr, int lane,
+// in_smem: the lower blocks of the tile were already placed in scr (row stride DS) by
+// diag_newest_to_smem(); otherwise the tile is read from T.
+__device__ __noinline__ void diag_factor_blk(const double *T, bool in_smem, double *Mg, double *dg, double *scr, int lane,
                                              int *s_fail, double *s_minpiv_w) {
     double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
     const int g = lane >> 2, t = lane & 3;
+    if (!in_smem) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        double v[4];
-        ldg4(v, T + q * 128 + lane * 4);
+        for (int q = 0; q < 8; ++q) {
+            double v[4];
+            ldg4(v, T + q * 128 + lane * 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sA[(8 * i + g) * DS + 4 * q + t] = v[i];
+            for (int i = 0; i < 4; ++i) sA[(8 * i + g) * DS + 4 * q + t] = v[i];
+        }
     }
     __syncwarp();
     int fail = 0;
@@ -149,66 +153,78 @@ __device__ __noinline__ void diag_factor_blk(const double *T, double *Mg, double
         }
         __syncwarp();
     }
-    // ---- M = D^-1 X to global memory, tile layout (blocks above the diagonal are zero)
+    // ---- M = D^-1 X to global memory, cm_mtile_off layout (blocks above the diagonal are not stored)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        double v[4];
+    for (int i = 0; i < 4; ++i) {
+        const double ri = s_rinv[8 * i + g];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            v[i] = ((q >> 1) <= i) ? sB[(8 * i + g) * DS + 4 * q + t] * s_rinv[8 * i + g] : 0.0;
-        stg4(Mg + q * 128 + lane * 4, v[0], v[1], v[2], v[3]);
+        for (int cj = 0; cj <= i; ++cj) {
+            const double2 x = *reinterpret_cast<const double2 *>(sB + (8 * i + g) * DS + 8 * cj + 2 * t);
+            asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(Mg + i * 256 + cj * 64 + lane * 2), "d"(x.x * ri), "d"(x.y * ri) : "memory");
+        }
     }
     __syncwarp();
 }
 
-// forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - sum_K L(J,K) y_K)
-__device__ __noinline__ void forward_row_w(const double *tiles, const double *minv, const double *dpiv, double *X,
-                                           double *s_r, int n_pad, int n_lc, int zero_bits, int bt, int J, int kcJ,
-                                           int lane) {
+// Newest term of the diagonal tile straight from the registers of R = L(I,I-1) (just solved):
+// lower blocks of  D(I,I) - R diag(d) R^T,  D(I,I) read from Dg (global, tile layout, older terms
+// already applied), result written to the diagonal scratch sA (row stride DS) where
+// diag_factor_blk() continues - the chain tile -> diagonal tile hand-over never touches global
+// memory.  Both MMA operands are register fragments of R: k-slot t of k-step (cs,e) is column
+// 8cs + 2t + e, the A fragment of row block ri is r.c[cs][e][ri] and the B fragment of output
+// column block cj is d_k * r.c[cs][e][cj] of the same lane.
+__device__ __forceinline__ void diag_newest_to_smem(const TileAcc &r, const double *Dg, const double *dJ, double *sA, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const double *pc = Dg + acc_cbase(lane);
+    double2 dk[4];
+#pragma unroll
+    for (int cs = 0; cs < 4; ++cs) dk[cs] = ldg2(dJ + cs * 8 + 2 * t);
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        double c0[4], c1[4];
+        ldg4(c0, pc + cj * 256);
+        ldg4(c1, pc + cj * 256 + 4);
+#pragma unroll
+        for (int cs = 0; cs < 4; ++cs) {
+            const double nb0 = -(dk[cs].x * r.c[cs][0][cj]);
+            const double nb1 = -(dk[cs].y * r.c[cs][1][cj]);
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+                if (ri >= cj) dmma_m8n8k4(c0[ri], c1[ri], r.c[cs][0][ri], nb0);
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+                if (ri >= cj) dmma_m8n8k4(c0[ri], c1[ri], r.c[cs][1][ri], nb1);
+        }
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+            if (ri >= cj) *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t) = make_double2(c0[ri], c1[ri]);
+    }
+}
+
+// forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - s_J), where
+// s_J = sum_K L(J,K) y_K was accumulated tile by tile (acc_matvec) into s_part while the tiles of
+// the row were still in registers - the row of L is not read again.
+__device__ __noinline__ void forward_row_w(const double *minv, const double *dpiv, double *X, const double *s_part,
+                                           double *s_r, int n_pad, int n_lc, int zero_bits, int J, int lane) {
     const int g = lane >> 2, tt = lane & 3;
-    const double *Mj = minv + (size_t)J * CM_TILE_ELEMS + lane * 4;
+    const double *pm = minv + (size_t)J * CM_TILE_ELEMS + lane * 2;
     for (int lc = 0; lc < n_lc; ++lc) {
         if ((zero_bits >> lc) & 1) continue;
         double *Xl = X + (size_t)lc * n_pad;
-        double part[4] = {0.0, 0.0, 0.0, 0.0};
-        const double *Ljk = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)kcJ * 128 + lane * 4;
-        const double *yk = Xl + kcJ * 4 + tt;
-        const int nst = J * 8 - kcJ;
-#pragma unroll 4
-        for (int q = 0; q < nst; ++q) {
-            double v[4];
-            ldg4(v, Ljk + q * 128);
-            const double y = yk[q * 4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) part[i] += v[i] * y;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1);
-            part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2);
-        }
-        if (tt == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s_r[i * 8 + g] = Xl[J * CM_TILE + i * 8 + g] - part[i];
-        }
+        s_r[lane] = Xl[J * CM_TILE + lane] - s_part[lc * 32 + lane];
         __syncwarp();
-        double zp[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            double v[4];
-            ldg4(v, Mj + q * 128);
-            const double rr = s_r[q * 4 + tt];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) zp[i] += v[i] * rr;
-        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 1);
-            zp[i] += __shfl_xor_sync(0xffffffffu, zp[i], 2);
-        }
-        if (tt == 0) {
+            double zp = 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) Xl[J * CM_TILE + i * 8 + g] = dpiv[J * CM_TILE + i * 8 + g] * zp[i];
+            for (int cj = 0; cj <= i; ++cj) {
+                const double2 b = ldg2(pm + i * 256 + cj * 64);
+                const double2 rr = *reinterpret_cast<const double2 *>(s_r + cj * 8 + 2 * tt);
+                zp += b.x * rr.x + b.y * rr.y;
+            }
+            zp += __shfl_xor_sync(0xffffffffu, zp, 1);
+            zp += __shfl_xor_sync(0xffffffffu, zp, 2);
+            if (tt == 0) Xl[J * CM_TILE + i * 8 + g] = dpiv[J * CM_TILE + i * 8 + g] * zp;
         }
         __syncwarp();
     }

@@ -30,6 +30,11 @@ __device__ __forceinline__ void stg4(double *p, double a, double b, double c, do
     asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
     asm volatile("st.global.v2.f64 [%0+16], {%1,%2};" :: "l"(p), "d"(c), "d"(d) : "memory");
 }
+__device__ __forceinline__ double2 ldg2(const double *p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void lds4(double (&v)[4], const double *p) {
     const double2 x = reinterpret_cast<const double2 *>(p)[0];
     const double2 y = reinterpret_cast<const double2 *>(p)[1];
@@ -124,25 +129,48 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
     }
 }
 
-// acc = A * Ms^T for one 32x32 tile A in global memory and Ms in shared memory, both in tile
-// layout (used as L(I,J) = acc(I,J) * (D_J^-1 L_JJ^-1)^T, the triangular solve as a product).
-__device__ __forceinline__ void acc_mul_smem(TileAcc &acc, const double *__restrict__ A,
-                                             const double *__restrict__ Ms, int lane) {
-    const double *pa = A + lane * 4;
-    const double *pb = Ms + lane * 4;
-    double a0[4], b0[4], a1[4], b1[4];
-    ldg4(a0, pa);
-    lds4(b0, pb);
+// acc <- acc * M^T in place, M = D_J^-1 L_JJ^-1 lower triangular in the cm_mtile_off layout (the
+// triangular solve of an off-diagonal tile as a tile product).  The accumulator fragments ARE the A
+// operand: k-slot t of k-step (cj,e) stands for column 8cj + 2t + e, which is exactly the element
+// c[cj][e][ri] this lane already holds, so the tile never leaves the registers between its update
+// stream and its solve.  Output block column co only needs the inputs cj <= co: going from the right,
+// every finished block overwrites an input block that is dead.  Columns left of block cj0 are zero.
+__device__ __forceinline__ void acc_solve_inplace(TileAcc &acc, const double *__restrict__ Mq, int cj0, int lane) {
+    const double *pm = Mq + lane * 2;
 #pragma unroll
-    for (int q = 0; q < 8; q += 2) {
-        ldg4(a1, pa + 128);
-        lds4(b1, pb + 128);
-        frag_mma<false>(acc, a0, b0);
-        pa += 256; pb += 256;
-        if (q + 2 < 8) {
-            ldg4(a0, pa);
-            lds4(b0, pb);
+    for (int co = 3; co >= 0; --co) {
+        double r0[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
+        double2 b[4];
+#pragma unroll
+        for (int cj = 0; cj <= co; ++cj) b[cj] = ldg2(pm + co * 256 + cj * 64);
+#pragma unroll
+        for (int cj = 0; cj <= co; ++cj) {
+            if (cj < cj0) continue;
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) dmma_m8n8k4(r0[ri], r1[ri], acc.c[cj][0][ri], b[cj].x);
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) dmma_m8n8k4(r0[ri], r1[ri], acc.c[cj][1][ri], b[cj].y);
         }
-        frag_mma<false>(acc, a1, b1);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) { acc.c[co][0][ri] = r0[ri]; acc.c[co][1][ri] = r1[ri]; }
+    }
+}
+
+// partial forward substitution of one finished tile R = L(I,J):  out[ri] = (R y)[ri*8 + lane/4]
+// (valid on every lane), y = the 32 forward-solved values of block J.
+__device__ __forceinline__ void acc_matvec(const TileAcc &r, const double *__restrict__ y, double (&out)[4], int lane) {
+    const double *py = y + 2 * (lane & 3);
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) out[ri] = 0.0;
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        const double2 yy = ldg2(py + cj * 8);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) out[ri] += r.c[cj][0][ri] * yy.x + r.c[cj][1][ri] * yy.y;
+    }
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        out[ri] += __shfl_xor_sync(0xffffffffu, out[ri], 1);
+        out[ri] += __shfl_xor_sync(0xffffffffu, out[ri], 2);
     }
 }

@@ -101,7 +101,7 @@ k3_factor_scalar(cm_model_dev m, cm_ws_layout L, char *ws) {
                         double s = (r == lane) ? 1.0 : 0.0;
                         for (int k = 0; k < r; ++k) s -= s_Ljj[r * LDS + k] * x[k];
                         x[r] = s;
-                        Mj[cm_tile_off(r, lane)] = s / s_dj[r];
+                        Mj[cm_mtile_off(r, lane)] = s / s_dj[r];
                     }
                     if (lane == 0) { s_minpiv = mp; if (fail) s_fail = 1; }
                 }

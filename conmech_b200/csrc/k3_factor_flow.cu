@@ -35,74 +35,65 @@ __device__ unsigned long long g_flow_prof[16];
 #define FP_T0(pc) long long _t0 = (pc) ? clock64() : 0
 #define FP_ADD(pc, slot) do { if (pc) { long long _n = clock64(); if ((threadIdx.x & 31) == 0) (pc)[slot] += _n - _t0; _t0 = _n; } } while (0)
 
-// acc = A * M^T for 32x32 tiles A and M in global memory, tile layout; the columns of A left of
-// k-step q0 (even) are zero and skipped.  M is lower triangular, so k-step q only reaches the
-// output column blocks cj >= q/2: 80 MMAs instead of 128.
-__device__ __forceinline__ void acc_mul_glob(TileAcc &acc, const double *__restrict__ A,
-                                             const double *__restrict__ M, int q0, int lane) {
-    const double *pa = A + lane * 4;
-    const double *pb = M + lane * 4;
-    double a[2][4], b[2][4];
-    ldg4(a[0], pa + q0 * 128);
-    ldg4(b[0], pb + q0 * 128);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (q < q0) continue;
-        const int cur = q & 1;
-        if (q + 1 < 8) {
-            ldg4(a[cur ^ 1], pa + (q + 1) * 128);
-            ldg4(b[cur ^ 1], pb + (q + 1) * 128);
-        }
-#pragma unroll
-        for (int ri = 0; ri < 4; ++ri)
-#pragma unroll
-            for (int cj = 0; cj < 4; ++cj)
-                if (cj >= (q >> 1)) dmma_m8n8k4(acc.c[cj][0][ri], acc.c[cj][1][ri], a[cur][ri], b[cur][cj]);
-    }
-}
-
-// tile (I,J), J < I: all update terms as they become available, then the solve against M_J
-__device__ __noinline__ void offdiag_tile(double *tiles, const double *minv, const double *dpiv, const int *kcol,
-                                          const unsigned char *aflag, volatile int *prog, int bt, int I, int J,
-                                          int kcI, int lane, long long *pc, volatile long long *tpub) {
+// tile (I,J), J < I: all update terms as they become available, then - still in registers - the
+// solve against M_J, the tile's share of the forward substitution and, for the chain tile
+// (J == I-1), the newest term of the diagonal tile, handed to the diagonal factorisation through
+// the shared scratch.  Returns true when the diagonal tile was placed in the scratch.
+__device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, const double *dpiv, const double *X,
+                                          const int *kcol, const unsigned char *aflag, volatile int *prog,
+                                          volatile int *yprog, int bt, int I, int J, int kcI, int n_pad, int n_lc,
+                                          int zero_bits, double *s_part, double *s_scr, int lane, long long *pc,
+                                          volatile long long *tpub) {
     double *T = cm_tile_ptr(tiles, bt, I, J);
     const bool has_a = aflag[I * bt + (J - I + bt - 1)] != 0;      // K2 assembled entries into this tile
     // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
     int qs = max(kcI, kcol[J]);
     int K = qs >> 3;
     FP_T0(pc);
+    TileAcc acc;
     if (K >= J && !has_a) {                       // no entries and no fill-in: the tile of L is zero
-        TileAcc z;
-        acc_zero(z);
-        acc_store(z, T, lane);
-        return;
-    }
-    if (K < J) {
-        TileAcc acc;
-        if (has_a) acc_load(acc, T, lane); else acc_zero(acc);
-        while (K < J) {
-            const int Kend = min(wait_prog_gt(prog, J, K), J);
-            FP_ADD(pc, 0);
-            const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
-            const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
-            acc_update_stream<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
-            K = Kend;
-            qs = K * 8;
-            FP_ADD(pc, 1);
-        }
+        acc_zero(acc);
         acc_store(acc, T, lane);
-        __syncwarp();
+        return false;
+    }
+    if (has_a) acc_load(acc, T, lane); else acc_zero(acc);
+    while (K < J) {
+        const int Kend = min(wait_prog_gt(prog, J, K), J);
+        FP_ADD(pc, 0);
+        const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
+        const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
+        acc_update_stream<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
+        K = Kend;
+        qs = K * 8;
         FP_ADD(pc, 1);
     }
     wait_prog_gt(prog, J, J);                     // M_J published
     FP_ADD(pc, 2);
     if (pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *tpub;     // reaction gap on the chain
-    TileAcc r;
-    acc_zero(r);
-    const int q0 = max(kcI - 8 * J, 0);            // leading zero columns of the row's first tile
-    acc_mul_glob(r, T, minv + (size_t)J * CM_TILE_ELEMS, q0, lane);
-    acc_store(r, T, lane);
+    acc_solve_inplace(acc, minv + (size_t)J * CM_TILE_ELEMS, max(kcI - 8 * J, 0) >> 1, lane);
+    acc_store(acc, T, lane);
     if (pc && J == I - 1) FP_ADD(pc, 10); else FP_ADD(pc, 3);
+    // share of this tile in the forward substitution of row I:  s_I += L(I,J) y_J
+    {
+        int y = *yprog;
+        while (y <= J) { __nanosleep(40); y = *yprog; }
+        __threadfence_block();
+    }
+    FP_ADD(pc, 7);
+    for (int lc = 0; lc < n_lc; ++lc) {
+        if ((zero_bits >> lc) & 1) continue;
+        double part[4];
+        acc_matvec(acc, X + (size_t)lc * n_pad + J * CM_TILE, part, lane);
+        if ((lane & 3) == 0) {
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) s_part[lc * 32 + ri * 8 + (lane >> 2)] += part[ri];
+        }
+    }
+    FP_ADD(pc, 8);
+    if (J != I - 1) return false;
+    diag_newest_to_smem(acc, cm_tile_ptr(tiles, bt, I, I), dpiv + J * CM_TILE, s_scr, lane);
+    FP_ADD(pc, 11);
+    return true;
 }
 
 // diagonal tile (I,I) -= sum over k-steps [q0, q1) of the own (final) row:  L(I,k) d_k L(I,k)^T
@@ -121,7 +112,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
     double *s_rhs = s_scr + DSCR;                                    // [NW][32] forward substitution scratch
-    double *s_minpiv = s_rhs + NW * 32;                              // [NW]
+    double *s_part = s_rhs + NW * 32;                                // [NW][n_lc][32] pending forward sums of the rows in progress
+    double *s_minpiv = s_part + NW * m.n_lc * 32;                    // [NW]
     int *s_prog = reinterpret_cast<int *>(s_minpiv + NW);            // [n_tile_rows_max] factor progress
     int *s_yprog = s_prog + m.n_tile_rows_max;                       // rows forward-substituted
     int *s_fail = s_yprog + 1;
@@ -154,31 +146,30 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     long long *pc = PROF ? s_pc[warp] : nullptr;
     if (PROF && lane == 0) for (int i = 0; i < 16; ++i) pc[i] = 0;
     const long long tstart = PROF ? clock64() : 0;
+    double *s_part_w = s_part + warp * n_lc * 32;
     for (int I = warp; I < NT; I += NW) {
         const int kfI = kfirst[I];
         const int kcI = kcol[I];                 // first nonzero column of the row in k-steps (even), kcI / 8 == kfI
+        for (int lc = 0; lc < n_lc; ++lc) s_part_w[lc * 32 + lane] = 0.0;
+        __syncwarp();
+        bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
         for (int J = kfI; J < I; ++J) {
             if (J == I - 1 && I - 2 >= kfI) {    // look-ahead: diagonal terms that do not need row I-1
                 FP_T0(pc);
                 diag_update(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            offdiag_tile(tiles, minv, dpiv, kcol, aflag, prog, bt, I, J, kcI, lane, pc, &s_tpub);
+            handed = offdiag_tile(tiles, minv, dpiv, X, kcol, aflag, prog, yprog, bt, I, J, kcI, L.n_pad, n_lc,
+                                  zero_bits, s_part_w, s_scr, lane, pc, &s_tpub);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
         }
         FP_T0(pc);
-        if (I > kfI) {                           // newest diagonal term (or all of them without look-ahead)
-            const int q0 = (I - 2 >= kfI) ? 8 * (I - 1) : kcI;
-            diag_update(tiles, dpiv, bt, I, q0, 8 * I, lane);
-        }
-        __syncwarp();
-        FP_ADD(pc, 11);
-        if (I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
+        if (!handed && I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
         FP_ADD(pc, 5);
-        diag_factor_blk(cm_tile_ptr(tiles, bt, I, I), minv + (size_t)I * CM_TILE_ELEMS, dpiv + I * CM_TILE, s_scr, lane,
-                        s_fail, s_minpiv + warp);
+        diag_factor_blk(cm_tile_ptr(tiles, bt, I, I), handed, minv + (size_t)I * CM_TILE_ELEMS, dpiv + I * CM_TILE, s_scr,
+                        lane, s_fail, s_minpiv + warp);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) { if (PROF) s_tpub = clock64(); prog[I] = I + 1; }
@@ -190,7 +181,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
             __threadfence_block();
         }
         FP_ADD(pc, 7);
-        forward_row_w(tiles, minv, dpiv, X, s_rhs + warp * 32, L.n_pad, n_lc, zero_bits, bt, I, kcI, lane);
+        forward_row_w(minv, dpiv, X, s_part_w, s_rhs + warp * 32, L.n_pad, n_lc, zero_bits, I, lane);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *yprog = I + 1;
@@ -210,7 +201,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
 }
 
 size_t flow_smem(const cm_model_dev &m, int nw) {
-    return (size_t)(DSCR + nw * 32 + nw) * sizeof(double) + (size_t)(m.n_tile_rows_max + 4) * sizeof(int);
+    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw) * sizeof(double) + (size_t)(m.n_tile_rows_max + 4) * sizeof(int);
 }
 
 }  // namespace

@@ -33,6 +33,32 @@ __device__ __forceinline__ void tile_tmatvec(const double *__restrict__ T, const
     }
 }
 
+// x = M^T w for a lower-triangular M_J tile in the cm_mtile_off layout: cs[2cj + e] (valid on lanes
+// 0..3) = column 8cj + 2*lane + e.  Only the stored blocks (row block >= column block) are read.
+__device__ __forceinline__ void mtile_tmatvec(const double *__restrict__ M, const double (&w4)[4], double (&cs)[8], int lane) {
+    const double *p = M + lane * 2;
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int i = cj; i < 4; ++i) {
+            const double2 b = ldg2(p + i * 256 + cj * 64);
+            sx += b.x * w4[i];
+            sy += b.y * w4[i];
+        }
+        cs[2 * cj] = sx;
+        cs[2 * cj + 1] = sy;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 4);
+        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
+        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
+    }
+}
+// where mtile_tmatvec leaves column q of its result: block 8*(q/2), lane pair 2*lane, parity q%2
+__device__ __forceinline__ int mcol(int q, int lane) { return ((q >> 1) << 3) + 2 * lane + (q & 1); }
+
 // NaN-propagating max (np.max semantics)
 __device__ __forceinline__ double nanmax(double a, double b) {
     if (a != a) return a;
@@ -128,11 +154,11 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                 double w4[4], cs[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) w4[i] = dpiv[I * CM_TILE + i * 8 + g] * Xl[I * CM_TILE + i * 8 + g];
-                tile_tmatvec(minv + (size_t)I * CM_TILE_ELEMS, w4, cs, lane);
+                mtile_tmatvec(minv + (size_t)I * CM_TILE_ELEMS, w4, cs, lane);
                 __syncwarp();
                 if (lane < 4)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) Xl[I * CM_TILE + q * 4 + lane] = cs[q];
+                    for (int q = 0; q < 8; ++q) Xl[I * CM_TILE + mcol(q, lane)] = cs[q];
             }
             for (int I = NT - 1; I > 0; --I) {
                 // M_{I-1} is needed at the end of this row's chain: start its DRAM read now
@@ -157,11 +183,11 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                         double w4[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) w4[i] = dpiv[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
-                        tile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
+                        mtile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
                         __syncwarp();
                         if (lane < 4)
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + q * 4 + lane] = cs[q];
+                            for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + mcol(q, lane)] = cs[q];
                     }
                 }
                 if (kf > I - 1 && warp == 0) {
@@ -170,11 +196,11 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     double w4[4], cs[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) w4[i] = dpiv[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
-                    tile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
+                    mtile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
                     __syncwarp();
                     if (lane < 4)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + q * 4 + lane] = cs[q];
+                        for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + mcol(q, lane)] = cs[q];
                 }
             }
             __syncthreads();
