@@ -59,7 +59,7 @@ __device__ __noinline__ void diag_factor_blk(const double *T, bool in_smem, doub
     int fail = 0;
     double minpiv = *s_minpiv_w;
     double dmine = 1.0, rmine = 1.0;
-#pragma unroll
+#pragma unroll 1                     // code size: the kernel's working set must stay inside the instruction cache
     for (int b = 0; b < 4; ++b) {
         const int c0 = 8 * b;
         double p[8], pk[8];
@@ -92,9 +92,7 @@ __device__ __noinline__ void diag_factor_blk(const double *T, bool in_smem, doub
         __syncwarp();
         if (b < 3) {
             // trailing blocks (ri,cj), b < cj <= ri:  A -= (L D)(ri,b) L(cj,b)^T
-#pragma unroll
             for (int ri = b + 1; ri < 4; ++ri)
-#pragma unroll
                 for (int cj = b + 1; cj <= ri; ++cj) {
                     double2 cc = *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t);
 #pragma unroll

@@ -40,12 +40,19 @@ __device__ unsigned long long g_flow_prof[16];
 // (J == I-1), the newest term of the diagonal tile, handed to the diagonal factorisation through
 // the shared scratch.  Returns true when the diagonal tile was placed in the scratch.
 __device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, const double *dpiv, const double *X,
-                                          const int *kcol, const unsigned char *aflag, volatile int *prog,
+                                          const int *kcol, const unsigned long long *arow, volatile int *prog,
                                           volatile int *yprog, int bt, int I, int J, int kcI, int n_pad, int n_lc,
                                           int zero_bits, double *s_part, double *s_scr, int lane, long long *pc,
                                           volatile long long *tpub) {
     double *T = cm_tile_ptr(tiles, bt, I, J);
-    const bool has_a = aflag[I * bt + (J - I + bt - 1)] != 0;      // K2 assembled entries into this tile
+    const int ab = J - I + bt - 1, aw = (bt + 63) >> 6;
+    const bool has_a = (arow[I * aw + (ab >> 6)] >> (ab & 63)) & 1ull;         // K2 assembled entries into this tile
+    // the next tile of the row that K2 assembled (the diagonal tile always is) comes from DRAM: start that read now
+    if ((arow[I * aw + ((ab + 1) >> 6)] >> ((ab + 1) & 63)) & 1ull) {
+        const double *nx = T + CM_TILE_ELEMS + lane * 16;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(nx));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 512));
+    }
     // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
     int qs = max(kcI, kcol[J]);
     int K = qs >> 3;
@@ -117,6 +124,10 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     int *s_prog = reinterpret_cast<int *>(s_minpiv + NW);            // [n_tile_rows_max] factor progress
     int *s_yprog = s_prog + m.n_tile_rows_max;                       // rows forward-substituted
     int *s_fail = s_yprog + 1;
+    int *s_kcol = s_yprog + 4;                                       // [n_tile_rows_max] envelope: first nonzero k-step of each row
+    unsigned long long *s_arow = reinterpret_cast<unsigned long long *>(s_kcol + m.n_tile_rows_max);   // 8-byte aligned: 2n+4 ints after s_prog
+                                                                     // [n_tile_rows_max][aw] bit b: tile (I, I-bt+1+b) was assembled by K2
+    const int aw = (m.band_tiles + 63) >> 6;
     __shared__ long long s_pc[PROF ? NW : 1][16];
     __shared__ long long s_tpub;
 
@@ -138,7 +149,15 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     volatile int *prog = s_prog;
     volatile int *yprog = s_yprog;
 
-    for (int I = t; I < NT; I += NW * 32) s_prog[I] = kfirst[I];
+    for (int I = t; I < NT; I += NW * 32) {
+        s_prog[I] = kfirst[I];
+        s_kcol[I] = kcol[I];
+        for (int w = 0; w < aw; ++w) {
+            unsigned long long bits = 0;
+            for (int b = 64 * w; b < bt && b < 64 * w + 64; ++b) bits |= (unsigned long long)(aflag[I * bt + b] != 0) << (b & 63);
+            s_arow[I * aw + w] = bits;
+        }
+    }
     if (t == 0) { *s_yprog = 0; *s_fail = 0; }
     if (t < NW) s_minpiv[t] = __longlong_as_double(0x7ff0000000000000LL);
     __syncthreads();
@@ -148,8 +167,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     const long long tstart = PROF ? clock64() : 0;
     double *s_part_w = s_part + warp * n_lc * 32;
     for (int I = warp; I < NT; I += NW) {
-        const int kfI = kfirst[I];
-        const int kcI = kcol[I];                 // first nonzero column of the row in k-steps (even), kcI / 8 == kfI
+        const int kcI = s_kcol[I];               // first nonzero column of the row in k-steps (even)
+        const int kfI = kcI >> 3;                // = kfirst[I], the first tile column of the row
         for (int lc = 0; lc < n_lc; ++lc) s_part_w[lc * 32 + lane] = 0.0;
         __syncwarp();
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
@@ -159,7 +178,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
                 diag_update(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            handed = offdiag_tile(tiles, minv, dpiv, X, kcol, aflag, prog, yprog, bt, I, J, kcI, L.n_pad, n_lc,
+            handed = offdiag_tile(tiles, minv, dpiv, X, s_kcol, s_arow, prog, yprog, bt, I, J, kcI, L.n_pad, n_lc,
                                   zero_bits, s_part_w, s_scr, lane, pc, &s_tpub);
             __threadfence_block();
             __syncwarp();
@@ -201,7 +220,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
 }
 
 size_t flow_smem(const cm_model_dev &m, int nw) {
-    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw) * sizeof(double) + (size_t)(m.n_tile_rows_max + 4) * sizeof(int);
+    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw) * sizeof(double) +
+           (size_t)(2 * m.n_tile_rows_max + 8) * sizeof(int) + (size_t)m.n_tile_rows_max * ((m.band_tiles + 63) >> 6) * sizeof(unsigned long long);
 }
 
 }  // namespace
