@@ -32,13 +32,15 @@ namespace {
 // 9 total, 10 solve product of the chain tile (I,I-1), 11 newest diagonal term, 12 gap between the
 // publication of M_{I-1} and the owner of row I noticing it)
 __device__ unsigned long long g_flow_prof[16];
-#define FP_T0(pc) long long _t0 = (pc) ? clock64() : 0
-#define FP_ADD(pc, slot) do { if (pc) { long long _n = clock64(); if ((threadIdx.x & 31) == 0) (pc)[slot] += _n - _t0; _t0 = _n; } } while (0)
+// (PROF is a template parameter of every function that uses these: the production build carries no trace of them)
+#define FP_T0(pc) long long _t0 = (PROF && (pc)) ? clock64() : 0
+#define FP_ADD(pc, slot) do { if (PROF && (pc)) { long long _n = clock64(); if ((threadIdx.x & 31) == 0) (pc)[slot] += _n - _t0; _t0 = _n; } } while (0)
 
 // tile (I,J), J < I: all update terms as they become available, then - still in registers - the
 // solve against M_J, the tile's share of the forward substitution and, for the chain tile
 // (J == I-1), the newest term of the diagonal tile, handed to the diagonal factorisation through
 // the shared scratch.  Returns true when the diagonal tile was placed in the scratch.
+template <bool PROF>
 __device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, const double *dpiv, const double *X,
                                           const int *kcol, const unsigned long long *arow, volatile int *prog,
                                           volatile int *yprog, int bt, int I, int J, int kcI, int n_pad, int n_lc,
@@ -59,8 +61,8 @@ __device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, con
     FP_T0(pc);
     TileAcc acc;
     if (K >= J && !has_a) {                       // no entries and no fill-in: the tile of L is zero
-        acc_zero(acc);
-        acc_store(acc, T, lane);
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) stg4(T + i * 128 + lane * 4, 0.0, 0.0, 0.0, 0.0);
         return false;
     }
     if (has_a) acc_load(acc, T, lane); else acc_zero(acc);
@@ -76,10 +78,10 @@ __device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, con
     }
     wait_prog_gt(prog, J, J);                     // M_J published
     FP_ADD(pc, 2);
-    if (pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *tpub;     // reaction gap on the chain
+    if (PROF && pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *tpub;     // reaction gap on the chain
     acc_solve_inplace(acc, minv + (size_t)J * CM_TILE_ELEMS, max(kcI - 8 * J, 0) >> 1, lane);
     acc_store(acc, T, lane);
-    if (pc && J == I - 1) FP_ADD(pc, 10); else FP_ADD(pc, 3);
+    if (PROF && pc && J == I - 1) FP_ADD(pc, 10); else FP_ADD(pc, 3);
     // share of this tile in the forward substitution of row I:  s_I += L(I,J) y_J
     {
         int y = *yprog;
@@ -154,6 +156,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         s_kcol[I] = kcol[I];
         for (int w = 0; w < aw; ++w) {
             unsigned long long bits = 0;
+#pragma unroll 1
             for (int b = 64 * w; b < bt && b < 64 * w + 64; ++b) bits |= (unsigned long long)(aflag[I * bt + b] != 0) << (b & 63);
             s_arow[I * aw + w] = bits;
         }
@@ -178,7 +181,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
                 diag_update(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            handed = offdiag_tile(tiles, minv, dpiv, X, s_kcol, s_arow, prog, yprog, bt, I, J, kcI, L.n_pad, n_lc,
+            handed = offdiag_tile<PROF>(tiles, minv, dpiv, X, s_kcol, s_arow, prog, yprog, bt, I, J, kcI, L.n_pad, n_lc,
                                   zero_bits, s_part_w, s_scr, lane, pc, &s_tpub);
             __threadfence_block();
             __syncwarp();
