@@ -26,6 +26,14 @@ __device__ __forceinline__ void ldg4(double (&v)[4], const double *p) {
     asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
     asm volatile("ld.global.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
 }
+// streaming variant for the operand streams and the accumulator reads: the two 16-byte halves of a
+// lane's 32 bytes still meet in L1 (same sector), but the line is the first to be evicted, so the
+// small data that IS re-read through L1 (spilled registers, M_J, pivots, envelope) survives the
+// streams.
+__device__ __forceinline__ void ldg4s(double (&v)[4], const double *p) {
+    asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
+    asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void stg4(double *p, double a, double b, double c, double d) {
     asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
     asm volatile("st.global.v2.f64 [%0+16], {%1,%2};" :: "l"(p), "d"(c), "d"(d) : "memory");
@@ -64,8 +72,8 @@ __device__ __forceinline__ void acc_load(TileAcc &a, const double *T, int lane) 
     const double *p = T + acc_cbase(lane);
 #pragma unroll
     for (int cj = 0; cj < 4; ++cj) {
-        ldg4(a.c[cj][0], p + cj * 256);
-        ldg4(a.c[cj][1], p + cj * 256 + 4);
+        ldg4s(a.c[cj][0], p + cj * 256);
+        ldg4s(a.c[cj][1], p + cj * 256 + 4);
     }
 }
 
@@ -101,12 +109,12 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
     const double *pb = B + lane * 4;
     const double *pd = d + (lane & 3);
     double a0[4], b0[4], a1[4], b1[4], d0, d1;
-    ldg4(a0, pa);
-    if (!SYRK) ldg4(b0, pb);
+    ldg4s(a0, pa);
+    if (!SYRK) ldg4s(b0, pb);
     d0 = pd[0];
     for (int q = 0; q < nsteps; q += 2) {
-        ldg4(a1, pa + 128);
-        if (!SYRK) ldg4(b1, pb + 128);
+        ldg4s(a1, pa + 128);
+        if (!SYRK) ldg4s(b1, pb + 128);
         d1 = pd[4];
         {
             const double nd = -d0;
@@ -116,8 +124,8 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
         }
         pa += 256; pb += 256; pd += 8;
         if (q + 2 < nsteps) {
-            ldg4(a0, pa);
-            if (!SYRK) ldg4(b0, pb);
+            ldg4s(a0, pa);
+            if (!SYRK) ldg4s(b0, pb);
             d0 = pd[0];
         }
         {
