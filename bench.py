@@ -285,30 +285,34 @@ def main():
     eng.enable_timing(True)
     stage_ms = np.zeros(3)
     n_waves = 0
-    wave = min(B, 4096)
     for k in range(args.steps):
         eng.solve_many_device(dev_masks[(args.warmup + k) % n_batches], want=want, out=out_dev)
         torch.cuda.synchronize(dev)
         stage_ms += eng.last_stage_ms()
-        n_waves += (B + wave - 1) // wave
+        n_waves += eng.last_wave_count()
     eng.enable_timing(False)
-    pf = eng.solve_many_device(dev_masks[args.warmup % n_batches], want=('profile_flops', 'n_free'))
-    torch.cuda.synchronize(dev)
-    flops_batch = float(pf['profile_flops'].sum().item())
-    nfree_mean = float(pf['n_free'].double().mean().item())
+    flops_batches = 0.0
+    nfree_mean = 0.0
+    for k in range(args.steps):              # algorithmic work of exactly the batches that were timed
+        pf = eng.solve_many_device(dev_masks[(args.warmup + k) % n_batches], want=('profile_flops', 'n_free'))
+        torch.cuda.synchronize(dev)
+        flops_batches += float(pf['profile_flops'].sum().item())
+        nfree_mean += float(pf['n_free'].double().mean().item()) / args.steps
+    # achieved = algorithmic flops of the timed batches / device time of their K3 launches
     k3_ms_per_launch = stage_ms[1] / n_waves
-    flops_per_launch = flops_batch * (min(B, wave) / B)
+    flops_per_launch = flops_batches / n_waves
+    subsets_per_launch = B * args.steps / n_waves
     achieved = flops_per_launch / (k3_ms_per_launch * 1e-3) / 1e12
     roofline = {'kernel': 'k3_factor_flow (block-band LDL^T, FP64 DMMA m8n8k4, dataflow rows)', 'bound': 'tensor',
                 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
-                'traffic': K3_DRAM_BYTES_PER_SUBSET * min(B, wave),
+                'traffic': K3_DRAM_BYTES_PER_SUBSET * subsets_per_launch,
                 'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum of one k3_factor_flow launch '
                                   '(4096 subsets), scaled to this launch size; profiles/r01_final_ncu_k2_k3_k4.txt',
                 'peak_source': 'cuBLAS DGEMM 8192^3 fp64 measured live in this run (MEASURED_PEAKS.json has no '
                                'fp64 entry; earlier measurement on this pool {} TFLOP/s)'.format(FP64_FALLBACK_TFLOPS),
                 'algorithmic_flops_per_launch': flops_per_launch,
                 'flops_definition': 'sum_j h_j^2 over the active DOFs of each subset (envelope LDL^T, multiply-add = 2)',
-                'avg_launch_ms': k3_ms_per_launch,
+                'avg_launch_ms': k3_ms_per_launch, 'subsets_per_launch': subsets_per_launch,
                 'stage_ms_per_step': {'k2_dofmap_assemble': stage_ms[0] / args.steps,
                                       'k3_factor': stage_ms[1] / args.steps,
                                       'k4_solve_recover': stage_ms[2] / args.steps}}

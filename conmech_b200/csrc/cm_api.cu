@@ -2,6 +2,7 @@
 // once-per-model precomputation: node->element incidence, the static solver ordering
 // (reverse Cuthill-McKee on the node graph), envelope statistics and the workspace layout.
 #include "cm_common.cuh"
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -34,6 +35,7 @@ struct cm_handle {
     // counters / timing
     long long launches = 0;
     int timing = 0;
+    int last_waves = 0;                  // waves of the most recent cm_solve_many call
     double stage_ms[3] = {0, 0, 0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // staging for the host-buffer entry point (grow only)
@@ -42,6 +44,11 @@ struct cm_handle {
     char *wsbuf = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;
+    // two internal lanes: consecutive waves of one call alternate between them (each with its own half
+    // of the workspace), so that the drain of one wave's factorisation overlaps the next wave
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_ev[3] = {nullptr, nullptr, nullptr};     // fork, join 0, join 1
+    int overlap = 1;
 };
 
 template <typename T>
@@ -293,6 +300,9 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
 
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
+    if (const char *e = getenv("CM_NO_OVERLAP")) h->overlap = (e[0] == '1') ? 0 : 1;
     if (ce == cudaSuccess) ce = cm_launch_element_tables(m, h->stream);
     h->launches++;
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
@@ -315,6 +325,8 @@ int cm_destroy(cm_handle *h) {
     if (h->wsbuf) cudaFree(h->wsbuf);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 2; ++i) if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
+    for (int i = 0; i < 3; ++i) if (h->lane_ev[i]) cudaEventDestroy(h->lane_ev[i]);
     delete h;
     return CM_OK;
 }
@@ -475,24 +487,41 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
     char *ws = reinterpret_cast<char *>(ws_dev);
     const uint32_t *masks = reinterpret_cast<const uint32_t *>(masks_dev);
     double acc_ms[3] = {0, 0, 0};
-    for (long long first = 0; first < B; first += wave) {
-        const int count = (int)std::min<long long>(wave, B - first);
-        if (h->timing) CU(cudaEventRecord(h->ev[0], st));
-        CU(cm_launch_dofmap_assemble(h->m, h->L, ws, masks, first, count, od, st));
-        if (h->timing) CU(cudaEventRecord(h->ev[1], st));
+    // Waves.  The batch is cut into equal waves (a short last wave would leave most SMs idle).
+    // Outside timing mode, and when the batch needs more than one wave, the workspace is split in two
+    // and consecutive waves alternate between two internal streams forked from / joined to `st`:
+    // a factorisation launch drains over roughly one CTA lifetime, and the other lane's kernels fill
+    // the SMs it frees.  Every wave is independent (own subsets, own outputs, own workspace half).
+    const int sm_fill = 2 * 592;                                   // two full sets of resident factorisation CTAs
+    const bool two_lanes = !h->timing && h->overlap && h->lane_stream[0] && B > wave / 2 && wave / 2 >= sm_fill;
+    const long long cap = two_lanes ? wave / 2 : wave;
+    const long long n_waves = (B + cap - 1) / cap;
+    const long long wsize = (B + n_waves - 1) / n_waves;
+    if (two_lanes) {
+        CU(cudaEventRecord(h->lane_ev[0], st));
+        for (int i = 0; i < 2; ++i) CU(cudaStreamWaitEvent(h->lane_stream[i], h->lane_ev[0], 0));
+    }
+    long long w = 0;
+    for (long long first = 0; first < B; first += wsize, ++w) {
+        const int count = (int)std::min<long long>(wsize, B - first);
+        cudaStream_t ls = two_lanes ? h->lane_stream[w & 1] : st;
+        char *lws = two_lanes ? ws + (size_t)(w & 1) * (size_t)cap * per : ws;
+        if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
+        CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, ls));
+        if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
         if (h->variant == 0)
-            CU(cm_launch_factor(h->m, h->L, ws, count, 0, st));
+            CU(cm_launch_factor(h->m, h->L, lws, count, 0, ls));
         else
         {
             // variant -> CTA configuration of the dataflow kernel (0 automatic, 1: 8 warps, 2: 4 warps, 3: 16 warps)
             const int cfg = h->variant == 1 ? 0 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2));
-            CU(cm_launch_factor_flow(h->m, h->L, ws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, st));
+            CU(cm_launch_factor_flow(h->m, h->L, lws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, ls));
         }
-        if (h->timing) CU(cudaEventRecord(h->ev[2], st));
-        CU(cm_launch_solve_recover(h->m, h->L, ws, masks, first, count, od, st));
+        if (h->timing) CU(cudaEventRecord(h->ev[2], ls));
+        CU(cm_launch_solve_recover(h->m, h->L, lws, masks, first, count, od, ls));
         h->launches += 3;
         if (h->timing) {
-            CU(cudaEventRecord(h->ev[3], st));
+            CU(cudaEventRecord(h->ev[3], ls));
             CU(cudaEventSynchronize(h->ev[3]));
             for (int i = 0; i < 3; ++i) {
                 float ms = 0;
@@ -501,7 +530,13 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
             }
         }
     }
+    if (two_lanes)
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventRecord(h->lane_ev[1 + i], h->lane_stream[i]));
+            CU(cudaStreamWaitEvent(st, h->lane_ev[1 + i], 0));
+        }
     if (h->timing) for (int i = 0; i < 3; ++i) h->stage_ms[i] = acc_ms[i];
+    h->last_waves = (int)n_waves;
     return CM_OK;
 }
 
@@ -582,6 +617,8 @@ int cm_last_stage_ms(const cm_handle *h, double *ms) {
     for (int i = 0; i < 3; ++i) ms[i] = h->stage_ms[i];
     return CM_OK;
 }
+
+int cm_last_wave_count(const cm_handle *h) { return h ? h->last_waves : 0; }
 
 int cm_element_kernel_dev(uint64_t xyz_u, uint64_t xyz_v, uint64_t props, uint64_t cr, int64_t n, uint64_t Kg,
                           uint64_t R3, uint64_t stream) {

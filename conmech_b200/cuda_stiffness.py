@@ -327,6 +327,9 @@ class CudaStiffness(StiffnessBase):
         self._lib.cm_last_stage_ms(self._handle, _ptr(ms))
         return ms
 
+    def last_wave_count(self):
+        return int(self._lib.cm_last_wave_count(self._handle))
+
     # ------------------------------------------------------------------ the reference interface
     def solve(self, exist_element_ids=[], if_cond_num=False):
         """numpy_stiffness.py:228-397 for one subset; stores nD / fR / eR like the reference
