@@ -88,10 +88,16 @@ __device__ double block_nanmax(double v, double *s_red) {
     return tot;
 }
 
+// XS: the solution vector of the load case in progress lives in shared memory (n_pad doubles).  The
+// back substitution is a chain of one step per tile row, and every step reads and writes a few
+// entries of x: from shared memory the chain step is one DRAM access (the tile) instead of five
+// dependent global round trips.
+template <bool XS>
 __global__ void __launch_bounds__(K4_THREADS)
 k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
                  cm_out_dev out) {
     __shared__ double s_red[K4_WARPS];
+    extern __shared__ __align__(16) double s_x[];
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long gs = first + blockIdx.x;
@@ -136,7 +142,9 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             }
             continue;
         }
-        double *Xl = X + (size_t)lc * L.n_pad;
+        double *Xg = X + (size_t)lc * L.n_pad;
+        double *Xl = XS ? s_x : Xg;
+        const double *dpl = XS ? s_x + L.n_pad : dpiv;       // pivots next to x (copied below)
 
         if (zero_load) {
             for (int r = t; r < NT * CM_TILE; r += K4_THREADS) Xl[r] = 0.0;
@@ -146,14 +154,18 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             // (I,J) of block row I (contiguous in memory) subtracts L(I,J)^T x_I from the pending
             // sum of block J; the warp that owns tile (I,I-1) then finishes x_{I-1} =
             // M^T (d .* s) with M = D^-1 L_JJ^-1 left by the factorisation.  One barrier per row.
-            for (int r = t; r < NT * CM_TILE; r += K4_THREADS) Xl[r] = Xl[r] / dpiv[r];
+            for (int r = t; r < NT * CM_TILE; r += K4_THREADS) {
+                const double d = dpiv[r];
+                if (XS) s_x[L.n_pad + r] = d;
+                Xl[r] = Xg[r] / d;
+            }
             __syncthreads();
             const int g = lane >> 2;
             if (warp == 0) {
                 const int I = NT - 1;
                 double w4[4], cs[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w4[i] = dpiv[I * CM_TILE + i * 8 + g] * Xl[I * CM_TILE + i * 8 + g];
+                for (int i = 0; i < 4; ++i) w4[i] = dpl[I * CM_TILE + i * 8 + g] * Xl[I * CM_TILE + i * 8 + g];
                 mtile_tmatvec(minv + (size_t)I * CM_TILE_ELEMS, w4, cs, lane);
                 __syncwarp();
                 if (lane < 4)
@@ -182,7 +194,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                         __syncwarp();
                         double w4[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) w4[i] = dpiv[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
+                        for (int i = 0; i < 4; ++i) w4[i] = dpl[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
                         mtile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
                         __syncwarp();
                         if (lane < 4)
@@ -195,7 +207,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     const int J = I - 1;
                     double w4[4], cs[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) w4[i] = dpiv[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
+                    for (int i = 0; i < 4; ++i) w4[i] = dpl[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
                     mtile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
                     __syncwarp();
                     if (lane < 4)
@@ -304,6 +316,17 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st) {
-    k4_solve_recover<<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, first, out);
+    const size_t xs_bytes = 2 * (size_t)L.n_pad * sizeof(double);      // x and the pivots
+    if (xs_bytes <= 64 * 1024) {
+        static size_t configured = 0;
+        if (xs_bytes > configured) {
+            cudaError_t e = cudaFuncSetAttribute(k4_solve_recover<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes);
+            if (e != cudaSuccess) return e;
+            configured = xs_bytes;
+        }
+        k4_solve_recover<true><<<count, K4_THREADS, xs_bytes, st>>>(m, L, ws, masks, first, out);
+    } else {
+        k4_solve_recover<false><<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, first, out);
+    }
     return cudaGetLastError();
 }
