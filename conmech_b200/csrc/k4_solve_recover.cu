@@ -179,6 +179,15 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + lane * 16));
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + 512 + lane * 16));
                 }
+                // ... and so are the tiles of the next row: request this warp's share one row ahead
+                if (I >= 2) {
+                    const int kfn = kfirst[I - 1];
+                    for (int J = I - 2 - warp; J >= kfn; J -= K4_WARPS) {
+                        const double *Tn = cm_tile_ptr(tiles, bt, I - 1, J) + lane * 16;
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn + 512));
+                    }
+                }
                 __syncthreads();
                 const int kf = kfirst[I];
                 double x4[4];
