@@ -29,7 +29,7 @@ class ModelInfo(C.Structure):
 
 
 OUT_FIELDS = ('flag', 'status', 'n_free', 'n_fixed', 'dof_map', 'node_exists', 'U', 'Rf', 'eR',
-              'compliance', 'max_trans', 'max_rot', 'min_pivot', 'profile_flops')
+              'compliance', 'max_trans', 'max_rot', 'min_pivot', 'profile_flops', 'sigma_max', 'max_abs_sigma')
 
 
 class SolveOut(C.Structure):

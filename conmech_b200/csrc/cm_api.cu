@@ -484,6 +484,8 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
     od.max_rot = reinterpret_cast<double *>(o->max_rot);
     od.min_pivot = reinterpret_cast<double *>(o->min_pivot);
     od.profile_flops = reinterpret_cast<double *>(o->profile_flops);
+    od.sigma_max = reinterpret_cast<double *>(o->sigma_max);
+    od.max_abs_sigma = reinterpret_cast<double *>(o->max_abs_sigma);
     char *ws = reinterpret_cast<char *>(ws_dev);
     const uint32_t *masks = reinterpret_cast<const uint32_t *>(masks_dev);
     double acc_ms[3] = {0, 0, 0};
@@ -561,6 +563,7 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
     Item i_c = item(o->compliance, Bn * Lc * 8), i_mt = item(o->max_trans, Bn * Lc * 8);
     Item i_mr = item(o->max_rot, Bn * Lc * 8), i_mp = item(o->min_pivot, Bn * 8);
     Item i_pf = item(o->profile_flops, Bn * 8);
+    Item i_sg = item(o->sigma_max, Bn * Lc * nE * 8), i_ms = item(o->max_abs_sigma, Bn * Lc * 8);
     if (off > h->stage_bytes) {
         if (h->stage) cudaFree(h->stage);
         h->stage = nullptr; h->stage_bytes = 0;
@@ -591,9 +594,10 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
     od.dof_map = dp(i_dof); od.node_exists = dp(i_ex); od.U = dp(i_U); od.Rf = dp(i_R); od.eR = dp(i_E);
     od.compliance = dp(i_c); od.max_trans = dp(i_mt); od.max_rot = dp(i_mr); od.min_pivot = dp(i_mp);
     od.profile_flops = dp(i_pf);
+    od.sigma_max = dp(i_sg); od.max_abs_sigma = dp(i_ms);
     int rc = cm_solve_many(h, (uint64_t)(h->stage + i_mask.off), B, &od, (uint64_t)h->wsbuf, h->ws_bytes, (uint64_t)st);
     if (rc != CM_OK) return rc;
-    const Item *outs[] = {&i_flag, &i_status, &i_nfree, &i_nfixed, &i_dof, &i_ex, &i_U, &i_R, &i_E, &i_c, &i_mt, &i_mr, &i_mp, &i_pf};
+    const Item *outs[] = {&i_flag, &i_status, &i_nfree, &i_nfixed, &i_dof, &i_ex, &i_U, &i_R, &i_E, &i_c, &i_mt, &i_mr, &i_mp, &i_pf, &i_sg, &i_ms};
     for (const Item *it : outs)
         if (it->host) CU(cudaMemcpyAsync(it->host, h->stage + it->off, it->bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

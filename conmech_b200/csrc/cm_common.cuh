@@ -100,7 +100,7 @@ struct cm_out_dev {
     unsigned char *flag, *status;
     int *n_free, *n_fixed, *dof_map;
     unsigned char *node_exists;
-    double *U, *Rf, *eR, *compliance, *max_trans, *max_rot, *min_pivot, *profile_flops;
+    double *U, *Rf, *eR, *compliance, *max_trans, *max_rot, *min_pivot, *profile_flops, *sigma_max, *max_abs_sigma;
 };
 
 // kernel launchers (one per stage); all enqueue on `st` and return the launch error

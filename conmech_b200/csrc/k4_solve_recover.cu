@@ -133,7 +133,9 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             if (Uo) for (int i = t; i < 6 * nV; i += K4_THREADS) Uo[i] = 0.0;
             if (Ro) for (int i = t; i < 6 * nV; i += K4_THREADS) Ro[i] = 0.0;
             if (Eo) for (int i = t; i < 12 * nE; i += K4_THREADS) Eo[i] = 0.0;
+            if (out.sigma_max) for (int i = t; i < nE; i += K4_THREADS) out.sigma_max[ol * (size_t)nE + i] = 0.0;
             if (t == 0) {
+                if (out.max_abs_sigma) out.max_abs_sigma[ol] = nan("");
                 if (out.flag) out.flag[ol] = 0;
                 if (out.status) out.status[ol] = (unsigned char)status;
                 if (out.compliance) out.compliance[ol] = 0.0;
@@ -283,31 +285,65 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             }
         }
 
-        // ---- element end forces in local axes, four threads per element (one per 3-row block)
-        if (Eo) {
-            for (int idx = t; idx < 4 * nE; idx += K4_THREADS) {
-                int e = idx >> 2, pblk = idx & 3;
-                double *dst = Eo + (size_t)e * 12 + 3 * pblk;
-                if (!elem_on(mask, e)) { dst[0] = dst[1] = dst[2] = 0.0; continue; }
-                int n0 = m.conn[2 * e], n1 = m.conn[2 * e + 1];
-                double ue[12];
+        // ---- element end forces in local axes, four threads per element (one per 3-row block:
+        // F end 0, M end 0, F end 1, M end 1), and from them the reference's stress measure
+        // (stiffness_checker.py:330-365): sigma = N/A, sign(sigma) * (|sigma| + My/W + Mz/W) with
+        // r = sqrt(A/pi), W = Iy/r for BOTH axes, My/Mz = larger end moment in magnitude
+        double *So = out.sigma_max ? out.sigma_max + ol * (size_t)nE : nullptr;
+        double smax = -1.0;
+        if (Eo || So || out.max_abs_sigma) {
+            for (int i0 = 0; i0 < 4 * nE; i0 += K4_THREADS) {       // uniform trip count: shuffles below
+                const int idx = i0 + t;
+                const bool valid = idx < 4 * nE;
+                const int e = valid ? idx >> 2 : 0, pblk = idx & 3;
+                const bool on = valid && elem_on(mask, e);
+                double d3[3] = {0.0, 0.0, 0.0};
+                if (on) {
+                    int n0 = m.conn[2 * e], n1 = m.conn[2 * e + 1];
+                    double ue[12];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) { ue[j] = u_at(6 * n0 + j); ue[6 + j] = u_at(6 * n1 + j); }
-                double tv[3];
+                    for (int j = 0; j < 6; ++j) { ue[j] = u_at(6 * n0 + j); ue[6 + j] = u_at(6 * n1 + j); }
+                    double tv[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double *krow = m.Kg + (size_t)e * 144 + (3 * pblk + a) * 12;
-                    double s = 0.0;
+                    for (int a = 0; a < 3; ++a) {
+                        const double *krow = m.Kg + (size_t)e * 144 + (3 * pblk + a) * 12;
+                        double s = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) s += krow[j] * ue[j];
-                    tv[a] = s;
+                        for (int j = 0; j < 12; ++j) s += krow[j] * ue[j];
+                        tv[a] = s;
+                    }
+                    const double *R3 = m.R3 + (size_t)e * 9;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                        d3[a] = -(R3[3 * a] * tv[0] + R3[3 * a + 1] * tv[1] + R3[3 * a + 2] * tv[2]);
                 }
-                const double *R3 = m.R3 + (size_t)e * 9;
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-                    dst[a] = -(R3[3 * a] * tv[0] + R3[3 * a + 1] * tv[1] + R3[3 * a + 2] * tv[2]);
+                if (Eo && valid) {
+                    double *dst = Eo + (size_t)e * 12 + 3 * pblk;
+                    dst[0] = d3[0]; dst[1] = d3[1]; dst[2] = d3[2];
+                }
+                if (So || out.max_abs_sigma) {
+                    const int l0 = lane & ~3;
+                    const double N = __shfl_sync(0xffffffffu, d3[0], l0);
+                    const double My0 = __shfl_sync(0xffffffffu, d3[1], l0 + 1), My1 = __shfl_sync(0xffffffffu, d3[1], l0 + 3);
+                    const double Mz0 = __shfl_sync(0xffffffffu, d3[2], l0 + 1), Mz1 = __shfl_sync(0xffffffffu, d3[2], l0 + 3);
+                    if (valid && pblk == 0) {
+                        double sg = 0.0;
+                        if (on) {
+                            const double A = m.props[(size_t)e * 7], Iy = m.props[(size_t)e * 7 + 2];
+                            const double My = fmax(fabs(My0), fabs(My1)), Mz = fmax(fabs(Mz0), fabs(Mz1));
+                            const double rr = sqrt(__ddiv_rn(A, 3.141592653589793));
+                            const double W = __ddiv_rn(Iy, rr);
+                            const double sigma = __ddiv_rn(N, A);
+                            const double mag = __dadd_rn(__dadd_rn(fabs(sigma), __ddiv_rn(My, W)), __ddiv_rn(Mz, W));
+                            sg = sigma > 0.0 ? mag : -mag;
+                            smax = nanmax(smax, fabs(sg));
+                        }
+                        if (So) So[e] = sg;
+                    }
+                }
             }
         }
+        if (out.max_abs_sigma) smax = block_nanmax(smax, s_red);
 
         if (t == 0) {
             if (out.flag) out.flag[ol] = (mt < m.trans_tol) ? 1 : 0;
@@ -315,6 +351,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             if (out.compliance) out.compliance[ol] = comp;
             if (out.max_trans) out.max_trans[ol] = mt;
             if (out.max_rot) out.max_rot[ol] = mr;
+            if (out.max_abs_sigma) out.max_abs_sigma[ol] = smax < 0.0 ? 0.0 : smax;
         }
         __syncthreads();
     }

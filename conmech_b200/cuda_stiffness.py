@@ -27,7 +27,8 @@ DEFAULT_GRAVITY_DIRECTION = np.array([0., 0., -1.])
 _OUT_DTYPE = {'flag': np.uint8, 'status': np.uint8, 'n_free': np.int32, 'n_fixed': np.int32,
               'dof_map': np.int32, 'node_exists': np.uint8, 'U': np.float64, 'Rf': np.float64,
               'eR': np.float64, 'compliance': np.float64, 'max_trans': np.float64,
-              'max_rot': np.float64, 'min_pivot': np.float64, 'profile_flops': np.float64}
+              'max_rot': np.float64, 'min_pivot': np.float64, 'profile_flops': np.float64,
+              'sigma_max': np.float64, 'max_abs_sigma': np.float64}
 
 
 def _ptr(a):
@@ -252,7 +253,7 @@ class CudaStiffness(StiffnessBase):
         return {'flag': (B, L), 'status': (B, L), 'n_free': (B,), 'n_fixed': (B,), 'dof_map': (B, 6 * nV),
                 'node_exists': (B, nV), 'U': (B, L, 6 * nV), 'Rf': (B, L, 6 * nV), 'eR': (B, L, nE, 12),
                 'compliance': (B, L), 'max_trans': (B, L), 'max_rot': (B, L), 'min_pivot': (B,),
-                'profile_flops': (B,)}
+                'profile_flops': (B,), 'sigma_max': (B, L, nE), 'max_abs_sigma': (B, L)}
 
     def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):
         """Solve B element subsets (list of id lists, [] = full structure, or a (B, words)

@@ -128,6 +128,10 @@ typedef struct cm_solve_out {
     uint64_t min_pivot;   /* f64 [B]        smallest LDL^T pivot of the scaled matrix             */
     uint64_t profile_flops; /* f64 [B]      sum_j h_j^2 of the subset's K_mm envelope (algorithmic work  */
                           /*                of the factorisation, one multiply-add counted as 2)  */
+    uint64_t sigma_max;   /* f64 [B*L*nE]   max axial normal stress per element, the reference's          */
+                          /*                get_sigma_max_per_element (stiffness_checker.py:330-365: solid */
+                          /*                round sections, both section moduli from Iy); 0 when absent    */
+    uint64_t max_abs_sigma; /* f64 [B*L]    max over the subset's elements of |sigma_max|                  */
 } cm_solve_out;
 
 /* Factorisation kernel variant: 1 (default) = FP64 tensor-core block-band LDL^T, dataflow
@@ -171,6 +175,8 @@ typedef struct cm_solve_out_host {
     double *max_rot;
     double *min_pivot;
     double *profile_flops;
+    double *sigma_max;
+    double *max_abs_sigma;
 } cm_solve_out_host;
 
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,

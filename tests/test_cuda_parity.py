@@ -396,3 +396,48 @@ def test_config3_100k_subsets_properties():
             rs = eng.solve_many([subsets[b] for b in sample], want=ALL)
             check_against_oracle(eng, orc, [subsets[b] for b in sample], rs, tag='g1k-100k-sample')
     assert 0 < n_true < B
+
+
+def test_sigma_max_on_device():
+    """the stress post-processing of the facade, computed in K4 for every (subset, load
+    case): per-element sigma_max and its maximum magnitude, against the reference formula applied
+    to the ORACLE's element reactions."""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(4, 4, 4)
+    lc = LoadCase(gravity_load=GravityLoad([0, 0, -1]))
+    sc, orc = make_pair(model, lc)
+    eng = sc._sc_ins
+    subsets = [[]] + [syn.connected_subset(model, s) for s in range(24)]
+    r = eng.solve_many(subsets, want=('flag', 'status', 'eR', 'sigma_max', 'max_abs_sigma'))
+    nE = len(model.elements)
+    A = np.array([sc.get_element_crosssec(e).A for e in range(nE)])
+    Iy = np.array([sc.get_element_crosssec(e).Iy for e in range(nE)])
+    W = Iy / np.sqrt(A / np.pi)
+    checked = 0
+    for b, ids in enumerate(subsets):
+        o = orc.solve(ids)
+        if not o.has_result:
+            continue
+        ids2 = list(ids) or list(range(nE))
+        eR = o.eR
+        sigma = eR[:, 0] / A
+        mag = np.abs(sigma) + np.maximum(np.abs(eR[:, 4]), np.abs(eR[:, 10])) / W + np.maximum(np.abs(eR[:, 5]), np.abs(eR[:, 11])) / W
+        ref = np.where(sigma > 0, mag, -mag)
+        got = r['sigma_max'][b, 0]
+        scale = np.max(np.abs(ref[ids2]))
+        # the sign is that of N/A: rounding noise for members without axial force, so magnitudes are
+        # compared everywhere and signs where the axial stress is not negligible
+        assert np.max(np.abs(np.abs(got[ids2]) - np.abs(ref[ids2]))) <= REL_TOL * scale, b
+        firm = [e for e in ids2 if abs(sigma[e]) > 1e-6 * scale]
+        assert np.array_equal(np.sign(got[firm]), np.sign(ref[firm])), b
+        absent = np.setdiff1d(np.arange(nE), ids2)
+        assert not got[absent].any()
+        assert abs(r['max_abs_sigma'][b, 0] - np.max(np.abs(got))) == 0.0
+        checked += 1
+    assert checked >= 20
+    # the facade's host-side accessor agrees with the device array for a single solve
+    ids = subsets[3]
+    sc.solve(ids)
+    host = sc.get_sigma_max_per_element()
+    for e, v in host.items():
+        assert abs(abs(v) - abs(r['sigma_max'][3, 0][e])) <= REL_TOL * max(abs(v), 1e-300) + 1e-12 * scale

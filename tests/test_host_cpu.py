@@ -26,7 +26,7 @@ def test_capi_loads_and_exports_header_symbols():
     assert b'sm_100a' in lib.cm_version()
     # struct layouts the header promises
     import ctypes as C
-    assert C.sizeof(_capi.SolveOut) == 14 * 8 and C.sizeof(_capi.SolveOutHost) == 14 * 8
+    assert C.sizeof(_capi.SolveOut) == 16 * 8 and C.sizeof(_capi.SolveOutHost) == 16 * 8
     assert C.sizeof(_capi.ModelDesc) == 16 + 6 * 8
 
 
@@ -166,3 +166,15 @@ def test_solve_many_sharded_gloo_world2():
     for r in range(world):
         for k, v in ref.items():
             assert np.array_equal(ret[r][k], v), (r, k)
+
+
+def test_fragment_maps_of_the_factorisation_kernel():
+    """tools/frag_emulator.py: lane-level emulation of the FP64 MMA fragment maps that
+    k3_factor_flow.cu relies on (in-register solve product, SYRK from registers, M_J layout)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'frag_emulator.py')
+    spec = importlib.util.spec_from_file_location('frag_emulator', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
