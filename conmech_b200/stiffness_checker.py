@@ -74,15 +74,23 @@ class StiffnessChecker(object):
                 assert 0 <= e_id < nE and int(e_id) == e_id, 'element id not within range!'
         return self._sc_ins.solve(exist_element_ids, if_cond_num=if_cond_num)
 
-    def solve_many(self, list_of_existing_ids, return_details=False):
+    def solve_many(self, list_of_existing_ids, return_details=False, with_stress=False):
         """Batched ``solve``: one flag per subset, all solved in one GPU pass.  With
-        ``return_details`` also returns {'status','max_trans','compliance'} arrays."""
-        r = self._sc_ins.solve_many(list_of_existing_ids,
-                                    want=('flag', 'status', 'max_trans', 'compliance'))
+        ``return_details`` also returns {'status','max_trans','compliance'} arrays;
+        ``with_stress`` adds 'max_abs_sigma' (largest |sigma_max| over the subset's elements, the
+        batched counterpart of ``get_sigma_max_per_element``) to them."""
+        names = ('status', 'max_trans', 'compliance') + (('max_abs_sigma',) if with_stress else ())
+        r = self._sc_ins.solve_many(list_of_existing_ids, want=('flag',) + names)
         flags = [bool(f) for f in r['flag'][:, 0]]
-        if return_details:
-            return flags, {k: r[k][:, 0].copy() for k in ('status', 'max_trans', 'compliance')}
+        if return_details or with_stress:
+            return flags, {k: r[k][:, 0].copy() for k in names}
         return flags
+
+    def get_sigma_max_per_element_many(self, list_of_existing_ids):
+        """``get_sigma_max_per_element`` for many subsets at once, computed on the device: a
+        (B, nE) array (first load case), 0 for elements that are not in the subset."""
+        r = self._sc_ins.solve_many(list_of_existing_ids, want=('flag', 'sigma_max'))
+        return r['sigma_max'][:, 0].copy()
 
     def solve_sequence(self, order, return_details=False):
         """Stiffness check of EVERY prefix of a construction sequence in one batched pass: flag k
