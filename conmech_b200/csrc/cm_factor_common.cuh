@@ -11,6 +11,22 @@ constexpr int DSCR = 2 * 32 * DS + 2 * 32;      // CTA scratch of the diagonal f
                                                 // per CTA: the diagonal factorisations of a subset form
                                                 // a dependency chain, so only one is ever in progress.
 
+// Per-CTA context of the factorisation kernel in SHARED memory.  The device functions below are real
+// calls (not inlined: the register allocator does best with the stream loops in functions of their
+// own); with two dozen pointer/size arguments most of them travelled through the stack - local
+// memory, which misses the L1 under the operand streams - and were reloaded from L2 at every use.
+// Instead every function takes two or three integers in registers and reads what it needs from this
+// block at the point of use (volatile: never cached in registers across a stream, never spilled).
+struct K3Ctx {
+    double *tiles; double *minv; double *dpiv; double *X;
+    const int *kcol; const unsigned long long *arow; int *prog; int *yprog;
+    double *s_part; double *s_rhs; double *s_scr; double *s_minpiv; int *s_fail;
+    long long *pc; long long *tpub;
+    int bt, n_pad, n_lc, zero_bits;
+};
+__shared__ K3Ctx s_ctx;
+#define CTX(f) (((volatile K3Ctx *)&s_ctx)->f)
+
 __device__ __forceinline__ double fast_rcp(double d) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
@@ -42,11 +58,13 @@ __device__ __forceinline__ double dneg(double x) {       // sign flip on the int
 // 301-319; <= -1e-14 is rejected: :326-336; NaN fails both) sets *s_fail and is replaced by 1.
 // in_smem: the lower blocks of the tile were already placed in scr (row stride DS) by
 // diag_newest_to_smem(); otherwise the tile is read from T.
-__device__ __noinline__ void diag_factor_blk(const double *T, bool in_smem, double *Mg, double *dg, double *scr, int lane,
-                                             int *s_fail, double *s_minpiv_w) {
+__device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
+    double *scr = CTX(s_scr);
     double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
+    double *s_minpiv_w = CTX(s_minpiv) + (threadIdx.x >> 5);
     const int g = lane >> 2, t = lane & 3;
     if (!in_smem) {
+        const double *T = cm_tile_ptr(CTX(tiles), CTX(bt), I, I);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             double v[4];
@@ -104,9 +122,9 @@ __device__ __noinline__ void diag_factor_blk(const double *T, bool in_smem, doub
             __syncwarp();
         }
     }
-    dg[lane] = dmine;
+    CTX(dpiv)[I * CM_TILE + lane] = dmine;
     s_rinv[lane] = rmine;
-    if (lane == 0) { *s_minpiv_w = minpiv; if (fail) *s_fail = 1; }
+    if (lane == 0) { *s_minpiv_w = minpiv; if (fail) *CTX(s_fail) = 1; }
     // ---- X = L^-1.  Diagonal blocks: lane 8*bb + j owns column j of X_bb (substitution on e_j)
     {
         const int bb = lane >> 3, j = lane & 7;
@@ -152,6 +170,7 @@ __device__ __noinline__ void diag_factor_blk(const double *T, bool in_smem, doub
         __syncwarp();
     }
     // ---- M = D^-1 X to global memory, cm_mtile_off layout (blocks above the diagonal are not stored)
+    double *Mg = CTX(minv) + (size_t)I * CM_TILE_ELEMS;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const double ri = s_rinv[8 * i + g];
@@ -202,13 +221,16 @@ __device__ __forceinline__ void diag_newest_to_smem(const TileAcc &r, const doub
 // forward substitution of block row J for every load case:  y_J = D_J M_J (b_J - s_J), where
 // s_J = sum_K L(J,K) y_K was accumulated tile by tile (acc_matvec) into s_part while the tiles of
 // the row were still in registers - the row of L is not read again.
-__device__ __noinline__ void forward_row_w(const double *minv, const double *dpiv, double *X, const double *s_part,
-                                           double *s_r, int n_pad, int n_lc, int zero_bits, int J, int lane) {
+__device__ __noinline__ void forward_row_w(int J, int lane) {
     const int g = lane >> 2, tt = lane & 3;
-    const double *pm = minv + (size_t)J * CM_TILE_ELEMS + lane * 2;
+    const int n_lc = CTX(n_lc), zero_bits = CTX(zero_bits), warp = threadIdx.x >> 5;
+    const double *pm = CTX(minv) + (size_t)J * CM_TILE_ELEMS + lane * 2;
+    const double *dpiv = CTX(dpiv);
+    const double *s_part = CTX(s_part) + warp * n_lc * 32;
+    double *s_r = CTX(s_rhs) + warp * 32;
     for (int lc = 0; lc < n_lc; ++lc) {
         if ((zero_bits >> lc) & 1) continue;
-        double *Xl = X + (size_t)lc * n_pad;
+        double *Xl = CTX(X) + (size_t)lc * CTX(n_pad);
         s_r[lane] = Xl[J * CM_TILE + lane] - s_part[lc * 32 + lane];
         __syncwarp();
 #pragma unroll

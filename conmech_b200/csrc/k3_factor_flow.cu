@@ -41,13 +41,12 @@ __device__ unsigned long long g_flow_prof[16];
 // (J == I-1), the newest term of the diagonal tile, handed to the diagonal factorisation through
 // the shared scratch.  Returns true when the diagonal tile was placed in the scratch.
 template <bool PROF>
-__device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, const double *dpiv, const double *X,
-                                          const int *kcol, const unsigned long long *arow, volatile int *prog,
-                                          volatile int *yprog, int bt, int I, int J, int kcI, int n_pad, int n_lc,
-                                          int zero_bits, double *s_part, double *s_scr, int lane, long long *pc,
-                                          volatile long long *tpub) {
-    double *T = cm_tile_ptr(tiles, bt, I, J);
+__device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
+    const int bt = CTX(bt);
+    long long *pc = PROF ? CTX(pc) + (threadIdx.x >> 5) * 16 : nullptr;
+    double *T = cm_tile_ptr(CTX(tiles), bt, I, J);
     const int ab = J - I + bt - 1, aw = (bt + 63) >> 6;
+    const unsigned long long *arow = CTX(arow);
     const bool has_a = (arow[I * aw + (ab >> 6)] >> (ab & 63)) & 1ull;         // K2 assembled entries into this tile
     // the next tile of the row that K2 assembled (the diagonal tile always is) comes from DRAM: start that read now
     if ((arow[I * aw + ((ab + 1) >> 6)] >> ((ab + 1) & 63)) & 1ull) {
@@ -56,7 +55,7 @@ __device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, con
         asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 512));
     }
     // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
-    int qs = max(kcI, kcol[J]);
+    int qs = max(kcI, CTX(kcol)[J]);
     int K = qs >> 3;
     FP_T0(pc);
     TileAcc acc;
@@ -67,52 +66,59 @@ __device__ __noinline__ bool offdiag_tile(double *tiles, const double *minv, con
     }
     if (has_a) acc_load(acc, T, lane); else acc_zero(acc);
     while (K < J) {
-        const int Kend = min(wait_prog_gt(prog, J, K), J);
+        const int Kend = min(wait_prog_gt(CTX(prog), J, K), J);
         FP_ADD(pc, 0);
+        const double *tiles = CTX(tiles);
         const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
         const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
-        acc_update_stream<false>(acc, A, Bm, dpiv + qs * 4, Kend * 8 - qs, lane);
+        acc_update_stream<false>(acc, A, Bm, CTX(dpiv) + qs * 4, Kend * 8 - qs, lane);
         K = Kend;
         qs = K * 8;
         FP_ADD(pc, 1);
     }
-    wait_prog_gt(prog, J, J);                     // M_J published
+    wait_prog_gt(CTX(prog), J, J);                // M_J published
     FP_ADD(pc, 2);
-    if (PROF && pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *tpub;     // reaction gap on the chain
-    acc_solve_inplace(acc, minv + (size_t)J * CM_TILE_ELEMS, max(kcI - 8 * J, 0) >> 1, lane);
-    acc_store(acc, T, lane);
+    if (PROF && pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *CTX(tpub);     // reaction gap on the chain
+    acc_solve_inplace(acc, CTX(minv) + (size_t)J * CM_TILE_ELEMS, max(kcI - 8 * J, 0) >> 1, lane);
+    acc_store(acc, cm_tile_ptr(CTX(tiles), bt, I, J), lane);
     if (PROF && pc && J == I - 1) FP_ADD(pc, 10); else FP_ADD(pc, 3);
     // share of this tile in the forward substitution of row I:  s_I += L(I,J) y_J
     {
+        volatile int *yprog = CTX(yprog);
         int y = *yprog;
         while (y <= J) { __nanosleep(40); y = *yprog; }
         __threadfence_block();
     }
     FP_ADD(pc, 7);
-    for (int lc = 0; lc < n_lc; ++lc) {
-        if ((zero_bits >> lc) & 1) continue;
-        double part[4];
-        acc_matvec(acc, X + (size_t)lc * n_pad + J * CM_TILE, part, lane);
-        if ((lane & 3) == 0) {
+    {
+        const int n_lc = CTX(n_lc), zero_bits = CTX(zero_bits);
+        double *s_part = CTX(s_part) + (threadIdx.x >> 5) * n_lc * 32;
+        for (int lc = 0; lc < n_lc; ++lc) {
+            if ((zero_bits >> lc) & 1) continue;
+            double part[4];
+            acc_matvec(acc, CTX(X) + (size_t)lc * CTX(n_pad) + J * CM_TILE, part, lane);
+            if ((lane & 3) == 0) {
 #pragma unroll
-            for (int ri = 0; ri < 4; ++ri) s_part[lc * 32 + ri * 8 + (lane >> 2)] += part[ri];
+                for (int ri = 0; ri < 4; ++ri) s_part[lc * 32 + ri * 8 + (lane >> 2)] += part[ri];
+            }
         }
     }
     FP_ADD(pc, 8);
     if (J != I - 1) return false;
-    diag_newest_to_smem(acc, cm_tile_ptr(tiles, bt, I, I), dpiv + J * CM_TILE, s_scr, lane);
+    diag_newest_to_smem(acc, cm_tile_ptr(CTX(tiles), bt, I, I), CTX(dpiv) + J * CM_TILE, CTX(s_scr), lane);
     FP_ADD(pc, 11);
     return true;
 }
 
 // diagonal tile (I,I) -= sum over k-steps [q0, q1) of the own (final) row:  L(I,k) d_k L(I,k)^T
-__device__ __noinline__ void diag_update(double *tiles, const double *dpiv, int bt, int I, int q0, int q1, int lane) {
-    double *T = cm_tile_ptr(tiles, bt, I, I);
+__device__ __noinline__ void diag_update(int I, int q0, int q1, int lane) {
+    const int bt = CTX(bt);
+    double *tiles = CTX(tiles);
     const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)q0 * 128;
     TileAcc acc;
-    acc_load(acc, T, lane);
-    acc_update_stream<true>(acc, A, nullptr, dpiv + q0 * 4, q1 - q0, lane);
-    acc_store(acc, T, lane);
+    acc_load(acc, cm_tile_ptr(tiles, bt, I, I), lane);
+    acc_update_stream<true>(acc, A, nullptr, CTX(dpiv) + q0 * 4, q1 - q0, lane);
+    acc_store(acc, cm_tile_ptr(CTX(tiles), bt, I, I), lane);
 }
 
 template <int NW, bool PROF>
@@ -151,6 +157,13 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     volatile int *prog = s_prog;
     volatile int *yprog = s_yprog;
 
+    if (t == 0) {
+        s_ctx.tiles = tiles; s_ctx.minv = minv; s_ctx.dpiv = dpiv; s_ctx.X = X;
+        s_ctx.kcol = s_kcol; s_ctx.arow = s_arow; s_ctx.prog = s_prog; s_ctx.yprog = s_yprog;
+        s_ctx.s_part = s_part; s_ctx.s_rhs = s_rhs; s_ctx.s_scr = s_scr; s_ctx.s_minpiv = s_minpiv; s_ctx.s_fail = s_fail;
+        s_ctx.pc = PROF ? &s_pc[0][0] : nullptr; s_ctx.tpub = &s_tpub;
+        s_ctx.bt = bt; s_ctx.n_pad = L.n_pad; s_ctx.n_lc = n_lc; s_ctx.zero_bits = zero_bits;
+    }
     for (int I = t; I < NT; I += NW * 32) {
         s_prog[I] = kfirst[I];
         s_kcol[I] = kcol[I];
@@ -178,11 +191,10 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         for (int J = kfI; J < I; ++J) {
             if (J == I - 1 && I - 2 >= kfI) {    // look-ahead: diagonal terms that do not need row I-1
                 FP_T0(pc);
-                diag_update(tiles, dpiv, bt, I, kcI, 8 * (I - 1), lane);
+                diag_update(I, kcI, 8 * (I - 1), lane);
                 FP_ADD(pc, 4);
             }
-            handed = offdiag_tile<PROF>(tiles, minv, dpiv, X, s_kcol, s_arow, prog, yprog, bt, I, J, kcI, L.n_pad, n_lc,
-                                  zero_bits, s_part_w, s_scr, lane, pc, &s_tpub);
+            handed = offdiag_tile<PROF>(I, J, kcI, lane);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
@@ -190,8 +202,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         FP_T0(pc);
         if (!handed && I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
         FP_ADD(pc, 5);
-        diag_factor_blk(cm_tile_ptr(tiles, bt, I, I), handed, minv + (size_t)I * CM_TILE_ELEMS, dpiv + I * CM_TILE, s_scr,
-                        lane, s_fail, s_minpiv + warp);
+        diag_factor_blk(I, handed, lane);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) { if (PROF) s_tpub = clock64(); prog[I] = I + 1; }
@@ -203,7 +214,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
             __threadfence_block();
         }
         FP_ADD(pc, 7);
-        forward_row_w(minv, dpiv, X, s_part_w, s_rhs + warp * 32, L.n_pad, n_lc, zero_bits, I, lane);
+        forward_row_w(I, lane);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *yprog = I + 1;
