@@ -44,11 +44,12 @@ struct cm_handle {
     char *wsbuf = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;
-    // two internal lanes: consecutive waves of one call alternate between them (each with its own half
+    // internal lanes: consecutive waves of one call rotate over them (each with its own share
     // of the workspace), so that the drain of one wave's factorisation overlaps the next wave
-    cudaStream_t lane_stream[2] = {nullptr, nullptr};
-    cudaEvent_t lane_ev[3] = {nullptr, nullptr, nullptr};     // fork, join 0, join 1
+    cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t lane_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // fork, join per lane
     int overlap = 1;
+    int n_lanes = 3;                     // CM_LANES=1..4: 2 lanes 250 k, 3 lanes 255 k, 4 lanes 255 k solves/s on config 3
 };
 
 template <typename T>
@@ -300,8 +301,9 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
 
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
-    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
+    if (const char *e = getenv("CM_LANES")) { int n = atoi(e); if (n >= 1 && n <= 4) h->n_lanes = n; }
     if (const char *e = getenv("CM_NO_OVERLAP")) h->overlap = (e[0] == '1') ? 0 : 1;
     if (ce == cudaSuccess) ce = cm_launch_element_tables(m, h->stream);
     h->launches++;
@@ -325,8 +327,8 @@ int cm_destroy(cm_handle *h) {
     if (h->wsbuf) cudaFree(h->wsbuf);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
-    for (int i = 0; i < 2; ++i) if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
-    for (int i = 0; i < 3; ++i) if (h->lane_ev[i]) cudaEventDestroy(h->lane_ev[i]);
+    for (int i = 0; i < 4; ++i) if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
+    for (int i = 0; i < 5; ++i) if (h->lane_ev[i]) cudaEventDestroy(h->lane_ev[i]);
     delete h;
     return CM_OK;
 }
@@ -494,20 +496,21 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
     // and consecutive waves alternate between two internal streams forked from / joined to `st`:
     // a factorisation launch drains over roughly one CTA lifetime, and the other lane's kernels fill
     // the SMs it frees.  Every wave is independent (own subsets, own outputs, own workspace half).
-    const int sm_fill = 2 * 592;                                   // two full sets of resident factorisation CTAs
-    const bool two_lanes = !h->timing && h->overlap && h->lane_stream[0] && B > wave / 2 && wave / 2 >= sm_fill;
-    const long long cap = two_lanes ? wave / 2 : wave;
+    const int sm_fill = getenv("CM_LANE_MIN") ? atoi(getenv("CM_LANE_MIN")) : 2 * 592;     // two full sets of resident factorisation CTAs
+    const int NL = h->n_lanes;
+    const bool two_lanes = !h->timing && h->overlap && NL > 1 && h->lane_stream[0] && B > wave / NL && wave / NL >= sm_fill;
+    const long long cap = two_lanes ? wave / NL : wave;
     const long long n_waves = (B + cap - 1) / cap;
     const long long wsize = (B + n_waves - 1) / n_waves;
     if (two_lanes) {
         CU(cudaEventRecord(h->lane_ev[0], st));
-        for (int i = 0; i < 2; ++i) CU(cudaStreamWaitEvent(h->lane_stream[i], h->lane_ev[0], 0));
+        for (int i = 0; i < NL; ++i) CU(cudaStreamWaitEvent(h->lane_stream[i], h->lane_ev[0], 0));
     }
     long long w = 0;
     for (long long first = 0; first < B; first += wsize, ++w) {
         const int count = (int)std::min<long long>(wsize, B - first);
-        cudaStream_t ls = two_lanes ? h->lane_stream[w & 1] : st;
-        char *lws = two_lanes ? ws + (size_t)(w & 1) * (size_t)cap * per : ws;
+        cudaStream_t ls = two_lanes ? h->lane_stream[w % NL] : st;
+        char *lws = two_lanes ? ws + (size_t)(w % NL) * (size_t)cap * per : ws;
         if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
         CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, ls));
         if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
@@ -533,7 +536,7 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         }
     }
     if (two_lanes)
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NL; ++i) {
             CU(cudaEventRecord(h->lane_ev[1 + i], h->lane_stream[i]));
             CU(cudaStreamWaitEvent(st, h->lane_ev[1 + i], 0));
         }

@@ -191,8 +191,8 @@ int cm_reset_counters(cm_handle *h);
 int cm_enable_timing(cm_handle *h, int32_t on);
 int cm_last_stage_ms(const cm_handle *h, double *ms /*[3]*/);
 /* Number of waves (K2 -> K3 -> K4 launch triples) the most recent cm_solve_many* call was cut
- * into.  Outside timing mode consecutive waves alternate between two internal streams forked
- * from and joined to the caller's stream, each with its own half of the workspace. */
+ * into.  Outside timing mode consecutive waves rotate over three internal streams forked
+ * from and joined to the caller's stream, each with its own third of the workspace. */
 int cm_last_wave_count(const cm_handle *h);
 
 /* Stand-alone element kernel for many elements (roofline measurement of the element kernel,
