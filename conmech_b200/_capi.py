@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libconmech_b200.so')
+# CONMECH_B200_LIB: another build of the same library (A/B timing of kernel variants); never a fallback
+LIB_PATH = os.environ.get('CONMECH_B200_LIB') or os.path.join(_HERE, 'lib', 'libconmech_b200.so')
 
 CM_OK = 0
 ST_OK, ST_NO_SUPPORT, ST_NO_FIXED_DOF, ST_SINGULAR, ST_ZERO_LOAD = 0, 1, 2, 3, 4

@@ -446,7 +446,7 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
 
 int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
-    if (variant < 0 || variant > 6) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..6");
+    if (variant < 0 || variant > 9) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..9");
     h->variant = variant;
     return CM_OK;
 }
@@ -513,13 +513,14 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         char *lws = two_lanes ? ws + (size_t)(w % NL) * (size_t)cap * per : ws;
         if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
         CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, ls));
+        if (h->variant != 0) { CU(cm_launch_schedule(h->L, lws, count, ls)); h->launches += 1; }
         if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
         if (h->variant == 0)
             CU(cm_launch_factor(h->m, h->L, lws, count, 0, ls));
         else
         {
             // variant -> CTA configuration of the dataflow kernel (0 automatic, 1: 8 warps, 2: 4 warps, 3: 16 warps)
-            const int cfg = h->variant == 1 ? 0 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2));
+            const int cfg = h->variant == 1 ? 0 : (h->variant >= 7 ? h->variant - 3 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2)));   // 7/8/9: 2/3/1 warps
             CU(cm_launch_factor_flow(h->m, h->L, lws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, ls));
         }
         if (h->timing) CU(cudaEventRecord(h->ev[2], ls));

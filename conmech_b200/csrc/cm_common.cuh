@@ -21,6 +21,8 @@
 #define CM_INFO_NFIXED 3
 #define CM_INFO_ZERO_LOAD 4        // bit lc set: ||P_lc|| <= eps
 #define CM_INFO_JACOBI 5           // 1: Jacobi scaling applied, 0: identity (a |k_ii| <= eps)
+#define CM_INFO_COST 6             // factorisation cost of the subset (float bits of its envelope flops; 0: nothing to factor)
+#define CM_INFO_SCHED 7            // scheduling: record r holds the slab index of the subset with the r-th largest cost
 
 // Element (r,k) of a 32x32 tile, "fragment-major" order: [k/4][(r%8)*4 + k%4][r/8].
 // For the FP64 MMA m8n8k4 (lane = 4*g + t) the four A (or B) fragments of k-step ks that a lane
@@ -114,6 +116,7 @@ cudaError_t cm_launch_element_generic(const double *xyz_u, const double *xyz_v, 
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,
                                       const cm_out_dev &out, cudaStream_t st);
+cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,

@@ -106,7 +106,11 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
                                                   const double *__restrict__ B, const double *__restrict__ d,
                                                   int nsteps, int lane) {
     const double *pa = A + lane * 4;
+#if defined(CM_EXP) && CM_EXP >= 1          // timing experiment (wrong results): B stream = A stream, meets it in L1
+    const double *pb = A + lane * 4;
+#else
     const double *pb = B + lane * 4;
+#endif
     const double *pd = d + (lane & 3);
     double a0[4], b0[4], a1[4], b1[4], d0, d1;
     ldg4s(a0, pa);
@@ -122,7 +126,11 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
             for (int i = 0; i < 4; ++i) b0[i] = (SYRK ? a0[i] : b0[i]) * nd;
             frag_mma<SYRK>(acc, a0, b0);
         }
+#if defined(CM_EXP) && CM_EXP >= 2          // timing experiment: the streams do not advance (operands from L1)
+        pd += 8;
+#else
         pa += 256; pb += 256; pd += 8;
+#endif
         if (q + 2 < nsteps) {
             ldg4s(a0, pa);
             if (!SYRK) ldg4s(b0, pb);

@@ -128,6 +128,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         info[CM_INFO_NFIXED] = n_fixed;
         info[CM_INFO_ZERO_LOAD] = 0;
         info[CM_INFO_JACOBI] = 1;
+        info[CM_INFO_COST] = 0;
     }
     if (status != CM_ST_OK) return;      // uniform for the block
 
@@ -222,6 +223,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     }
     __syncthreads();
     if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
+    if (t == 0) info[CM_INFO_COST] = __float_as_int((float)s_work + 1.0f);      // > 0, monotone in the work
     for (int I = t; I < NT; I += T) { kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1; }
     for (int i = t; i < NT * m.band_tiles; i += T) aflag_g[i] = s_aflag[i];
 
@@ -363,6 +365,40 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 }
 
 }  // namespace
+
+// Scheduling order of a wave for the factorisation: largest subsets first.  The subsets of a wave
+// differ in cost by more than an order of magnitude (20-90 % of the elements, cost ~ n b^2), the
+// hardware hands out CTAs in blockIdx order, and the launch ends with whatever was started last -
+// so the big ones go first and the tail of the launch is made of short CTAs.  Rank by counting
+// (stable: ties keep slab order), deterministic, no atomics: thread i compares its key with every
+// other key of the wave (staged through shared memory) and writes its slab index into record
+// `rank`.  count^2 integer comparisons - microseconds for the wave sizes in use.
+namespace {
+__global__ void __launch_bounds__(256) k2_schedule(cm_ws_layout L, char *ws, int count) {
+    __shared__ int s_key[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    auto info_of = [&](int s) { return reinterpret_cast<int *>(ws + (size_t)s * L.per_subset + L.off_info); };
+    const int mine = i < count ? info_of(i)[CM_INFO_COST] : -1;
+    int rank = 0;
+    for (int j0 = 0; j0 < count; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        __syncthreads();
+        s_key[threadIdx.x] = j < count ? info_of(j)[CM_INFO_COST] : -1;
+        __syncthreads();
+        const int n = min(256, count - j0);
+        for (int k = 0; k < n; ++k) {
+            const int key = s_key[k];
+            rank += (key > mine || (key == mine && j0 + k < i)) ? 1 : 0;
+        }
+    }
+    if (i < count) info_of(rank)[CM_INFO_SCHED] = i;
+}
+}  // namespace
+
+cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
+    k2_schedule<<<(count + 255) / 256, 256, 0, st>>>(L, ws, count);
+    return cudaGetLastError();
+}
 
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,

@@ -122,7 +122,7 @@ __device__ __noinline__ void diag_update(int I, int q0, int q1, int lane) {
 }
 
 template <int NW, bool PROF>
-__global__ void __launch_bounds__(NW * 32, NW <= 16 ? 16 / NW : 1)
+__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW <= 16 ? 16 / NW : 1))
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
@@ -140,7 +140,9 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     __shared__ long long s_tpub;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    char *slab = ws + (size_t)blockIdx.x * L.per_subset;
+    // CTA r factors the subset with the r-th largest cost of the wave (k2_schedule): big ones first
+    const int sb = reinterpret_cast<const int *>(ws + (size_t)blockIdx.x * L.per_subset + L.off_info)[CM_INFO_SCHED];
+    char *slab = ws + (size_t)sb * L.per_subset;
     int *info = reinterpret_cast<int *>(slab + L.off_info);
     if (info[CM_INFO_STATUS] != CM_ST_OK) return;
     const int NT = info[CM_INFO_NT];
@@ -269,10 +271,13 @@ cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, 
         }
         config = 2;
         if (count <= 2 * n_sm && m.band_tiles > 8) config = 1;
-        if (count <= n_sm && m.band_tiles > 16) config = 3;
+        if (m.band_tiles > 16) config = 3;       // config 5 (band of 35 tiles), 512 subsets, largest first: 16 warps 142 ms, 8 warps 147 ms, 4 warps 209 ms
     }
     if (config == 1) return prof ? launch_flow<8, true>(m, L, ws, count, st) : launch_flow<8, false>(m, L, ws, count, st);
     if (config == 3) return launch_flow<16, false>(m, L, ws, count, st);
+    if (config == 4) return launch_flow<2, false>(m, L, ws, count, st);
+    if (config == 5) return launch_flow<3, false>(m, L, ws, count, st);
+    if (config == 6) return launch_flow<1, false>(m, L, ws, count, st);
     return prof ? launch_flow<4, true>(m, L, ws, count, st) : launch_flow<4, false>(m, L, ws, count, st);
 }
 
