@@ -20,7 +20,7 @@ constexpr int DSCR = 2 * 32 * DS + 2 * 32;      // CTA scratch of the diagonal f
 struct K3Ctx {
     double *tiles; double *minv; double *dpiv; double *X;
     const int *kcol; const unsigned long long *arow; int *prog; int *yprog;
-    double *s_part; double *s_rhs; double *s_scr; double *s_minpiv; int *s_fail;
+    double *s_part; double *s_rhs; double *s_scr; double *s_minpiv; int *s_fail; double2 *s_dacc;
     long long *pc; long long *tpub;
     int bt, n_pad, n_lc, zero_bits;
 };
@@ -57,7 +57,7 @@ __device__ __forceinline__ double dneg(double x) {       // sign flip on the int
 // A pivot that violates the reference's rules (exact zero raises in SuperLU: numpy_stiffness.py:
 // 301-319; <= -1e-14 is rejected: :326-336; NaN fails both) sets *s_fail and is replaced by 1.
 // in_smem: the lower blocks of the tile were already placed in scr (row stride DS) by
-// diag_newest_to_smem(); otherwise the tile is read from T.
+// diag_term(); otherwise the tile is read from T.
 __device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
     double *scr = CTX(s_scr);
     double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
@@ -183,38 +183,52 @@ __device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
     __syncwarp();
 }
 
-// Newest term of the diagonal tile straight from the registers of R = L(I,I-1) (just solved):
-// lower blocks of  D(I,I) - R diag(d) R^T,  D(I,I) read from Dg (global, tile layout, older terms
-// already applied), result written to the diagonal scratch sA (row stride DS) where
-// diag_factor_blk() continues - the chain tile -> diagonal tile hand-over never touches global
-// memory.  Both MMA operands are register fragments of R: k-slot t of k-step (cs,e) is column
-// 8cs + 2t + e, the A fragment of row block ri is r.c[cs][e][ri] and the B fragment of output
-// column block cj is d_k * r.c[cs][e][cj] of the same lane.
-__device__ __forceinline__ void diag_newest_to_smem(const TileAcc &r, const double *Dg, const double *dJ, double *sA, int lane) {
+// Diagonal-tile term of a finished off-diagonal tile R = L(I,J), both MMA operands straight from the
+// registers of R (k-slot t of k-step (cs,e) is column 8cs + 2t + e: the A fragment of row block ri is
+// r.c[cs][e][ri], the B fragment of output column block cj is d_k * r.c[cs][e][cj] of the same lane):
+//     dacc -= R diag(d_J) R^T      (lower atoms only)
+// dacc is the warp's pending sum for the diagonal tile of its row in SHARED memory ([atom][lane]
+// double2, atom = ri(ri+1)/2 + cj; 16-byte accesses, conflict free) - the row of L is never read
+// back from global memory for the SYRK part of the diagonal tile.  For the chain tile (J = I-1,
+// Dg != nullptr) the result is instead completed with the assembled diagonal tile Dg (global, tile
+// layout) and written to the diagonal scratch sA (row stride DS) where diag_factor_blk() continues:
+// the chain tile -> diagonal tile hand-over never touches global memory.  Column blocks left of cs0
+// are zero in R (envelope).
+__device__ __forceinline__ void diag_term(const TileAcc &r, const double *Dg, const double2 (&dk)[4], double *sA,
+                                          double2 *dacc, int cs0, int lane) {
     const int g = lane >> 2, t = lane & 3;
+    const bool chain = Dg != nullptr;
     const double *pc = Dg + acc_cbase(lane);
-    double2 dk[4];
-#pragma unroll
-    for (int cs = 0; cs < 4; ++cs) dk[cs] = ldg2(dJ + cs * 8 + 2 * t);
 #pragma unroll
     for (int cj = 0; cj < 4; ++cj) {
         double c0[4], c1[4];
-        ldg4(c0, pc + cj * 256);
-        ldg4(c1, pc + cj * 256 + 4);
+#pragma unroll
+        for (int ri = cj; ri < 4; ++ri) {
+            const double2 v = dacc[(ri * (ri + 1) / 2 + cj) * 32 + lane];
+            c0[ri] = v.x; c1[ri] = v.y;
+        }
+        if (chain) {
+            double g0[4], g1[4];
+            ldg4(g0, pc + cj * 256);
+            ldg4(g1, pc + cj * 256 + 4);
+#pragma unroll
+            for (int ri = cj; ri < 4; ++ri) { c0[ri] += g0[ri]; c1[ri] += g1[ri]; }
+        }
 #pragma unroll
         for (int cs = 0; cs < 4; ++cs) {
+            if (cs < cs0) continue;
             const double nb0 = -(dk[cs].x * r.c[cs][0][cj]);
             const double nb1 = -(dk[cs].y * r.c[cs][1][cj]);
 #pragma unroll
-            for (int ri = 0; ri < 4; ++ri)
-                if (ri >= cj) dmma_m8n8k4(c0[ri], c1[ri], r.c[cs][0][ri], nb0);
+            for (int ri = cj; ri < 4; ++ri) dmma_m8n8k4(c0[ri], c1[ri], r.c[cs][0][ri], nb0);
 #pragma unroll
-            for (int ri = 0; ri < 4; ++ri)
-                if (ri >= cj) dmma_m8n8k4(c0[ri], c1[ri], r.c[cs][1][ri], nb1);
+            for (int ri = cj; ri < 4; ++ri) dmma_m8n8k4(c0[ri], c1[ri], r.c[cs][1][ri], nb1);
         }
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri)
-            if (ri >= cj) *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t) = make_double2(c0[ri], c1[ri]);
+        for (int ri = cj; ri < 4; ++ri) {
+            if (chain) *reinterpret_cast<double2 *>(sA + (8 * ri + g) * DS + 8 * cj + 2 * t) = make_double2(c0[ri], c1[ri]);
+            else dacc[(ri * (ri + 1) / 2 + cj) * 32 + lane] = make_double2(c0[ri], c1[ri]);
+        }
     }
 }
 

@@ -59,7 +59,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     int K = qs >> 3;
     FP_T0(pc);
     TileAcc acc;
-    if (K >= J && !has_a) {                       // no entries and no fill-in: the tile of L is zero
+    if (K >= J && !has_a && J != I - 1) {         // no entries and no fill-in: the tile of L is zero (the chain tile still hands the diagonal over)
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) stg4(T + i * 128 + lane * 4, 0.0, 0.0, 0.0, 0.0);
         return false;
@@ -90,6 +90,12 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
         __threadfence_block();
     }
     FP_ADD(pc, 7);
+    double2 dk[4];                                // pivots of block J for the diagonal term below: in flight with the y loads
+    {
+        const double *dJ = CTX(dpiv) + J * CM_TILE + 2 * (lane & 3);
+#pragma unroll
+        for (int cs = 0; cs < 4; ++cs) dk[cs] = ldg2(dJ + cs * 8);
+    }
     {
         const int n_lc = CTX(n_lc), zero_bits = CTX(zero_bits);
         double *s_part = CTX(s_part) + (threadIdx.x >> 5) * n_lc * 32;
@@ -104,21 +110,13 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
         }
     }
     FP_ADD(pc, 8);
-    if (J != I - 1) return false;
-    diag_newest_to_smem(acc, cm_tile_ptr(CTX(tiles), bt, I, I), CTX(dpiv) + J * CM_TILE, CTX(s_scr), lane);
-    FP_ADD(pc, 11);
-    return true;
-}
-
-// diagonal tile (I,I) -= sum over k-steps [q0, q1) of the own (final) row:  L(I,k) d_k L(I,k)^T
-__device__ __noinline__ void diag_update(int I, int q0, int q1, int lane) {
-    const int bt = CTX(bt);
-    double *tiles = CTX(tiles);
-    const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)q0 * 128;
-    TileAcc acc;
-    acc_load(acc, cm_tile_ptr(tiles, bt, I, I), lane);
-    acc_update_stream<true>(acc, A, nullptr, CTX(dpiv) + q0 * 4, q1 - q0, lane);
-    acc_store(acc, cm_tile_ptr(CTX(tiles), bt, I, I), lane);
+    // this tile's term of the diagonal tile of the row, from the same registers (pending sum in shared
+    // memory); the chain tile completes the diagonal tile and hands it to the factorisation
+    const bool chain = J == I - 1;
+    diag_term(acc, chain ? cm_tile_ptr(CTX(tiles), bt, I, I) : nullptr, dk, CTX(s_scr),
+              CTX(s_dacc) + (threadIdx.x >> 5) * 320, max(kcI - 8 * J, 0) >> 1, lane);
+    if (chain) FP_ADD(pc, 11); else FP_ADD(pc, 4);
+    return chain;
 }
 
 template <int NW, bool PROF>
@@ -129,7 +127,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     double *s_rhs = s_scr + DSCR;                                    // [NW][32] forward substitution scratch
     double *s_part = s_rhs + NW * 32;                                // [NW][n_lc][32] pending forward sums of the rows in progress
     double *s_minpiv = s_part + NW * m.n_lc * 32;                    // [NW]
-    int *s_prog = reinterpret_cast<int *>(s_minpiv + NW);            // [n_tile_rows_max] factor progress
+    double2 *s_dacc = reinterpret_cast<double2 *>(s_minpiv + NW + (NW & 1));   // [NW][10][32] pending diagonal-tile sums (16-byte aligned)
+    int *s_prog = reinterpret_cast<int *>(s_dacc + NW * 320);        // [n_tile_rows_max] factor progress
     int *s_yprog = s_prog + m.n_tile_rows_max;                       // rows forward-substituted
     int *s_fail = s_yprog + 1;
     int *s_kcol = s_yprog + 4;                                       // [n_tile_rows_max] envelope: first nonzero k-step of each row
@@ -162,7 +161,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     if (t == 0) {
         s_ctx.tiles = tiles; s_ctx.minv = minv; s_ctx.dpiv = dpiv; s_ctx.X = X;
         s_ctx.kcol = s_kcol; s_ctx.arow = s_arow; s_ctx.prog = s_prog; s_ctx.yprog = s_yprog;
-        s_ctx.s_part = s_part; s_ctx.s_rhs = s_rhs; s_ctx.s_scr = s_scr; s_ctx.s_minpiv = s_minpiv; s_ctx.s_fail = s_fail;
+        s_ctx.s_part = s_part; s_ctx.s_rhs = s_rhs; s_ctx.s_scr = s_scr; s_ctx.s_minpiv = s_minpiv; s_ctx.s_fail = s_fail; s_ctx.s_dacc = s_dacc;
         s_ctx.pc = PROF ? &s_pc[0][0] : nullptr; s_ctx.tpub = &s_tpub;
         s_ctx.bt = bt; s_ctx.n_pad = L.n_pad; s_ctx.n_lc = n_lc; s_ctx.zero_bits = zero_bits;
     }
@@ -184,18 +183,18 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     if (PROF && lane == 0) for (int i = 0; i < 16; ++i) pc[i] = 0;
     const long long tstart = PROF ? clock64() : 0;
     double *s_part_w = s_part + warp * n_lc * 32;
+    double2 *s_dacc_w = s_dacc + warp * 320;
     for (int I = warp; I < NT; I += NW) {
         const int kcI = s_kcol[I];               // first nonzero column of the row in k-steps (even)
         const int kfI = kcI >> 3;                // = kfirst[I], the first tile column of the row
         for (int lc = 0; lc < n_lc; ++lc) s_part_w[lc * 32 + lane] = 0.0;
+        if (kfI < I) {                           // pending sum of the diagonal tile (diag_term)
+#pragma unroll
+            for (int a = 0; a < 10; ++a) s_dacc_w[a * 32 + lane] = make_double2(0.0, 0.0);
+        }
         __syncwarp();
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
         for (int J = kfI; J < I; ++J) {
-            if (J == I - 1 && I - 2 >= kfI) {    // look-ahead: diagonal terms that do not need row I-1
-                FP_T0(pc);
-                diag_update(I, kcI, 8 * (I - 1), lane);
-                FP_ADD(pc, 4);
-            }
             handed = offdiag_tile<PROF>(I, J, kcI, lane);
             __threadfence_block();
             __syncwarp();
@@ -236,7 +235,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
 }
 
 size_t flow_smem(const cm_model_dev &m, int nw) {
-    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw) * sizeof(double) +
+    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw + (nw & 1) + nw * 640) * sizeof(double) +
            (size_t)(2 * m.n_tile_rows_max + 8) * sizeof(int) + (size_t)m.n_tile_rows_max * ((m.band_tiles + 63) >> 6) * sizeof(unsigned long long);
 }
 
