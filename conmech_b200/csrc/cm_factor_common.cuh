@@ -91,15 +91,26 @@ __device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
             s_col[lane] = p[c];
             __syncwarp();
             double d = s_col[c0 + c];
-            if (!(d > -CM_EPS) || d == 0.0) { fail = 1; d = 1.0; }
+            // The pivot -> next pivot recurrence is the critical path of the whole kernel, and every
+            // dependent FP64 instruction on it queues behind the other warps' DMMAs.  Keep it to the
+            // reciprocal (hardware seed, relative error <= 2^-23, and ONE cubic Newton step:
+            // x (1 + e + e^2), error e^3) and one FMA per updated entry: the products with the pivot
+            // row do not need the reciprocal and are formed while it is computed.
+            double u[8];
+#pragma unroll
+            for (int k = c + 1; k < 8; ++k) u[k] = p[c] * s_col[c0 + k];
+            double x;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+            const double e = fma(-d, x, 1.0);
+            const double t2 = fma(e, e, e);
+            double rinv = fma(x, t2, x);
+            if (!(d > -CM_EPS) || d == 0.0) { fail = 1; d = 1.0; rinv = 1.0; }
             minpiv = fmin(minpiv, d);
-            const double rinv = fast_rcp(d);
             if (lane == c0 + c) { dmine = d; rmine = rinv; }
             pk[c] = p[c];                        // (L D)[lane][c0+c]
-            const double l = p[c] * rinv;        // L[lane][c0+c] for lane > c0+c (unused otherwise)
-            p[c] = l;
 #pragma unroll
-            for (int k = c + 1; k < 8; ++k) p[k] -= l * s_col[c0 + k];
+            for (int k = c + 1; k < 8; ++k) p[k] = fma(-u[k], rinv, p[k]);
+            p[c] = p[c] * rinv;                  // L[lane][c0+c] for lane > c0+c (unused otherwise)
             __syncwarp();
         }
 #pragma unroll
@@ -189,16 +200,14 @@ __device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
 //     dacc -= R diag(d_J) R^T      (lower atoms only)
 // dacc is the warp's pending sum for the diagonal tile of its row in SHARED memory ([atom][lane]
 // double2, atom = ri(ri+1)/2 + cj; 16-byte accesses, conflict free) - the row of L is never read
-// back from global memory for the SYRK part of the diagonal tile.  For the chain tile (J = I-1,
-// Dg != nullptr) the result is instead completed with the assembled diagonal tile Dg (global, tile
-// layout) and written to the diagonal scratch sA (row stride DS) where diag_factor_blk() continues:
-// the chain tile -> diagonal tile hand-over never touches global memory.  Column blocks left of cs0
+// back from global memory for the SYRK part of the diagonal tile.  The sum starts from the assembled
+// diagonal tile (loaded at the start of the row, off the critical path).  For the chain tile
+// (J = I-1) the result is written to the diagonal scratch sA (row stride DS) where
+// diag_factor_blk() continues: the chain tile -> diagonal tile hand-over never touches global memory.  Column blocks left of cs0
 // are zero in R (envelope).
-__device__ __forceinline__ void diag_term(const TileAcc &r, const double *Dg, const double2 (&dk)[4], double *sA,
+__device__ __forceinline__ void diag_term(const TileAcc &r, bool chain, const double2 (&dk)[4], double *sA,
                                           double2 *dacc, int cs0, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    const bool chain = Dg != nullptr;
-    const double *pc = Dg + acc_cbase(lane);
 #pragma unroll
     for (int cj = 0; cj < 4; ++cj) {
         double c0[4], c1[4];
@@ -206,13 +215,6 @@ __device__ __forceinline__ void diag_term(const TileAcc &r, const double *Dg, co
         for (int ri = cj; ri < 4; ++ri) {
             const double2 v = dacc[(ri * (ri + 1) / 2 + cj) * 32 + lane];
             c0[ri] = v.x; c1[ri] = v.y;
-        }
-        if (chain) {
-            double g0[4], g1[4];
-            ldg4(g0, pc + cj * 256);
-            ldg4(g1, pc + cj * 256 + 4);
-#pragma unroll
-            for (int ri = cj; ri < 4; ++ri) { c0[ri] += g0[ri]; c1[ri] += g1[ri]; }
         }
 #pragma unroll
         for (int cs = 0; cs < 4; ++cs) {

@@ -227,19 +227,6 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     for (int I = t; I < NT; I += T) { kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1; }
     for (int i = t; i < NT * m.band_tiles; i += T) aflag_g[i] = s_aflag[i];
 
-    // ---- zero the tiles that will receive entries (16-byte stores); structurally empty tiles of the
-    // envelope are left untouched - the factorisation starts their accumulators from zero
-    {
-        const int bt = m.band_tiles;
-        double2 z2 = make_double2(0.0, 0.0);
-        for (int I = 0; I < NT; ++I)
-            for (int K = s_kfirst[I]; K <= I; ++K) {
-                if (!s_aflag[I * bt + (K - I + bt - 1)]) continue;
-                double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS);
-                for (int i = t; i < CM_TILE_ELEMS / 2; i += T) dst[i] = z2;
-            }
-    }
-
     // ---- diagonal of K_mm and the Jacobi scale (numpy_stiffness.py:283-290)
     int ok = 1;
     for (int idx = t; idx < 6 * nV; idx += T) {
@@ -248,17 +235,20 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         int r = node_row(m, v, i, s_base[v]);
         if (r < 0) continue;
         double kii = 0.0;
+        // (table reads are unconditional and the mask only selects: the loads of consecutive elements
+        // are then independent of the branch and overlap; adding 0.0 for an absent element is exact)
+#pragma unroll 4
         for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
-            int e = m.ne_elem[p];
-            if (!elem_on(s_mask, e)) continue;
-            int l = 6 * m.ne_end[p] + i;
-            kii += thr(m.Kg[(size_t)e * 144 + l * 12 + l]);
+            const int e = m.ne_elem[p];
+            const int l = 6 * m.ne_end[p] + i;
+            const double kv = thr(m.Kg[(size_t)e * 144 + l * 12 + l]);
+            kii += elem_on(s_mask, e) ? kv : 0.0;
         }
         dinv[r] = kii;
         if (!(fabs(kii) > CM_EPS)) ok = 0;
     }
     if (!ok) atomicOr(&s_red[3], 1);
-    __syncthreads();           // also orders the zero fill before the scatter below
+    __syncthreads();
     const int jacobi = s_red[3] ? 0 : 1;
     for (int r = t; r < NT * CM_TILE; r += T) {
         double d = 1.0;
@@ -271,10 +261,40 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     // ---- gather assembly, one warp per node: the 6x6 diagonal block (lower triangle) and one 6x6
     // block per lower pair (a,c) - 36 entries each, all entries of the node spread over the lanes.
     // An entry sums its contributing element entries in ascending element id.
+    //
+    // The tiles that receive entries are zero-filled first (16-byte stores; structurally empty tiles
+    // of the envelope are left untouched - the factorisation starts their accumulators from zero).
+    // Fill and scatter are interleaved in chunks of one node per warp in solver order (~1.5 tile
+    // rows): the 8-byte entry stores then meet their freshly zeroed sectors in L2 - with some 900
+    // CTAs resident a whole-matrix fill (2.4 MB per CTA) would be evicted to DRAM before the
+    // scatter and every entry would cost a sector read-modify-write there.
     {
         const int bt = m.band_tiles;
         const int lane = t & 31, warp = t >> 5, nw = T >> 5;
-        for (int a = warp; a < nV; a += nw) {
+        int zI = 0;                                   // tile rows [0, zI) are zero-filled
+        for (int pc = 0; pc < nV; pc += nw) {
+            // last solver row of the chunk = end of its last existing node
+            int Iend = zI;
+            {
+                const int pl = min(pc + nw, nV) - 1;
+                const int vl = m.order[pl];
+                const int rl = s_base[vl] + s_free[vl];         // s_base is an exclusive scan: rows of all nodes up to pl end here
+                Iend = pl == nV - 1 ? NT : min(NT, (rl + CM_TILE - 1) / CM_TILE);
+            }
+            if (Iend > zI) {
+                const double2 z2 = make_double2(0.0, 0.0);
+                for (int I = zI; I < Iend; ++I)
+                    for (int K = s_kfirst[I]; K <= I; ++K) {
+                        if (!s_aflag[I * bt + (K - I + bt - 1)]) continue;
+                        double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS);
+                        for (int i = t; i < CM_TILE_ELEMS / 2; i += T) dst[i] = z2;
+                    }
+                zI = Iend;
+                __syncthreads();                      // (uniform: every thread computes the same Iend)
+            }
+            const int pa = pc + warp;
+            if (pa >= nV) continue;
+            const int a = m.order[pa];
             if (s_free[a] == 0) continue;
             const int base_a = s_base[a];
             const int p0 = m.ne_ptr[a], p1 = m.ne_ptr[a + 1];
@@ -291,11 +311,12 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     if (j > i) continue;
                     cc = node_row(m, a, j, base_a);
                     if (cc < 0) continue;
+#pragma unroll 4
                     for (int p = p0; p < p1; ++p) {
                         const int e = m.ne_elem[p];
-                        if (!elem_on(s_mask, e)) continue;
                         const int o = 6 * m.ne_end[p];
-                        s += thr(m.Kg[(size_t)e * 144 + (o + i) * 12 + o + j]);
+                        const double kv = thr(m.Kg[(size_t)e * 144 + (o + i) * 12 + o + j]);
+                        s += elem_on(s_mask, e) ? kv : 0.0;
                     }
                 } else {
                     const int q = q0 + blk - 1;
@@ -306,10 +327,11 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     bool any = false;
                     for (int pe = m.lp_eptr[q]; pe < m.lp_eptr[q + 1]; ++pe) {
                         const int e = m.lp_elem[pe];
-                        if (!elem_on(s_mask, e)) continue;
                         const int ea = m.lp_end[pe];
-                        s += thr(m.Kg[(size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea) + j]);
-                        any = true;
+                        const double kv = thr(m.Kg[(size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea) + j]);
+                        const bool on = elem_on(s_mask, e);
+                        s += on ? kv : 0.0;
+                        any |= on;
                     }
                     if (!any) continue;          // no existing element joins the pair: the tile may be unassembled
                 }
@@ -336,10 +358,11 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             int v = idx / 6, i = idx - 6 * v;
             double pv = m.pnodal[(size_t)lc * 6 * nV + idx];
             double qs = 0.0;
+#pragma unroll 4
             for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
-                int e = m.ne_elem[p];
-                if (!elem_on(s_mask, e)) continue;
-                qs += m.q[((size_t)lc * m.nE + e) * 12 + 6 * m.ne_end[p] + i];
+                const int e = m.ne_elem[p];
+                const double qv = m.q[((size_t)lc * m.nE + e) * 12 + 6 * m.ne_end[p] + i];
+                qs += elem_on(s_mask, e) ? qv : 0.0;
             }
             pv += qs;
             Pl[idx] = pv;

@@ -113,7 +113,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     // this tile's term of the diagonal tile of the row, from the same registers (pending sum in shared
     // memory); the chain tile completes the diagonal tile and hands it to the factorisation
     const bool chain = J == I - 1;
-    diag_term(acc, chain ? cm_tile_ptr(CTX(tiles), bt, I, I) : nullptr, dk, CTX(s_scr),
+    diag_term(acc, chain, dk, CTX(s_scr),
               CTX(s_dacc) + (threadIdx.x >> 5) * 320, max(kcI - 8 * J, 0) >> 1, lane);
     if (chain) FP_ADD(pc, 11); else FP_ADD(pc, 4);
     return chain;
@@ -188,9 +188,21 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         const int kcI = s_kcol[I];               // first nonzero column of the row in k-steps (even)
         const int kfI = kcI >> 3;                // = kfirst[I], the first tile column of the row
         for (int lc = 0; lc < n_lc; ++lc) s_part_w[lc * 32 + lane] = 0.0;
-        if (kfI < I) {                           // pending sum of the diagonal tile (diag_term)
+        if (I + NW < NT) {                       // the diagonal tile of this warp's next row comes from DRAM: request it now
+            const double *nx = cm_tile_ptr(tiles, bt, I + NW, I + NW) + lane * 16;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nx));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 512));
+        }
+        if (kfI < I) {                           // pending sum of the diagonal tile (diag_term) starts from the assembled tile
+            const double *pd = cm_tile_ptr(tiles, bt, I, I) + acc_cbase(lane);
 #pragma unroll
-            for (int a = 0; a < 10; ++a) s_dacc_w[a * 32 + lane] = make_double2(0.0, 0.0);
+            for (int cj = 0; cj < 4; ++cj) {
+                double g0[4], g1[4];
+                ldg4s(g0, pd + cj * 256);
+                ldg4s(g1, pd + cj * 256 + 4);
+#pragma unroll
+                for (int ri = cj; ri < 4; ++ri) s_dacc_w[(ri * (ri + 1) / 2 + cj) * 32 + lane] = make_double2(g0[ri], g1[ri]);
+            }
         }
         __syncwarp();
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
