@@ -500,7 +500,8 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
     const int NL = h->n_lanes;
     const bool two_lanes = !h->timing && h->overlap && NL > 1 && h->lane_stream[0] && B > wave / NL && wave / NL >= sm_fill;
     const long long cap = two_lanes ? wave / NL : wave;
-    const long long n_waves = (B + cap - 1) / cap;
+    long long n_waves = (B + cap - 1) / cap;
+    if (two_lanes && getenv("CM_WAVE_ROUND") && atoi(getenv("CM_WAVE_ROUND")) && n_waves % NL) n_waves += NL - n_waves % NL;   // experiment: same number of waves per lane
     const long long wsize = (B + n_waves - 1) / n_waves;
     if (two_lanes) {
         CU(cudaEventRecord(h->lane_ev[0], st));
@@ -577,7 +578,8 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
     // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
     // (the driver is only asked about free memory when the workspace has to grow)
     const size_t per = h->L.per_subset;
-    size_t want = std::min<size_t>(Bn, 4096) * per;
+    static const size_t ws_subsets = getenv("CM_WS_SUBSETS") ? (size_t)std::max(1, atoi(getenv("CM_WS_SUBSETS"))) : 8192;      // 4096: 266 k, 8192: 273 k, 12500: 272 k solves/s on config 3 (profiles/r01c_experiments.txt)
+    size_t want = std::min<size_t>(Bn, ws_subsets) * per;
     if (want > h->ws_bytes) {
         size_t freeb = 0, totalb = 0;
         CU(cudaMemGetInfo(&freeb, &totalb));

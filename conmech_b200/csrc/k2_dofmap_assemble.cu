@@ -258,42 +258,40 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     if (t == 0) info[CM_INFO_JACOBI] = jacobi;
     __syncthreads();
 
-    // ---- gather assembly, one warp per node: the 6x6 diagonal block (lower triangle) and one 6x6
-    // block per lower pair (a,c) - 36 entries each, all entries of the node spread over the lanes.
+    // ---- gather assembly.  Per node: the 6x6 diagonal block (lower triangle) and one 6x6 block per
+    // lower pair (a,c) - 36 entries each, all entries of the node spread over the lanes of a warp.
     // An entry sums its contributing element entries in ascending element id.
     //
-    // The tiles that receive entries are zero-filled first (16-byte stores; structurally empty tiles
-    // of the envelope are left untouched - the factorisation starts their accumulators from zero).
-    // Fill and scatter are interleaved in chunks of one node per warp in solver order (~1.5 tile
-    // rows): the 8-byte entry stores then meet their freshly zeroed sectors in L2 - with some 900
-    // CTAs resident a whole-matrix fill (2.4 MB per CTA) would be evicted to DRAM before the
-    // scatter and every entry would cost a sector read-modify-write there.
+    // One warp per TILE ROW, no block barrier: the warp zero-fills the row's tiles that receive
+    // entries (16-byte stores; structurally empty tiles of the envelope are left untouched - the
+    // factorisation starts their accumulators from zero) and then scatters the entries of the
+    // nodes whose rows fall into this tile row - a node that straddles two tile rows is visited by
+    // both owners, each taking its rows.  The 8-byte entry stores meet their freshly zeroed sectors
+    // in L1/L2; with a whole-matrix fill first (2.4 MB per CTA, some 900 CTAs resident) the zeros
+    // were evicted to DRAM before the scatter and every entry cost a sector read-modify-write there.
+    // s_tmp[p] = first solver row of the node at position p of the static order (exclusive scan above).
     {
         const int bt = m.band_tiles;
         const int lane = t & 31, warp = t >> 5, nw = T >> 5;
-        int zI = 0;                                   // tile rows [0, zI) are zero-filled
-        for (int pc = 0; pc < nV; pc += nw) {
-            // last solver row of the chunk = end of its last existing node
-            int Iend = zI;
+        for (int IR = warp; IR < NT; IR += nw) {
             {
-                const int pl = min(pc + nw, nV) - 1;
-                const int vl = m.order[pl];
-                const int rl = s_base[vl] + s_free[vl];         // s_base is an exclusive scan: rows of all nodes up to pl end here
-                Iend = pl == nV - 1 ? NT : min(NT, (rl + CM_TILE - 1) / CM_TILE);
-            }
-            if (Iend > zI) {
                 const double2 z2 = make_double2(0.0, 0.0);
-                for (int I = zI; I < Iend; ++I)
-                    for (int K = s_kfirst[I]; K <= I; ++K) {
-                        if (!s_aflag[I * bt + (K - I + bt - 1)]) continue;
-                        double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS);
-                        for (int i = t; i < CM_TILE_ELEMS / 2; i += T) dst[i] = z2;
-                    }
-                zI = Iend;
-                __syncthreads();                      // (uniform: every thread computes the same Iend)
+                for (int K = s_kfirst[IR]; K <= IR; ++K) {
+                    if (!s_aflag[IR * bt + (K - IR + bt - 1)]) continue;
+                    double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)IR * bt + (K - IR + bt - 1)) * CM_TILE_ELEMS);
+#pragma unroll 4
+                    for (int i = lane; i < CM_TILE_ELEMS / 2; i += 32) dst[i] = z2;
+                }
             }
-            const int pa = pc + warp;
-            if (pa >= nV) continue;
+            __syncwarp();
+            // first position whose node ends beyond the first row of the tile row (binary search on the scan)
+            const int row0 = IR * CM_TILE, row1 = min(row0 + CM_TILE, ns);
+            int lo = 0, hi = nV;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_tmp[mid] + s_free[m.order[mid]] > row0) hi = mid; else lo = mid + 1;
+            }
+            for (int pa = lo; pa < nV && s_tmp[pa] < row1; ++pa) {
             const int a = m.order[pa];
             if (s_free[a] == 0) continue;
             const int base_a = s_base[a];
@@ -304,7 +302,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                 const int blk = idx / 36, ij = idx - 36 * blk;
                 const int i = ij / 6, j = ij - 6 * i;
                 const int r = node_row(m, a, i, base_a);
-                if (r < 0) continue;
+                if (r < 0 || (r >> 5) != IR) continue;
                 int cc;
                 double s = 0.0;
                 if (blk == 0) {
@@ -339,7 +337,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                 const int I = r >> 5, K = cc >> 5;
                 tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = s;
             }
+            }
         }
+        __syncthreads();
         // unit diagonal on the padding rows of the last tile
         for (int r = ns + t; r < NT * CM_TILE; r += T) {
             int I = r >> 5;

@@ -279,7 +279,7 @@ class CudaStiffness(StiffnessBase):
         return res
 
     def solve_many_device(self, masks, want=('flag', 'status', 'max_trans', 'compliance'), out=None,
-                          max_in_flight=4096):
+                          max_in_flight=None):
         """Same on DEVICE buffers: ``masks`` is a (B, words) int32/uint32 torch CUDA tensor; outputs
         are torch CUDA tensors; kernels are enqueued on torch's current stream and the call
         returns without synchronising."""
@@ -302,6 +302,8 @@ class CudaStiffness(StiffnessBase):
                 setattr(od, name, tns.data_ptr())
             else:
                 setattr(od, name, 0)
+        if max_in_flight is None:
+            max_in_flight = int(os.environ.get('CM_WS_SUBSETS', 8192))
         n_fly = int(min(B, max_in_flight))
         nbytes = int(self._lib.cm_workspace_bytes(self._handle, n_fly))
         key = (dev.index, self._n_lc)
