@@ -30,8 +30,8 @@ METRIC = 'partial-structure solves/sec (1k-elem frame)'
 UNIT = 'solves/s'
 FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool's B200 (round 1)
 # DRAM bytes (read + write) of ONE k3_factor_flow launch over 4096 config-3 subsets, from the ncu --set full
-# capture summarised in profiles/r01b_ncu_k2_k3_k4.txt (29.82 GB read + 11.45 GB written)
-K3_DRAM_BYTES_PER_SUBSET = (29.818193e9 + 11.446938e9) / 4096
+# capture summarised in profiles/r01c_ncu_k2_k3_k4.txt (24.66 GB read + 9.52 GB written)
+K3_DRAM_BYTES_PER_SUBSET = (24.656677e9 + 9.519647e9) / 4096
 
 
 def parse():
@@ -307,7 +307,7 @@ def main():
                 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
                 'traffic': K3_DRAM_BYTES_PER_SUBSET * subsets_per_launch,
                 'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum of one k3_factor_flow launch '
-                                  '(4096 subsets), scaled to this launch size; profiles/r01b_ncu_k2_k3_k4.txt',
+                                  '(4096 subsets), scaled to this launch size; profiles/r01c_ncu_k2_k3_k4.txt',
                 'peak_source': 'cuBLAS DGEMM 8192^3 fp64 measured live in this run (MEASURED_PEAKS.json has no '
                                'fp64 entry; earlier measurement on this pool {} TFLOP/s)'.format(FP64_FALLBACK_TFLOPS),
                 'algorithmic_flops_per_launch': flops_per_launch,

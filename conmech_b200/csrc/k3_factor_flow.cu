@@ -120,7 +120,10 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
 }
 
 template <int NW, bool PROF>
-__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW <= 16 ? 16 / NW : 1))
+#ifndef CM_K3_CTAS4
+#define CM_K3_CTAS4 4          // resident 4-warp CTAs per SM the register allocation aims at (timing experiments: 5)
+#endif
+__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 4 ? CM_K3_CTAS4 : (NW <= 16 ? 16 / NW : 1)))
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
