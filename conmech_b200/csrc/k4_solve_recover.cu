@@ -15,46 +15,56 @@ constexpr int K4_WARPS = K4_THREADS / 32;
 __device__ __forceinline__ double thr(double k) { return (fabs(k) > CM_EPS) ? k : 0.0; }
 __device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (mask[e >> 5] >> (e & 31)) & 1u; }
 
-// colsum[ks] (valid on lanes 0..3, column 4*ks + lane) = sum_r T[r][4*ks + lane] * w[r] for a tile in
-// fragment-major layout; w4 holds w[i*8 + lane/4], i = 0..3.  One 32-byte load per lane and k-step.
-__device__ __forceinline__ void tile_tmatvec(const double *__restrict__ T, const double (&w4)[4], double (&cs)[8], int lane) {
+// NB right-hand sides at once.  cs[j][ks] (valid on lanes 0..3, column 4*ks + lane) =
+// sum_r T[r][4*ks + lane] * w_j[r] for a tile in fragment-major layout; w4[j] holds
+// w_j[i*8 + lane/4], i = 0..3.  One 32-byte load per lane and k-step, shared by the NB vectors.
+template <int NB>
+__device__ __forceinline__ void tile_tmatvec(const double *__restrict__ T, const double (&w4)[NB][4], double (&cs)[NB][8], int lane) {
     const double *p = T + lane * 4;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         double v[4];
         ldg4(v, p + q * 128);
-        cs[q] = v[0] * w4[0] + v[1] * w4[1] + v[2] * w4[2] + v[3] * w4[3];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) cs[j][q] = v[0] * w4[j][0] + v[1] * w4[j][1] + v[2] * w4[j][2] + v[3] * w4[j][3];
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 4);
-        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
-        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
-    }
+    for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            cs[j][q] += __shfl_xor_sync(0xffffffffu, cs[j][q], 4);
+            cs[j][q] += __shfl_xor_sync(0xffffffffu, cs[j][q], 8);
+            cs[j][q] += __shfl_xor_sync(0xffffffffu, cs[j][q], 16);
+        }
 }
 
-// x = M^T w for a lower-triangular M_J tile in the cm_mtile_off layout: cs[2cj + e] (valid on lanes
-// 0..3) = column 8cj + 2*lane + e.  Only the stored blocks (row block >= column block) are read.
-__device__ __forceinline__ void mtile_tmatvec(const double *__restrict__ M, const double (&w4)[4], double (&cs)[8], int lane) {
+// x_j = M^T w_j for a lower-triangular M_J tile in the cm_mtile_off layout: cs[j][2cj + e] (valid on
+// lanes 0..3) = column 8cj + 2*lane + e.  Only the stored blocks (row block >= column block) are read.
+template <int NB>
+__device__ __forceinline__ void mtile_tmatvec(const double *__restrict__ M, const double (&w4)[NB][4], double (&cs)[NB][8], int lane) {
     const double *p = M + lane * 2;
 #pragma unroll
     for (int cj = 0; cj < 4; ++cj) {
-        double sx = 0.0, sy = 0.0;
+        double sx[NB], sy[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { sx[j] = 0.0; sy[j] = 0.0; }
 #pragma unroll
         for (int i = cj; i < 4; ++i) {
             const double2 b = ldg2(p + i * 256 + cj * 64);
-            sx += b.x * w4[i];
-            sy += b.y * w4[i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) { sx[j] += b.x * w4[j][i]; sy[j] += b.y * w4[j][i]; }
         }
-        cs[2 * cj] = sx;
-        cs[2 * cj + 1] = sy;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { cs[j][2 * cj] = sx[j]; cs[j][2 * cj + 1] = sy[j]; }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 4);
-        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
-        cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
-    }
+    for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            cs[j][q] += __shfl_xor_sync(0xffffffffu, cs[j][q], 4);
+            cs[j][q] += __shfl_xor_sync(0xffffffffu, cs[j][q], 8);
+            cs[j][q] += __shfl_xor_sync(0xffffffffu, cs[j][q], 16);
+        }
 }
 // where mtile_tmatvec leaves column q of its result: block 8*(q/2), lane pair 2*lane, parity q%2
 __device__ __forceinline__ int mcol(int q, int lane) { return ((q >> 1) << 3) + 2 * lane + (q & 1); }
@@ -88,16 +98,18 @@ __device__ double block_nanmax(double v, double *s_red) {
     return tot;
 }
 
-// XS: the solution vector of the load case in progress lives in shared memory (n_pad doubles).  The
-// back substitution is a chain of one step per tile row, and every step reads and writes a few
+// XS: the solution vectors of the load cases in progress live in shared memory (n_pad doubles each).
+// The back substitution is a chain of one step per tile row, and every step reads and writes a few
 // entries of x: from shared memory the chain step is one DRAM access (the tile) instead of five
-// dependent global round trips.
-template <bool XS>
+// dependent global round trips.  NB load cases share one pass over L (every tile is read once for
+// the NB right-hand sides); the recovery below then runs per load case.
+template <bool XS, int NB>
 __global__ void __launch_bounds__(K4_THREADS)
 k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
                  cm_out_dev out) {
+    static_assert(XS || NB == 1, "several right-hand sides per pass need the shared-memory vectors");
     __shared__ double s_red[K4_WARPS];
-    extern __shared__ __align__(16) double s_x[];
+    extern __shared__ __align__(16) double s_x[];            // XS: [NB][n_pad] solutions, then [n_pad] pivots
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long gs = first + blockIdx.x;
@@ -116,11 +128,96 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
     const uint32_t *mask = masks + (size_t)gs * m.mask_words;
     const int bt = m.band_tiles, nV = m.nV, nE = m.nE, n_lc = m.n_lc;
     const int zero_bits = info[CM_INFO_ZERO_LOAD];
+    const int n_pad = L.n_pad;
 
     if (out.min_pivot && t == 0)
-        out.min_pivot[gs] = (status == CM_ST_OK || status == CM_ST_SINGULAR) ? dpiv[L.n_pad] : nan("");
+        out.min_pivot[gs] = (status == CM_ST_OK || status == CM_ST_SINGULAR) ? dpiv[n_pad] : nan("");
 
-    for (int lc = 0; lc < n_lc; ++lc) {
+    for (int lc0 = 0; lc0 < n_lc; lc0 += NB) {
+      // ---- back substitution of the load cases lc0 .. lc0+NB-1 in one pass over L (status OK only;
+      // a load case with a zero load vector rides along as x = 0)
+      const double *dpl = XS ? s_x + NB * n_pad : dpiv;       // pivots next to x (copied below)
+      if (status == CM_ST_OK) {
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+              const int lc = lc0 + j;
+              const bool live = lc < n_lc && !((zero_bits >> lc) & 1);
+              any |= live;
+              double *Xg = X + (size_t)(lc < n_lc ? lc : 0) * n_pad;
+              double *Xl = XS ? s_x + j * n_pad : Xg;
+              for (int r = t; r < NT * CM_TILE; r += K4_THREADS) {
+                  const double d = dpiv[r];
+                  if (XS && j == 0) s_x[NB * n_pad + r] = d;
+                  Xl[r] = live ? Xg[r] / d : 0.0;
+              }
+          }
+          __syncthreads();
+          if (any) {
+            // L^T x = D^-1 y, row-oriented: once x_I is known every tile (I,J) of block row I
+            // (contiguous in memory) subtracts L(I,J)^T x_I from the pending sum of block J; the warp
+            // that owns tile (I,I-1) then finishes x_{I-1} = M^T (d .* s) with M = D^-1 L_JJ^-1 left by
+            // the factorisation.  One barrier per row.
+            double *Xb = XS ? s_x : X + (size_t)lc0 * n_pad;   // vector j at Xb + j*n_pad (NB == 1 without XS)
+            const int g = lane >> 2;
+            auto finish_block = [&](int J) {                   // x_J = M_J^T (d .* s_J), one warp
+                double w4[NB][4], cs[NB][8];
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w4[j][i] = dpl[J * CM_TILE + i * 8 + g] * Xb[j * n_pad + J * CM_TILE + i * 8 + g];
+                mtile_tmatvec<NB>(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
+                __syncwarp();
+                if (lane < 4)
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) Xb[j * n_pad + J * CM_TILE + mcol(q, lane)] = cs[j][q];
+            };
+            if (warp == 0) finish_block(NT - 1);
+            for (int I = NT - 1; I > 0; --I) {
+                // M_{I-1} is needed at the end of this row's chain: start its DRAM read now
+                if (warp == 0) {
+                    const double *Mn = minv + (size_t)(I - 1) * CM_TILE_ELEMS;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + lane * 16));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + 512 + lane * 16));
+                }
+                // ... and so are the tiles of the next row: request this warp's share one row ahead
+                if (I >= 2) {
+                    const int kfn = kfirst[I - 1];
+                    for (int J = I - 2 - warp; J >= kfn; J -= K4_WARPS) {
+                        const double *Tn = cm_tile_ptr(tiles, bt, I - 1, J) + lane * 16;
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn + 512));
+                    }
+                }
+                __syncthreads();
+                const int kf = kfirst[I];
+                double x4[NB][4];
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x4[j][i] = Xb[j * n_pad + I * CM_TILE + i * 8 + g];
+                for (int J = I - 1 - warp; J >= kf; J -= K4_WARPS) {
+                    double cs[NB][8];
+                    tile_tmatvec<NB>(cm_tile_ptr(tiles, bt, I, J), x4, cs, lane);
+                    if (lane < 4)
+#pragma unroll
+                        for (int j = 0; j < NB; ++j)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) Xb[j * n_pad + J * CM_TILE + q * 4 + lane] -= cs[j][q];
+                    if (J == I - 1) {
+                        __syncwarp();
+                        finish_block(J);
+                    }
+                }
+                // row I has no tile left of the diagonal: block I-1 is complete without it
+                if (kf > I - 1 && warp == 0) finish_block(I - 1);
+            }
+            __syncthreads();
+          }
+      }
+      for (int lc = lc0; lc < lc0 + NB && lc < n_lc; ++lc) {
         const size_t ol = (size_t)gs * n_lc + lc;
         double *Uo = out.U ? out.U + ol * 6 * nV : nullptr;
         double *Ro = out.Rf ? out.Rf + ol * 6 * nV : nullptr;
@@ -144,88 +241,9 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             }
             continue;
         }
-        double *Xg = X + (size_t)lc * L.n_pad;
-        double *Xl = XS ? s_x : Xg;
-        const double *dpl = XS ? s_x + L.n_pad : dpiv;       // pivots next to x (copied below)
-
-        if (zero_load) {
+        double *Xl = XS ? s_x + (lc - lc0) * n_pad : X + (size_t)lc * n_pad;
+        if (status != CM_ST_OK) {            // singular matrix, zero load: the solve is skipped, U = 0
             for (int r = t; r < NT * CM_TILE; r += K4_THREADS) Xl[r] = 0.0;
-            __syncthreads();
-        } else {
-            // ---- back substitution L^T x = D^-1 y, row-oriented: once x_I is known every tile
-            // (I,J) of block row I (contiguous in memory) subtracts L(I,J)^T x_I from the pending
-            // sum of block J; the warp that owns tile (I,I-1) then finishes x_{I-1} =
-            // M^T (d .* s) with M = D^-1 L_JJ^-1 left by the factorisation.  One barrier per row.
-            for (int r = t; r < NT * CM_TILE; r += K4_THREADS) {
-                const double d = dpiv[r];
-                if (XS) s_x[L.n_pad + r] = d;
-                Xl[r] = Xg[r] / d;
-            }
-            __syncthreads();
-            const int g = lane >> 2;
-            if (warp == 0) {
-                const int I = NT - 1;
-                double w4[4], cs[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) w4[i] = dpl[I * CM_TILE + i * 8 + g] * Xl[I * CM_TILE + i * 8 + g];
-                mtile_tmatvec(minv + (size_t)I * CM_TILE_ELEMS, w4, cs, lane);
-                __syncwarp();
-                if (lane < 4)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) Xl[I * CM_TILE + mcol(q, lane)] = cs[q];
-            }
-            for (int I = NT - 1; I > 0; --I) {
-                // M_{I-1} is needed at the end of this row's chain: start its DRAM read now
-                if (warp == 0) {
-                    const double *Mn = minv + (size_t)(I - 1) * CM_TILE_ELEMS;
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + lane * 16));
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + 512 + lane * 16));
-                }
-                // ... and so are the tiles of the next row: request this warp's share one row ahead
-                if (I >= 2) {
-                    const int kfn = kfirst[I - 1];
-                    for (int J = I - 2 - warp; J >= kfn; J -= K4_WARPS) {
-                        const double *Tn = cm_tile_ptr(tiles, bt, I - 1, J) + lane * 16;
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn));
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn + 512));
-                    }
-                }
-                __syncthreads();
-                const int kf = kfirst[I];
-                double x4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) x4[i] = Xl[I * CM_TILE + i * 8 + g];
-                for (int J = I - 1 - warp; J >= kf; J -= K4_WARPS) {
-                    double cs[8];
-                    tile_tmatvec(cm_tile_ptr(tiles, bt, I, J), x4, cs, lane);
-                    if (lane < 4)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + q * 4 + lane] -= cs[q];
-                    if (J == I - 1) {
-                        __syncwarp();
-                        double w4[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) w4[i] = dpl[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
-                        mtile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
-                        __syncwarp();
-                        if (lane < 4)
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + mcol(q, lane)] = cs[q];
-                    }
-                }
-                if (kf > I - 1 && warp == 0) {
-                    // row I has no tile left of the diagonal: block I-1 is complete without it
-                    const int J = I - 1;
-                    double w4[4], cs[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) w4[i] = dpl[J * CM_TILE + i * 8 + g] * Xl[J * CM_TILE + i * 8 + g];
-                    mtile_tmatvec(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
-                    __syncwarp();
-                    if (lane < 4)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) Xl[J * CM_TILE + mcol(q, lane)] = cs[q];
-                }
-            }
             __syncthreads();
         }
 
@@ -354,25 +372,43 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             if (out.max_abs_sigma) out.max_abs_sigma[ol] = smax < 0.0 ? 0.0 : smax;
         }
         __syncthreads();
+      }
     }
 }
 
 }  // namespace
 
+template <int NB>
+static cudaError_t launch_k4_xs(const cm_model_dev &m, const cm_ws_layout &L, char *ws, const uint32_t *masks,
+                                long long first, int count, const cm_out_dev &out, cudaStream_t st) {
+    const size_t xs_bytes = (size_t)(NB + 1) * L.n_pad * sizeof(double);      // NB solutions and the pivots
+    static size_t configured = 0;
+    if (xs_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k4_solve_recover<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes);
+        if (e != cudaSuccess) return e;
+        configured = xs_bytes;
+    }
+    k4_solve_recover<true, NB><<<count, K4_THREADS, xs_bytes, st>>>(m, L, ws, masks, first, out);
+    return cudaGetLastError();
+}
+
+// Load cases per pass over L: as many as keep the shared-memory vectors within 64 KB per CTA (the
+// kernel is HBM-bound through many resident CTAs), at most 4.  CM_K4_NB overrides (timing).
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st) {
-    const size_t xs_bytes = 2 * (size_t)L.n_pad * sizeof(double);      // x and the pivots
-    if (xs_bytes <= 64 * 1024) {
-        static size_t configured = 0;
-        if (xs_bytes > configured) {
-            cudaError_t e = cudaFuncSetAttribute(k4_solve_recover<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes);
-            if (e != cudaSuccess) return e;
-            configured = xs_bytes;
-        }
-        k4_solve_recover<true><<<count, K4_THREADS, xs_bytes, st>>>(m, L, ws, masks, first, out);
-    } else {
-        k4_solve_recover<false><<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, first, out);
+    const size_t vec = (size_t)L.n_pad * sizeof(double);
+    static const int nb_env = getenv("CM_K4_NB") ? atoi(getenv("CM_K4_NB")) : 0;
+    int nb = 0;
+    if (2 * vec <= 64 * 1024) {
+        nb = 1;
+        if (m.n_lc >= 2 && 3 * vec <= 64 * 1024) nb = 2;
+        if (m.n_lc >= 3 && 5 * vec <= 64 * 1024) nb = 4;
+        if (nb_env == 1 || (nb_env == 2 && 3 * vec <= 200 * 1024) || (nb_env == 4 && 5 * vec <= 200 * 1024)) nb = nb_env;
     }
+    if (nb == 4) return launch_k4_xs<4>(m, L, ws, masks, first, count, out, st);
+    if (nb == 2) return launch_k4_xs<2>(m, L, ws, masks, first, count, out, st);
+    if (nb == 1) return launch_k4_xs<1>(m, L, ws, masks, first, count, out, st);
+    k4_solve_recover<false, 1><<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, first, out);
     return cudaGetLastError();
 }
