@@ -12,18 +12,28 @@ def ids_to_mask(ids, nE):
 
 def pack_masks(list_of_ids, nE, out=None):
     """(B, ceil(nE/32)) uint32 masks for a list of id lists.  An empty list means the full
-    structure (reference ``numpy_stiffness.py:230-231``).  Ids out of range raise IndexError."""
+    structure (reference ``numpy_stiffness.py:230-231``).  Ids out of range raise IndexError.
+
+    Vectorised over the whole batch (one flat id array, one scatter, one packbits): the batched
+    solve consumes several hundred thousand subsets per second and GPU, a Python loop over the
+    subsets does not keep up."""
     B = len(list_of_ids)
     W = (nE + 31) // 32
+    if B == 0:
+        return np.zeros((0, W), dtype=np.uint32) if out is None else out
+    lens = np.fromiter((len(ids) for ids in list_of_ids), dtype=np.int64, count=B)
+    total = int(lens.sum())
+    if total:      # (np.asarray per list is ~3x faster than one np.fromiter over the chained lists)
+        flat = np.concatenate([np.asarray(ids, dtype=np.int64).ravel() for ids in list_of_ids if len(ids)])
+    else:
+        flat = np.zeros(0, dtype=np.int64)
+    if total and (flat.min() < 0 or flat.max() >= nE):
+        raise IndexError('element id not within range!')
     bits = np.zeros((B, W * 32), dtype=np.uint8)
-    for b, ids in enumerate(list_of_ids):
-        if len(ids) == 0:
-            bits[b, :nE] = 1
-        else:
-            idx = np.asarray(ids, dtype=np.int64)
-            if idx.min() < 0 or idx.max() >= nE:
-                raise IndexError('element id not within range!')
-            bits[b, idx] = 1
+    if total:
+        bits.reshape(-1)[np.repeat(np.arange(B, dtype=np.int64) * (W * 32), lens) + flat] = 1
+    if (lens == 0).any():
+        bits[lens == 0, :nE] = 1
     packed = np.packbits(bits.reshape(B, W, 32), axis=2, bitorder='little')      # (B, W, 4) bytes
     packed = np.ascontiguousarray(packed).view('<u4').reshape(B, W)
     if out is not None:

@@ -299,19 +299,22 @@ def test_config3_full_size_properties():
     assert_array_equal(rd['U'].cpu().numpy(), r['U'])
 
 
-def test_config4_multi_loadcase():
-    """BASELINE config 4: joints on horizontals, height-field subsets, four load cases solved
-    in ONE pass against the oracle solved once per (subset, load case)."""
+@pytest.mark.parametrize('n_lc', [4, 3, 2])
+def test_config4_multi_loadcase(n_lc):
+    """BASELINE config 4: joints on horizontals, height-field subsets, several load cases solved
+    in ONE pass against the oracle solved once per (subset, load case).  4 / 3 / 2 load cases
+    exercise the back substitution with four right-hand sides per pass over L, a partly filled
+    group of four, and two per pass."""
     from conmech_b200 import synthetic as syn, StiffnessChecker
     dims = (5, 5, 5)
     model = syn.grid_frame(*dims, joints=True)
-    lcs = syn.config4_loadcases(model)
+    lcs = syn.config4_loadcases(model)[:n_lc]
     sc = StiffnessChecker(model, checker_engine='cuda')
     sc.set_load_cases(lcs)
     eng = sc._sc_ins
     subsets = [[]] + [syn.heightfield_subset(model, *dims, seed=s) for s in range(100, 112)]
     r = eng.solve_many(subsets, want=ALL)
-    assert r['flag'].shape == (len(subsets), 4)
+    assert r['flag'].shape == (len(subsets), n_lc)
     for li, lc in enumerate(lcs):
         orc = FrameOracle(model)                    # fresh per load case (Q6)
         orc.set_loads(lc)
