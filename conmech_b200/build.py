@@ -32,6 +32,22 @@ def _newer(a, b):
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
+def build_host_packer(force=False, logs=None):
+    """_cmpack: CPython extension (plain C, gcc) that packs Python id lists into subset bit masks."""
+    import sysconfig
+    src = os.path.join(HERE, 'csrc_host', 'cmpack.c')
+    out = os.path.join(HERE, '_cmpack' + sysconfig.get_config_var('EXT_SUFFIX'))
+    if force or _newer(src, out):
+        cmd = [os.environ.get('CC', 'gcc'), '-O2', '-shared', '-fPIC', '-I' + sysconfig.get_paths()['include'], src, '-o', out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if logs is not None:
+            logs.append('$ ' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('gcc failed on cmpack.c')
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
@@ -58,6 +74,7 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(logs[-1])
             raise RuntimeError('link failed')
+    build_host_packer(force, logs)
     if logs:
         with open(os.path.join(LIBDIR, 'build.log'), 'w') as f:
             f.write('\n'.join(logs))

@@ -2,6 +2,11 @@
 word e//32 set = element e exists)."""
 import numpy as np
 
+try:                                   # host-side helper only; the numpy path is equivalent
+    from . import _cmpack
+except ImportError:                    # pragma: no cover
+    _cmpack = None
+
 
 def ids_to_mask(ids, nE):
     m = np.zeros((nE + 31) // 32, dtype=np.uint32)
@@ -21,6 +26,16 @@ def pack_masks(list_of_ids, nE, out=None):
     W = (nE + 31) // 32
     if B == 0:
         return np.zeros((0, W), dtype=np.uint32) if out is None else out
+    if _cmpack is not None and not isinstance(list_of_ids, np.ndarray):
+        # native packer (csrc_host/cmpack.c, built by conmech_b200.build): ~5 ns per id straight from
+        # the Python lists; the numpy path below (same result) costs ~70 ns per id on lists
+        dst = out if (out is not None and out.dtype == np.uint32 and out.flags.c_contiguous and out.shape == (B, W)) \
+            else np.empty((B, W), dtype=np.uint32)
+        _cmpack.pack(list_of_ids, int(nE), dst)
+        if out is not None and dst is not out:
+            out[...] = dst
+            return out
+        return dst
     lens = np.fromiter((len(ids) for ids in list_of_ids), dtype=np.int64, count=B)
     total = int(lens.sum())
     if total:      # (np.asarray per list is ~3x faster than one np.fromiter over the chained lists)

@@ -66,6 +66,39 @@ def test_masks_roundtrip():
         pack_masks([[40]], 40)
 
 
+def test_native_mask_packer_matches_numpy():
+    """The CPython packer (csrc_host/cmpack.c) and the numpy path produce the same masks for lists,
+    tuples, sets, ranges and integer arrays; empty = full structure; out-of-range ids raise."""
+    import random
+    import numpy as np
+    from conmech_b200 import masks
+    assert masks._cmpack is not None, 'run python -m conmech_b200.build'
+    nE = 931
+    rng = random.Random(1)
+    subs = [rng.sample(range(nE), rng.randint(1, 900)) for _ in range(200)]
+    subs[3] = []
+    subs[4] = tuple(subs[4])
+    subs[5] = set(subs[5])
+    subs[6] = range(10, 500, 3)
+    subs[7] = np.array(subs[7], dtype=np.int32)
+    subs[8] = np.array(subs[8], dtype=np.int64)
+    subs[9] = np.array(subs[9], dtype=np.uint16)
+    subs[10] = [nE - 1, 0, 0, 31, 32]
+    native = masks.pack_masks(subs, nE)
+    saved, masks._cmpack = masks._cmpack, None
+    try:
+        ref = masks.pack_masks([list(x) for x in subs], nE)
+    finally:
+        masks._cmpack = saved
+    assert native.dtype == np.uint32 and native.shape == (200, 30)
+    assert (native == ref).all()
+    assert set(masks.mask_to_ids(native[10], nE)) == {0, 31, 32, nE - 1}
+    assert len(masks.mask_to_ids(native[3], nE)) == nE
+    for bad in ([[0, nE]], [[-1]], [np.array([5, 5000])]):
+        with pytest.raises(IndexError):
+            masks.pack_masks(bad, nE)
+
+
 def test_model_io_roundtrip(models_dir):
     from conmech_b200 import Model, LoadCase
     for f in sorted(os.listdir(models_dir)):

@@ -26,3 +26,11 @@ for timing in (False, True):
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter(); od = eng.solve_many_device(dm, want=want, out=od); torch.cuda.synchronize(); t1 = time.perf_counter()
     print('device path timing={} wall {:.1f} ms stage {}'.format(timing, (t1 - t0) * 1e3, eng.last_stage_ms() if timing else ''))
+# the facade call a user makes: Python id lists in, flags out (packing by the native packer included)
+from conmech_b200 import masks as _m
+lists = [_m.mask_to_ids(masks[b], len(model.elements)).tolist() for b in range(B)]
+for rep in range(3):
+    t0 = time.perf_counter(); flags = sc.solve_many(lists); t1 = time.perf_counter()
+print('facade solve_many(list of id lists): wall {:.1f} ms -> {:.0f} solves/s ({} True)'.format((t1 - t0) * 1e3, B / (t1 - t0), int(np.sum(flags))))
+t0 = time.perf_counter(); _m.pack_masks(lists, len(model.elements)); t1 = time.perf_counter()
+print('  of which packing {:.1f} ms'.format((t1 - t0) * 1e3))
