@@ -262,21 +262,61 @@ class CudaStiffness(StiffnessBase):
         in include/conmech_b200.h for names and shapes.  ``out`` may hold preallocated
         (e.g. pinned) arrays to write into."""
         self._push_loads()
-        masks = self._as_masks(subsets)
-        B = masks.shape[0]
+        prepacked = isinstance(subsets, np.ndarray) and subsets.dtype == np.uint32 and subsets.ndim == 2
+        B = len(subsets)
         shapes = self._out_shapes(B)
         res = {}
-        oh = _capi.SolveOutHost()
         for name in OUT_FIELDS:
             if name in want:
                 a = out[name] if out is not None and name in out else np.empty(shapes[name], dtype=_OUT_DTYPE[name])
                 assert a.flags['C_CONTIGUOUS'] and a.dtype == _OUT_DTYPE[name] and a.size == int(np.prod(shapes[name]))
-                res[name] = a
-                setattr(oh, name, a.ctypes.data)
-            else:
-                setattr(oh, name, None)
-        _capi.check(self._lib.cm_solve_many_host(self._handle, _ptr(masks), B, C.byref(oh)))
+                res[name] = a.reshape(shapes[name])
+
+        def run(masks, b0, b1):
+            oh = _capi.SolveOutHost()
+            for name in OUT_FIELDS:
+                setattr(oh, name, res[name][b0:b1].ctypes.data if name in res else None)
+            _capi.check(self._lib.cm_solve_many_host(self._handle, _ptr(masks), b1 - b0, C.byref(oh)))
+
+        if not prepacked and not isinstance(subsets, (list, tuple)):
+            subsets = list(subsets)
+        if prepacked or B < 2 * self.PIPELINE_CHUNK:
+            run(self._as_masks(subsets), 0, B)
+            return res
+        # Python id lists, large batch: packing (GIL held, ~5 ns per id) and the GPU call (ctypes
+        # releases the GIL) are pipelined chunk by chunk - one worker thread makes every call into the
+        # handle, in order, while this thread packs the next chunk.
+        import queue
+        import threading
+        q, err = queue.Queue(maxsize=2), []
+
+        def worker():
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if not err:
+                    try:
+                        run(*item)
+                    except Exception as e:          # noqa: BLE001 - re-raised below on the caller's thread
+                        err.append(e)
+
+        th = threading.Thread(target=worker, name='conmech-b200-solve', daemon=True)
+        th.start()
+        try:
+            n_chunks = min(8, B // self.PIPELINE_CHUNK)
+            step = -(-B // n_chunks)
+            for b0 in range(0, B, step):
+                b1 = min(B, b0 + step)
+                q.put((pack_masks(subsets[b0:b1], self.nE), b0, b1))
+        finally:
+            q.put(None)
+            th.join()
+        if err:
+            raise err[0]
         return res
+
+    PIPELINE_CHUNK = 2048          # subsets per pipelined chunk of solve_many (id lists only)
 
     def solve_many_device(self, masks, want=('flag', 'status', 'max_trans', 'compliance'), out=None,
                           max_in_flight=None):

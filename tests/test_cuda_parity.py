@@ -299,6 +299,31 @@ def test_config3_full_size_properties():
     assert_array_equal(rd['U'].cpu().numpy(), r['U'])
 
 
+def test_solve_many_from_id_lists_pipelined():
+    """The facade call with Python id lists (packing pipelined with the GPU calls chunk by chunk,
+    one worker thread) returns exactly what the one-call path on pre-packed masks returns."""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad, StiffnessChecker
+    from conmech_b200.masks import pack_masks
+    model = syn.grid_frame(4, 4, 4)
+    sc = StiffnessChecker(model, checker_engine='cuda')
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    sc.set_nodal_displacement_tol(trans_tol=2e-5)
+    eng = sc._sc_ins
+    B = 2 * eng.PIPELINE_CHUNK + 777
+    lists = [syn.connected_subset(model, s) for s in range(B)]
+    lists[5] = []
+    want = ('flag', 'status', 'max_trans', 'compliance', 'n_free')
+    r_lists = eng.solve_many(lists, want=want)
+    r_masks = eng.solve_many(pack_masks(lists, len(model.elements)), want=want)
+    for k in want:
+        assert_array_equal(r_lists[k], r_masks[k])
+    flags = sc.solve_many(lists)
+    assert flags == [bool(f) for f in r_masks['flag'][:, 0]]
+    with pytest.raises(IndexError):
+        eng.solve_many(lists[:B - 1] + [[len(model.elements)]], want=('flag',))
+    assert eng.solve_many(lists[:3], want=('flag',))['flag'].shape == (3, 1)     # the handle is still usable
+
+
 @pytest.mark.parametrize('n_lc', [4, 3, 2])
 def test_config4_multi_loadcase(n_lc):
     """BASELINE config 4: joints on horizontals, height-field subsets, several load cases solved
