@@ -288,6 +288,32 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     UP(dev_upload(h, lp_eptr.data(), lp_eptr.size(), &d_lp_eptr));
     UP(dev_upload(h, lp_elem.data(), lp_elem.size(), &d_lp_elem));
     UP(dev_upload(h, lp_end.data(), lp_end.size(), &d_lp_end));
+    {   // K2's index tables as one blob (ints, then bytes, every table 16-byte aligned)
+        std::vector<char> blob;
+        auto put = [&](int which, const void *src, size_t bytes) {
+            blob.resize((blob.size() + 15) & ~(size_t)15);
+            m.k2_off[which] = (int)blob.size();
+            const char *c = static_cast<const char *>(src);
+            blob.insert(blob.end(), c, c + bytes);
+        };
+        put(CM_K2T_ORDER, h->order.data(), sizeof(int) * nV);
+        put(CM_K2T_NE_PTR, ne_ptr.data(), sizeof(int) * ne_ptr.size());
+        put(CM_K2T_NE_ELEM, ne_elem.data(), sizeof(int) * ne_elem.size());
+        put(CM_K2T_LP_PTR, lp_ptr.data(), sizeof(int) * lp_ptr.size());
+        put(CM_K2T_LP_NODE, lp_node.data(), sizeof(int) * lp_node.size());
+        put(CM_K2T_LP_EPTR, lp_eptr.data(), sizeof(int) * lp_eptr.size());
+        put(CM_K2T_LP_ELEM, lp_elem.data(), sizeof(int) * lp_elem.size());
+        put(CM_K2T_NODE_SUP, node_sup.data(), sizeof(int) * nV);
+        put(CM_K2T_CONN, d->conn, sizeof(int) * 2 * (size_t)nE);
+        put(CM_K2T_NE_END, ne_end.data(), ne_end.size());
+        put(CM_K2T_LP_END, lp_end.data(), lp_end.size());
+        put(CM_K2T_SUP_COND, d->sup_cond, (size_t)6 * nS);
+        blob.resize((blob.size() + 15) & ~(size_t)15);
+        char *d_blob;
+        UP(dev_upload(h, blob.data(), blob.size(), &d_blob));
+        m.k2_blob = d_blob;
+        m.k2_blob_bytes = (int)blob.size();
+    }
     UP(dev_upload<double>(h, nullptr, (size_t)144 * nE, &m.Kg));
     UP(dev_upload<double>(h, nullptr, (size_t)9 * nE, &m.R3));
     UP(dev_upload<double>(h, nullptr, (size_t)nE, &m.elen));

@@ -12,6 +12,8 @@
 #define CM_EPS 1e-14               // reference DOUBLE_EPS (numpy_stiffness_assembly.py:8)
 #define CM_BIG 1e14                // reference DOUBLE_INF (numpy_stiffness_assembly.py:9)
 #define CM_MAX_LC 8                // load cases solved together per subset
+enum { CM_K2T_ORDER = 0, CM_K2T_NE_PTR, CM_K2T_NE_ELEM, CM_K2T_LP_PTR, CM_K2T_LP_NODE, CM_K2T_LP_EPTR, CM_K2T_LP_ELEM,
+       CM_K2T_NODE_SUP, CM_K2T_CONN, CM_K2T_NE_END, CM_K2T_LP_END, CM_K2T_SUP_COND };
 #define CM_INFO_INTS 16            // per-subset info record (ints)
 
 // info record slots
@@ -73,6 +75,12 @@ struct cm_model_dev {
     const unsigned char *lp_end;   // [<= nE]
     const int *order;      // [nV] solver position -> node
     const int *pos;        // [nV] node -> solver position
+    // The index tables K2 walks (order, ne_*, lp_*, node_sup, conn, sup_cond), once more as ONE
+    // contiguous blob: K2 copies it to shared memory when it fits, so that the dependent address
+    // chains of its gather run at shared-memory latency.  Offsets in bytes (CM_K2T_* below).
+    const char *k2_blob;
+    int k2_blob_bytes;
+    int k2_off[12];
     const double *q;       // [n_lc*nE*12] lumped element loads
     const double *pnodal;  // [n_lc*6nV]
     double trans_tol;

@@ -43,17 +43,21 @@ __device__ int block_excl_scan(int *data, int n, int *scratch) {
 __device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (mask[e >> 5] >> (e & 31)) & 1u; }
 
 // solver row of local DOF i of node v (-1 if fixed); base = first solver row of the node
-__device__ __forceinline__ int node_row(const cm_model_dev &m, int v, int i, int base) {
-    int s = m.node_sup[v];
+__device__ __forceinline__ int node_row(const int *node_sup, const unsigned char *sup_cond, int v, int i, int base) {
+    int s = node_sup[v];
     if (s < 0) return base + i;
-    const unsigned char *c = m.sup_cond + 6 * s;
+    const unsigned char *c = sup_cond + 6 * s;
     if (c[i]) return -1;
     int r = base;
     for (int j = 0; j < i; ++j) r += c[j] ? 0 : 1;
     return r;
 }
 
-__global__ void __launch_bounds__(K2_THREADS)
+#ifndef K2_MIN_CTAS
+#define K2_MIN_CTAS 5          // 48 registers: five CTAs per SM (measured best: 4 CTAs at 60 registers 3.35 ms, 5 at 48 3.0 ms, 6 at 40 with spills 3.36 ms)
+#endif
+template <bool TS>      // TS: the index tables are staged in shared memory
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
                    cm_out_dev out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -67,6 +71,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     unsigned char *s_free = reinterpret_cast<unsigned char *>(s_mask + m.mask_words);   // [nV] free DOFs (0 if absent)
     unsigned char *s_exist = s_free + m.nV;                        // [nV]
     unsigned char *s_aflag = s_exist + m.nV;                       // [n_tile_rows_max*band_tiles] tile holds K_mm entries
+    char *s_blob = reinterpret_cast<char *>((reinterpret_cast<size_t>(s_aflag + m.n_tile_rows_max * m.band_tiles) + 15) & ~(size_t)15);   // [k2_blob_bytes] if TS
     __shared__ int s_red[8];
     __shared__ unsigned long long s_work;
     __shared__ double s_dred[K2_THREADS / 32];
@@ -87,6 +92,26 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     const uint32_t *gmask = masks + (size_t)gs * m.mask_words;
     const int nV = m.nV;
 
+    // index tables: shared-memory copies when they fit (one coalesced pass), the global blob otherwise
+    const char *blob = TS ? s_blob : m.k2_blob;
+    if (TS) {
+        const int4 *src = reinterpret_cast<const int4 *>(m.k2_blob);
+        int4 *dst = reinterpret_cast<int4 *>(s_blob);
+        for (int i = t; i < (m.k2_blob_bytes >> 4); i += T) dst[i] = src[i];
+    }
+    const int *order = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_ORDER]);
+    const int *ne_ptr = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_NE_PTR]);
+    const int *ne_elem = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_NE_ELEM]);
+    const int *lp_ptr = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_LP_PTR]);
+    const int *lp_node = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_LP_NODE]);
+    const int *lp_eptr = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_LP_EPTR]);
+    const int *lp_elem = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_LP_ELEM]);
+    const int *node_sup = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_NODE_SUP]);
+    const int *conn = reinterpret_cast<const int *>(blob + m.k2_off[CM_K2T_CONN]);
+    const unsigned char *ne_end = reinterpret_cast<const unsigned char *>(blob + m.k2_off[CM_K2T_NE_END]);
+    const unsigned char *lp_end = reinterpret_cast<const unsigned char *>(blob + m.k2_off[CM_K2T_LP_END]);
+    const unsigned char *sup_cond = reinterpret_cast<const unsigned char *>(blob + m.k2_off[CM_K2T_SUP_COND]);
+
     for (int w = t; w < m.mask_words; w += T) s_mask[w] = gmask[w];
     if (t < 8) s_red[t] = 0;
     if (t == 0) s_work = 0ull;
@@ -96,11 +121,11 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     int my_fixed = 0, my_exist = 0, my_sup = 0;
     for (int v = t; v < nV; v += T) {
         bool ex = false;
-        for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) ex |= elem_on(s_mask, m.ne_elem[p]);
+        for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) ex |= elem_on(s_mask, ne_elem[p]);
         int nfix = 0;
-        int s = m.node_sup[v];
+        int s = node_sup[v];
         if (ex && s >= 0) {
-            for (int i = 0; i < 6; ++i) nfix += m.sup_cond[6 * s + i] ? 1 : 0;
+            for (int i = 0; i < 6; ++i) nfix += sup_cond[6 * s + i] ? 1 : 0;
             my_sup = 1;
         }
         s_exist[v] = ex ? 1 : 0;
@@ -143,9 +168,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         for (int v = t; v < nV; v += T) {
             if (!s_exist[v]) continue;
             int r = s_tmp[v];
-            int s = m.node_sup[v];
+            int s = node_sup[v];
             for (int i = 0; i < 6; ++i)
-                if (s < 0 || !m.sup_cond[6 * s + i]) dm[r++] = 6 * v + i;
+                if (s < 0 || !sup_cond[6 * s + i]) dm[r++] = 6 * v + i;
         }
         __syncthreads();
         // fixed
@@ -154,11 +179,11 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         block_excl_scan(s_tmp, nV, s_scan);
         for (int v = t; v < nV; v += T) {
             if (!s_exist[v]) continue;
-            int s = m.node_sup[v];
+            int s = node_sup[v];
             if (s < 0) continue;
             int r = n_free + s_tmp[v];
             for (int i = 0; i < 6; ++i)
-                if (m.sup_cond[6 * s + i]) dm[r++] = 6 * v + i;
+                if (sup_cond[6 * s + i]) dm[r++] = 6 * v + i;
         }
         __syncthreads();
         // absent
@@ -174,10 +199,10 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     }
 
     // ---- compacted solver numbering: free DOFs of existing nodes in the static node ordering
-    for (int p = t; p < nV; p += T) s_tmp[p] = s_free[m.order[p]];
+    for (int p = t; p < nV; p += T) s_tmp[p] = s_free[order[p]];
     __syncthreads();
     block_excl_scan(s_tmp, nV, s_scan);
-    for (int p = t; p < nV; p += T) s_base[m.order[p]] = s_tmp[p];
+    for (int p = t; p < nV; p += T) s_base[order[p]] = s_tmp[p];
     const int ns = n_free;
     const int NT = (ns + CM_TILE - 1) / CM_TILE;
     for (int I = t; I < NT; I += T) { s_kfirst[I] = I; s_kcol[I] = 8 * I; }
@@ -186,7 +211,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     for (int v = t; v < nV; v += T) {
         int base = s_base[v];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) sidx[6 * v + i] = s_exist[v] ? node_row(m, v, i, base) : -1;
+        for (int i = 0; i < 6; ++i) sidx[6 * v + i] = s_exist[v] ? node_row(node_sup, sup_cond, v, i, base) : -1;
         // envelope: first column touched by the rows of this node
         int nf = s_free[v];
         if (nf == 0) continue;
@@ -197,10 +222,10 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         // neighbours that come earlier in the solver order
         s_aflag[I0 * btf + btf - 1] = 1;
         if (I1 != I0) { s_aflag[I1 * btf + btf - 1] = 1; s_aflag[I1 * btf + btf - 2] = 1; }
-        for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
-            int e = m.ne_elem[p];
+        for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) {
+            int e = ne_elem[p];
             if (!elem_on(s_mask, e)) continue;
-            int c = m.conn[2 * e + (m.ne_end[p] ? 0 : 1)];
+            int c = conn[2 * e + (ne_end[p] ? 0 : 1)];
             if (!s_free[c]) continue;
             const int bc = s_base[c];
             cmin = min(cmin, bc);
@@ -232,15 +257,15 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     for (int idx = t; idx < 6 * nV; idx += T) {
         int v = idx / 6, i = idx - 6 * v;
         if (!s_exist[v]) continue;
-        int r = node_row(m, v, i, s_base[v]);
+        int r = node_row(node_sup, sup_cond, v, i, s_base[v]);
         if (r < 0) continue;
         double kii = 0.0;
         // (table reads are unconditional and the mask only selects: the loads of consecutive elements
         // are then independent of the branch and overlap; adding 0.0 for an absent element is exact)
 #pragma unroll 4
-        for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
-            const int e = m.ne_elem[p];
-            const int l = 6 * m.ne_end[p] + i;
+        for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) {
+            const int e = ne_elem[p];
+            const int l = 6 * ne_end[p] + i;
             const double kv = thr(m.Kg[(size_t)e * 144 + l * 12 + l]);
             kii += elem_on(s_mask, e) ? kv : 0.0;
         }
@@ -277,6 +302,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             {
                 const double2 z2 = make_double2(0.0, 0.0);
                 for (int K = s_kfirst[IR]; K <= IR; ++K) {
+#if defined(K2_EXP) && K2_EXP == 1          // timing experiment (wrong results): no zero fill
+                    continue;
+#endif
                     if (!s_aflag[IR * bt + (K - IR + bt - 1)]) continue;
                     double2 *dst = reinterpret_cast<double2 *>(tiles + ((size_t)IR * bt + (K - IR + bt - 1)) * CM_TILE_ELEMS);
 #pragma unroll 4
@@ -289,53 +317,86 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             int lo = 0, hi = nV;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (s_tmp[mid] + s_free[m.order[mid]] > row0) hi = mid; else lo = mid + 1;
+                if (s_tmp[mid] + s_free[order[mid]] > row0) hi = mid; else lo = mid + 1;
             }
+#if defined(K2_EXP) && K2_EXP == 2          // timing experiment (wrong results): no gather/scatter
+            lo = nV;
+#endif
             for (int pa = lo; pa < nV && s_tmp[pa] < row1; ++pa) {
-            const int a = m.order[pa];
+            const int a = order[pa];
             if (s_free[a] == 0) continue;
             const int base_a = s_base[a];
-            const int p0 = m.ne_ptr[a], p1 = m.ne_ptr[a + 1];
-            const int q0 = m.lp_ptr[a];
-            const int total = 36 * (1 + m.lp_ptr[a + 1] - q0);
-            for (int idx = lane; idx < total; idx += 32) {
-                const int blk = idx / 36, ij = idx - 36 * blk;
-                const int i = ij / 6, j = ij - 6 * i;
-                const int r = node_row(m, a, i, base_a);
+            const int p0 = ne_ptr[a], p1 = ne_ptr[a + 1];
+            const int q0 = lp_ptr[a];
+            // One lane per (block, row): the 6 entries of row i of a 6x6 block are 48 contiguous bytes of the
+            // element's K_G - three 16-byte loads in flight per lane and element instead of one 8-byte
+            // load, and the index arithmetic is paid once per six entries.
+            const int n_items = 6 * (1 + lp_ptr[a + 1] - q0);
+            for (int it = lane; it < n_items; it += 32) {
+                const int blk = it / 6, i = it - 6 * blk;
+                const int r = node_row(node_sup, sup_cond, a, i, base_a);
                 if (r < 0 || (r >> 5) != IR) continue;
-                int cc;
-                double s = 0.0;
+                double s6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                int c = a, base_c = base_a;
                 if (blk == 0) {
-                    if (j > i) continue;
-                    cc = node_row(m, a, j, base_a);
-                    if (cc < 0) continue;
-#pragma unroll 4
+#pragma unroll 2
                     for (int p = p0; p < p1; ++p) {
-                        const int e = m.ne_elem[p];
-                        const int o = 6 * m.ne_end[p];
-                        const double kv = thr(m.Kg[(size_t)e * 144 + (o + i) * 12 + o + j]);
-                        s += elem_on(s_mask, e) ? kv : 0.0;
+                        const int e = ne_elem[p];
+                        const int o = 6 * ne_end[p];
+                        const double2 *kp = reinterpret_cast<const double2 *>(m.Kg + (size_t)e * 144 + (o + i) * 12 + o);
+#if defined(K2_EXP) && K2_EXP == 4          // timing experiment (wrong results): no stiffness-table reads
+                        const double2 v0 = make_double2(1.0 + e, 2.0), v1 = v0, v2 = v0; (void)kp;
+#else
+                        const double2 v0 = kp[0], v1 = kp[1], v2 = kp[2];
+#endif
+                        if (elem_on(s_mask, e)) {
+                            s6[0] += thr(v0.x); s6[1] += thr(v0.y); s6[2] += thr(v1.x);
+                            s6[3] += thr(v1.y); s6[4] += thr(v2.x); s6[5] += thr(v2.y);
+                        }
                     }
                 } else {
                     const int q = q0 + blk - 1;
-                    const int c = m.lp_node[q];
+                    c = lp_node[q];
                     if (s_free[c] == 0) continue;
-                    cc = node_row(m, c, j, s_base[c]);
-                    if (cc < 0) continue;
+                    base_c = s_base[c];
                     bool any = false;
-                    for (int pe = m.lp_eptr[q]; pe < m.lp_eptr[q + 1]; ++pe) {
-                        const int e = m.lp_elem[pe];
-                        const int ea = m.lp_end[pe];
-                        const double kv = thr(m.Kg[(size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea) + j]);
-                        const bool on = elem_on(s_mask, e);
-                        s += on ? kv : 0.0;
-                        any |= on;
+                    const int pe1 = lp_eptr[q + 1];
+                    for (int pe = lp_eptr[q]; pe < pe1; ++pe) {
+                        const int e = lp_elem[pe];
+                        const int ea = lp_end[pe];
+                        const double2 *kp = reinterpret_cast<const double2 *>(m.Kg + (size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea));
+#if defined(K2_EXP) && K2_EXP == 4
+                        const double2 v0 = make_double2(1.0 + e, 2.0), v1 = v0, v2 = v0; (void)kp;
+#else
+                        const double2 v0 = kp[0], v1 = kp[1], v2 = kp[2];
+#endif
+                        if (elem_on(s_mask, e)) {
+                            s6[0] += thr(v0.x); s6[1] += thr(v0.y); s6[2] += thr(v1.x);
+                            s6[3] += thr(v1.y); s6[4] += thr(v2.x); s6[5] += thr(v2.y);
+                            any = true;
+                        }
                     }
                     if (!any) continue;          // no existing element joins the pair: the tile may be unassembled
                 }
-                s = (dinv[r] * s) * dinv[cc];
-                const int I = r >> 5, K = cc >> 5;
-                tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = s;
+                // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only)
+                const double dr = dinv[r];
+                const int sc = node_sup[c];
+                const int jmax = blk == 0 ? i : 5;
+                const int I = r >> 5;
+                int cc = base_c;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    if (sc >= 0 && sup_cond[6 * sc + j]) continue;      // fixed DOF: no solver column
+                    if (j <= jmax) {
+                        const int K = cc >> 5;
+                        const double val = (dr * s6[j]) * dinv[cc];
+#if defined(K2_EXP) && K2_EXP == 3          // timing experiment (wrong results): entries computed but not stored
+                        if (val != val)
+#endif
+                        tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = val;
+                    }
+                    ++cc;
+                }
             }
             }
         }
@@ -359,16 +420,16 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             double pv = m.pnodal[(size_t)lc * 6 * nV + idx];
             double qs = 0.0;
 #pragma unroll 4
-            for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
-                const int e = m.ne_elem[p];
-                const double qv = m.q[((size_t)lc * m.nE + e) * 12 + 6 * m.ne_end[p] + i];
+            for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) {
+                const int e = ne_elem[p];
+                const double qv = m.q[((size_t)lc * m.nE + e) * 12 + 6 * ne_end[p] + i];
                 qs += elem_on(s_mask, e) ? qv : 0.0;
             }
             pv += qs;
             Pl[idx] = pv;
             sq += pv * pv;
             if (s_exist[v]) {
-                int r = node_row(m, v, i, s_base[v]);
+                int r = node_row(node_sup, sup_cond, v, i, s_base[v]);
                 if (r >= 0) Xl[r] = dinv[r] * pv;
             }
         }
@@ -426,14 +487,19 @@ cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaS
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,
                                       const cm_out_dev &out, cudaStream_t st) {
-    size_t smem = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
-                  (size_t)m.n_tile_rows_max * m.band_tiles + 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k2_dofmap_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t base = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
+                        (size_t)m.n_tile_rows_max * m.band_tiles + 16;
+    // tables in shared memory while five CTAs still fit an SM (the 1k-element frame needs 35 KB per CTA)
+    const bool ts = base + 16 + (size_t)m.k2_blob_bytes <= 44 * 1024;
+    const size_t smem = ts ? base + 16 + (size_t)m.k2_blob_bytes : base;
+    static size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[ts]) {
+        cudaError_t e = ts ? cudaFuncSetAttribute(k2_dofmap_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k2_dofmap_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[ts] = smem;
     }
-    k2_dofmap_assemble<<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out);
+    if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out);
+    else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out);
     return cudaGetLastError();
 }
