@@ -2,6 +2,8 @@
 // once-per-model precomputation: node->element incidence, the static solver ordering
 // (reverse Cuthill-McKee on the node graph), envelope statistics and the workspace layout.
 #include "cm_common.cuh"
+#include <chrono>
+#include <thread>
 #include <cstdlib>
 
 #include <algorithm>
@@ -633,6 +635,33 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
     for (const Item *it : outs)
         if (it->host) CU(cudaMemcpyAsync(it->host, h->stage + it->off, it->bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return CM_OK;
+}
+
+int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t B, const cm_solve_out_host *o,
+                              int64_t chunk, const volatile int32_t *ready) {
+    if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: null argument");
+    if (chunk <= 0) return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: chunk must be positive");
+    const cm_model_dev &m = h->m;
+    const size_t nV = m.nV, nE = m.nE, Lc = m.n_lc;
+    int64_t k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
+        if (ready) {
+            int32_t r;
+            while ((r = __atomic_load_n(const_cast<const int32_t *>(ready) + k, __ATOMIC_ACQUIRE)) == 0)
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+            if (r < 0) return fail(CM_ERR_STATE, "cm_solve_many_host_chunks: cancelled by the producer");
+        }
+        const int64_t n = std::min<int64_t>(chunk, B - b0);
+        cm_solve_out_host c = *o;
+        auto adv = [&](auto *&p, size_t per_subset) { if (p) p += (size_t)b0 * per_subset; };
+        adv(c.flag, Lc); adv(c.status, Lc); adv(c.n_free, 1); adv(c.n_fixed, 1); adv(c.dof_map, 6 * nV);
+        adv(c.node_exists, nV); adv(c.U, Lc * 6 * nV); adv(c.Rf, Lc * 6 * nV); adv(c.eR, Lc * nE * 12);
+        adv(c.compliance, Lc); adv(c.max_trans, Lc); adv(c.max_rot, Lc); adv(c.min_pivot, 1);
+        adv(c.profile_flops, 1); adv(c.sigma_max, Lc * nE); adv(c.max_abs_sigma, Lc);
+        int rc = cm_solve_many_host(h, masks_host + (size_t)b0 * m.mask_words, n, &c);
+        if (rc != CM_OK) return rc;
+    }
     return CM_OK;
 }
 

@@ -283,37 +283,38 @@ class CudaStiffness(StiffnessBase):
         if prepacked or B < 2 * self.PIPELINE_CHUNK:
             run(self._as_masks(subsets), 0, B)
             return res
-        # Python id lists, large batch: packing (GIL held, ~5 ns per id) and the GPU call (ctypes
-        # releases the GIL) are pipelined chunk by chunk - one worker thread makes every call into the
-        # handle, in order, while this thread packs the next chunk.
-        import queue
+        # Python id lists, large batch: packing (this thread, GIL held, ~5 ns per id) is pipelined with
+        # the GPU work chunk by chunk.  ONE worker thread makes ONE call into the library for the whole
+        # batch (cm_solve_many_host_chunks); inside it waits per chunk - without the GIL - for the
+        # 'ready' flag this thread sets after writing the chunk's masks.
         import threading
-        q, err = queue.Queue(maxsize=2), []
+        n_chunks = min(8, B // self.PIPELINE_CHUNK)
+        step = -(-B // n_chunks)
+        n_chunks = -(-B // step)
+        masks = np.empty((B, self._info.mask_words), dtype=np.uint32)
+        ready = np.zeros(n_chunks, dtype=np.int32)
+        oh = _capi.SolveOutHost()
+        for name in OUT_FIELDS:
+            setattr(oh, name, res[name].ctypes.data if name in res else None)
+        rc = []
 
         def worker():
-            while True:
-                item = q.get()
-                if item is None:
-                    return
-                if not err:
-                    try:
-                        run(*item)
-                    except Exception as e:          # noqa: BLE001 - re-raised below on the caller's thread
-                        err.append(e)
+            rc.append(self._lib.cm_solve_many_host_chunks(self._handle, _ptr(masks), B, C.byref(oh), step,
+                                                          ready.ctypes.data))
 
         th = threading.Thread(target=worker, name='conmech-b200-solve', daemon=True)
         th.start()
         try:
-            n_chunks = min(8, B // self.PIPELINE_CHUNK)
-            step = -(-B // n_chunks)
-            for b0 in range(0, B, step):
-                b1 = min(B, b0 + step)
-                q.put((pack_masks(subsets[b0:b1], self.nE), b0, b1))
-        finally:
-            q.put(None)
+            for k in range(n_chunks):
+                b0, b1 = k * step, min(B, (k + 1) * step)
+                pack_masks(subsets[b0:b1], self.nE, out=masks[b0:b1])
+                ready[k] = 1
+        except BaseException:
+            ready[ready == 0] = -1          # cancel the chunks that were not handed over
             th.join()
-        if err:
-            raise err[0]
+            raise
+        th.join()
+        _capi.check(rc[0])
         return res
 
     PIPELINE_CHUNK = 2048          # subsets per pipelined chunk of solve_many (id lists only)

@@ -182,6 +182,16 @@ typedef struct cm_solve_out_host {
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,
                        const cm_solve_out_host *out);
 
+/* The same batch in consecutive chunks of `chunk` subsets, for a caller that is still PRODUCING the
+ * masks while the first chunks are solved (the Python facade packs id lists - the reference's
+ * calling convention, StiffnessChecker.solve(exist_element_ids) stiffness_checker.py:153-182 - into
+ * masks chunk by chunk on another thread).  Before chunk k the call waits, without any interpreter
+ * lock, until ready[k] != 0 (producer: write the chunk's masks, then set ready[k] = 1; a negative
+ * value cancels the call, which then returns CM_ERR_STATE).  ready == NULL: no waiting.  Outputs
+ * are written at the subset's position in the full arrays, exactly as cm_solve_many_host does. */
+int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t B,
+                              const cm_solve_out_host *out, int64_t chunk, const volatile int32_t *ready);
+
 /* Counters since the last cm_reset_counters: kernels launched by this library, and device
  * milliseconds (CUDA events on the launching stream) per stage of the last cm_solve_many*
  * call when timing was enabled with cm_enable_timing(h, 1). stage: 0 dofmap+assembly,
