@@ -541,7 +541,7 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
         cudaStream_t ls = two_lanes ? h->lane_stream[w % NL] : st;
         char *lws = two_lanes ? ws + (size_t)(w % NL) * (size_t)cap * per : ws;
         if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
-        CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, ls));
+        CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, h->variant != 0 ? 1 : 0, ls));
         if (h->variant != 0) { CU(cm_launch_schedule(h->L, lws, count, ls)); h->launches += 1; }
         if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
         if (h->variant == 0)

@@ -121,9 +121,15 @@ cudaError_t cm_launch_element_loads(const cm_model_dev &m, int n_lc, const doubl
 cudaError_t cm_launch_element_generic(const double *xyz_u, const double *xyz_v, const double *props,
                                       const double *cr, long long n, double *Kg, double *R3,
                                       cudaStream_t st);
+// ktilde_rowmajor: K2 writes the assembled K~ tiles row-major (r*32 + k) instead of fragment-major.
+// K~ is only ever read as the INITIAL ACCUMULATOR of its tile (never as an MMA operand), the warp
+// that reads it owns the tile at that moment and overwrites it with L in the fragment-major layout -
+// so the layout K2 writes is free, and row-major makes the six entries of a block row contiguous
+// (2 sectors instead of 6 partial-sector writes).  The tensor-core factorisation reads it that way
+// (acc_load_rm); the scalar validation kernel wants fragment-major.
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,
-                                      const cm_out_dev &out, cudaStream_t st);
+                                      const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st);
 cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);

@@ -63,14 +63,14 @@ __device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
     double *sA = scr, *sB = scr + 32 * DS, *s_col = sB + 32 * DS, *s_rinv = s_col + 32;
     double *s_minpiv_w = CTX(s_minpiv) + (threadIdx.x >> 5);
     const int g = lane >> 2, t = lane & 3;
-    if (!in_smem) {
+    if (!in_smem) {                      // a row with nothing left of the diagonal: the assembled K~ tile, ROW-MAJOR (K2)
         const double *T = cm_tile_ptr(CTX(tiles), CTX(bt), I, I);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             double v[4];
-            ldg4(v, T + q * 128 + lane * 4);
+            ldg4(v, T + q * 128 + lane * 4);                 // elements 128q + 4*lane .. +3 = row 4q + lane/8, columns 4*(lane%8) ..
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sA[(8 * i + g) * DS + 4 * q + t] = v[i];
+            for (int i = 0; i < 4; ++i) sA[(4 * q + (lane >> 3)) * DS + 4 * (lane & 7) + i] = v[i];
         }
     }
     __syncwarp();

@@ -77,6 +77,20 @@ __device__ __forceinline__ void acc_load(TileAcc &a, const double *T, int lane) 
     }
 }
 
+// the same from an assembled K~ tile, which K2 leaves ROW-MAJOR (r*32 + k): the two values of one
+// (cj, ri) are 16 contiguous bytes, a warp load covers eight 64-byte row segments
+__device__ __forceinline__ void acc_load_rm(TileAcc &a, const double *T, int lane) {
+    const double *p = T + (lane >> 2) * 32 + 2 * (lane & 3);
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj)
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+            double2 v;
+            asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + ri * 256 + cj * 8) : "memory");
+            a.c[cj][0][ri] = v.x; a.c[cj][1][ri] = v.y;
+        }
+}
+
 __device__ __forceinline__ void acc_store(const TileAcc &a, double *T, int lane) {
     double *p = T + acc_cbase(lane);
 #pragma unroll

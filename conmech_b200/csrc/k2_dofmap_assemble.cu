@@ -62,7 +62,7 @@ __device__ __forceinline__ int node_row(const int *node_sup, const unsigned char
 template <bool TS>      // TS: the index tables are staged in shared memory
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
-                   cm_out_dev out) {
+                   cm_out_dev out, int ktilde_rm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout
     int *s_base = reinterpret_cast<int *>(smem_raw);             // [nV] first solver row of node
@@ -402,24 +402,36 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     }
                     if (!any) continue;          // no existing element joins the pair: the tile may be unassembled
                 }
-                // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only)
+                // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only):
+                // `cnt` consecutive columns from base_c on
                 const double dr = dinv[r];
                 const int sc = node_sup[c];
                 const int jmax = blk == 0 ? i : 5;
                 const int I = r >> 5;
-                int cc = base_c;
+                double vals[6];
+                int cnt = 0;
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    if (sc >= 0 && sup_cond[6 * sc + j]) continue;      // fixed DOF: no solver column
-                    if (j <= jmax) {
-                        const int K = cc >> 5;
-                        const double val = (dr * s6[j]) * dinv[cc];
-#if defined(K2_EXP) && K2_EXP == 3          // timing experiment (wrong results): entries computed but not stored
-                        if (val != val)
-#endif
-                        tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, cc & 31)] = val;
+                    if (sc >= 0 && sup_cond[6 * sc + j]) continue;        // fixed DOF: no solver column
+                    if (j <= jmax) { vals[cnt] = (dr * s6[j]) * dinv[base_c + cnt]; ++cnt; }
+                }
+                if (cnt == 0) continue;
+                const int K0 = base_c >> 5, K1 = (base_c + cnt - 1) >> 5;
+                if (ktilde_rm && K0 == K1) {
+                    // row-major K~ tile: the row's entries are contiguous - 16-byte stores where aligned
+                    double *dst = tiles + ((size_t)I * bt + (K0 - I + bt - 1)) * CM_TILE_ELEMS + (r & 31) * 32 + (base_c & 31);
+                    int x = 0;
+                    if ((base_c & 1) && x < cnt) { dst[0] = vals[0]; x = 1; }
+#pragma unroll
+                    for (int y = 0; y < 3; ++y)
+                        if (x + 1 < cnt) { *reinterpret_cast<double2 *>(dst + x) = make_double2(vals[x], vals[x + 1]); x += 2; }
+                    if (x < cnt) dst[x] = vals[x];
+                } else {
+                    for (int x = 0; x < cnt; ++x) {
+                        const int cc = base_c + x, K = cc >> 5;
+                        tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS +
+                              (ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31))] = vals[x];
                     }
-                    ++cc;
                 }
             }
             }
@@ -428,7 +440,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         // unit diagonal on the padding rows of the last tile
         for (int r = ns + t; r < NT * CM_TILE; r += T) {
             int I = r >> 5;
-            tiles[((size_t)I * bt + (bt - 1)) * CM_TILE_ELEMS + cm_tile_off(r & 31, r & 31)] = 1.0;
+            tiles[((size_t)I * bt + (bt - 1)) * CM_TILE_ELEMS + (ktilde_rm ? (r & 31) * 33 : cm_tile_off(r & 31, r & 31))] = 1.0;
         }
     }
 
@@ -510,7 +522,7 @@ cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaS
 
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                       const uint32_t *masks, long long first, int count,
-                                      const cm_out_dev &out, cudaStream_t st) {
+                                      const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st) {
     const size_t base = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
                         (size_t)m.n_tile_rows_max * m.band_tiles + 16;
     // tables in shared memory while five CTAs still fit an SM (the 1k-element frame needs 35 KB per CTA)
@@ -523,7 +535,7 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
         if (e != cudaSuccess) return e;
         configured[ts] = smem;
     }
-    if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out);
-    else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out);
+    if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out, ktilde_rowmajor);
+    else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out, ktilde_rowmajor);
     return cudaGetLastError();
 }

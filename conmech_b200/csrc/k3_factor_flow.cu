@@ -64,7 +64,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
         for (int i = 0; i < 8; ++i) stg4(T + i * 128 + lane * 4, 0.0, 0.0, 0.0, 0.0);
         return false;
     }
-    if (has_a) acc_load(acc, T, lane); else acc_zero(acc);
+    if (has_a) acc_load_rm(acc, T, lane); else acc_zero(acc);      // assembled K~ tiles are row-major (K2)
     while (K < J) {
         const int Kend = min(wait_prog_gt(CTX(prog), J, K), J);
         FP_ADD(pc, 0);
@@ -197,15 +197,15 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
             asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 512));
         }
         if (kfI < I) {                           // pending sum of the diagonal tile (diag_term) starts from the assembled tile
-            const double *pd = cm_tile_ptr(tiles, bt, I, I) + acc_cbase(lane);
+            const double *pd = cm_tile_ptr(tiles, bt, I, I) + (lane >> 2) * 32 + 2 * (lane & 3);      // row-major K~ (K2)
 #pragma unroll
-            for (int cj = 0; cj < 4; ++cj) {
-                double g0[4], g1[4];
-                ldg4s(g0, pd + cj * 256);
-                ldg4s(g1, pd + cj * 256 + 4);
+            for (int cj = 0; cj < 4; ++cj)
 #pragma unroll
-                for (int ri = cj; ri < 4; ++ri) s_dacc_w[(ri * (ri + 1) / 2 + cj) * 32 + lane] = make_double2(g0[ri], g1[ri]);
-            }
+                for (int ri = cj; ri < 4; ++ri) {
+                    double2 v;
+                    asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(pd + ri * 256 + cj * 8) : "memory");
+                    s_dacc_w[(ri * (ri + 1) / 2 + cj) * 32 + lane] = v;
+                }
         }
         __syncwarp();
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
