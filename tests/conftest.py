@@ -10,6 +10,10 @@ if REPO not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    # build the C-ABI library and the host packer before any test module imports the package
+    # (a fresh clone has no binaries; with everything up to date this is a few file-time checks)
+    import __graft_entry__ as ge
+    ge.build()
 
 
 @pytest.fixture(scope='session')
