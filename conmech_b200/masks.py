@@ -2,10 +2,22 @@
 word e//32 set = element e exists)."""
 import numpy as np
 
-try:                                   # host-side helper only; the numpy path is equivalent
-    from . import _cmpack
-except ImportError:                    # pragma: no cover
-    _cmpack = None
+USE_NATIVE = True                      # tests switch this off to compare with the numpy path
+_cmpack = None
+
+
+def _native_packer():
+    """The CPython packer (csrc_host/cmpack.c), imported on first use: a fresh clone builds it
+    (conmech_b200.build) after this module may already have been imported.  Host-side helper only;
+    the numpy path below is equivalent."""
+    global _cmpack
+    if _cmpack is None and USE_NATIVE:
+        try:
+            from . import _cmpack as mod
+            _cmpack = mod
+        except ImportError:
+            return None
+    return _cmpack if USE_NATIVE else None
 
 
 def ids_to_mask(ids, nE):
@@ -26,12 +38,13 @@ def pack_masks(list_of_ids, nE, out=None):
     W = (nE + 31) // 32
     if B == 0:
         return np.zeros((0, W), dtype=np.uint32) if out is None else out
-    if _cmpack is not None and not isinstance(list_of_ids, np.ndarray):
+    native = _native_packer()
+    if native is not None and not isinstance(list_of_ids, np.ndarray):
         # native packer (csrc_host/cmpack.c, built by conmech_b200.build): ~5 ns per id straight from
         # the Python lists; the numpy path below (same result) costs ~70 ns per id on lists
         dst = out if (out is not None and out.dtype == np.uint32 and out.flags.c_contiguous and out.shape == (B, W)) \
             else np.empty((B, W), dtype=np.uint32)
-        _cmpack.pack(list_of_ids, int(nE), dst)
+        native.pack(list_of_ids, int(nE), dst)
         if out is not None and dst is not out:
             out[...] = dst
             return out

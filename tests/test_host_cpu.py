@@ -72,7 +72,7 @@ def test_native_mask_packer_matches_numpy():
     import random
     import numpy as np
     from conmech_b200 import masks
-    assert masks._cmpack is not None, 'run python -m conmech_b200.build'
+    assert masks._native_packer() is not None, 'run python -m conmech_b200.build'
     nE = 931
     rng = random.Random(1)
     subs = [rng.sample(range(nE), rng.randint(1, 900)) for _ in range(200)]
@@ -85,11 +85,11 @@ def test_native_mask_packer_matches_numpy():
     subs[9] = np.array(subs[9], dtype=np.uint16)
     subs[10] = [nE - 1, 0, 0, 31, 32]
     native = masks.pack_masks(subs, nE)
-    saved, masks._cmpack = masks._cmpack, None
+    masks.USE_NATIVE = False
     try:
         ref = masks.pack_masks([list(x) for x in subs], nE)
     finally:
-        masks._cmpack = saved
+        masks.USE_NATIVE = True
     assert native.dtype == np.uint32 and native.shape == (200, 30)
     assert (native == ref).all()
     assert set(masks.mask_to_ids(native[10], nE)) == {0, 31, 32, nE - 1}
