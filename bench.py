@@ -30,8 +30,8 @@ METRIC = 'partial-structure solves/sec (1k-elem frame)'
 UNIT = 'solves/s'
 FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool's B200 (round 1)
 # DRAM bytes (read + write) of ONE k3_factor_flow launch over 4096 config-3 subsets, from the ncu --set full
-# capture summarised in profiles/r01c_ncu_k2_k3_k4.txt (24.66 GB read + 9.52 GB written)
-K3_DRAM_BYTES_PER_SUBSET = (24.656677e9 + 9.519647e9) / 4096
+# capture summarised in profiles/r01c_ncu_k2_k3_k4.txt (24.30 GB read + 9.52 GB written)
+K3_DRAM_BYTES_PER_SUBSET = (24.302537e9 + 9.517715e9) / 4096
 
 
 def parse():
