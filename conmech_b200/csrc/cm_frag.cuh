@@ -31,8 +31,12 @@ __device__ __forceinline__ void ldg4(double (&v)[4], const double *p) {
 // small data that IS re-read through L1 (spilled registers, M_J, pivots, envelope) survives the
 // streams.
 __device__ __forceinline__ void ldg4s(double (&v)[4], const double *p) {
+#if defined(CM_LD256) && CM_LD256       // experiment: one 256-bit load per lane instead of two 128-bit halves
+    asm volatile("ld.global.L1::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+#else
     asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
     asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+#endif
 }
 __device__ __forceinline__ void stg4(double *p, double a, double b, double c, double d) {
     asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
