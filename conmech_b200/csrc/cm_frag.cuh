@@ -135,6 +135,17 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
     if (!SYRK) ldg4s(b0, pb);
     d0 = pd[0];
     for (int q = 0; q < nsteps; q += 2) {
+#if defined(CM_PF_DIST) && CM_PF_DIST > 0      // experiment: pull the lane's sectors of k-steps q+D, q+D+1 into L1 with real (dummy) loads
+        {
+            unsigned z0, z1;
+            asm volatile("ld.global.L1::evict_last.b32 %0, [%1];" : "=r"(z0) : "l"(pa + 128 * CM_PF_DIST) : "memory");
+            asm volatile("ld.global.L1::evict_last.b32 %0, [%1];" : "=r"(z1) : "l"(pa + 128 * (CM_PF_DIST + 1)) : "memory");
+            if (!SYRK) {
+                asm volatile("ld.global.L1::evict_last.b32 %0, [%1];" : "=r"(z0) : "l"(pb + 128 * CM_PF_DIST) : "memory");
+                asm volatile("ld.global.L1::evict_last.b32 %0, [%1];" : "=r"(z1) : "l"(pb + 128 * (CM_PF_DIST + 1)) : "memory");
+            }
+        }
+#endif
         ldg4s(a1, pa + 128);
         if (!SYRK) ldg4s(b1, pb + 128);
         d1 = pd[4];
