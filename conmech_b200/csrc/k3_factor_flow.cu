@@ -86,7 +86,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     {
         volatile int *yprog = CTX(yprog);
         int y = *yprog;
-        while (y <= J) { __nanosleep(40); y = *yprog; }
+        while (y <= J) { __nanosleep(CM_SLEEP_NS); y = *yprog; }
         __threadfence_block();
     }
     FP_ADD(pc, 7);
@@ -226,7 +226,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         // forward substitution of row I once rows < I are done (they finish one chain step earlier)
         {
             int y = *yprog;
-            while (y < I) { __nanosleep(40); y = *yprog; }
+            while (y < I) { __nanosleep(CM_SLEEP_NS); y = *yprog; }
             __threadfence_block();
         }
         FP_ADD(pc, 7);
