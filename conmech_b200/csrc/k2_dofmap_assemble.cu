@@ -419,7 +419,11 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                 const int K0 = base_c >> 5, K1 = (base_c + cnt - 1) >> 5;
                 if (ktilde_rm && K0 == K1) {
                     // row-major K~ tile: the row's entries are contiguous - 16-byte stores where aligned
+#if defined(K2_EXP) && K2_EXP == 5          // timing experiment (wrong results): all entry stores into one 8 KB tile of the slab
+                    double *dst = tiles + (r & 31) * 32 + (base_c & 31);       // (same alignment as the real destination)
+#else
                     double *dst = tiles + ((size_t)I * bt + (K0 - I + bt - 1)) * CM_TILE_ELEMS + (r & 31) * 32 + (base_c & 31);
+#endif
                     int x = 0;
                     if ((base_c & 1) && x < cnt) { dst[0] = vals[0]; x = 1; }
 #pragma unroll
