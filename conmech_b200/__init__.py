@@ -9,7 +9,7 @@ from .io_base import (Model, LoadCase, Node, Element, Support, Joint, CrossSec, 
 from .stiffness_base import StiffnessBase
 from .cuda_stiffness import CudaStiffness
 from .stiffness_checker import StiffnessChecker
-from .masks import pack_masks, ids_to_mask, mask_to_ids
+from .masks import pack_masks, pack_masks_csr, ids_to_mask, mask_to_ids
 from .sharding import shard_range, solve_many_sharded
 
 __version__ = '0.1.0'

@@ -96,7 +96,47 @@ static PyObject *pack(PyObject *self, PyObject *args) {
     Py_RETURN_NONE;
 }
 
+/* pack_csr(flat_ids, offsets, nE, out): subset b = flat_ids[offsets[b] : offsets[b+1]] (int64 buffers),
+ * the form a planner that keeps its subsets in arrays already has - no Python objects per id. */
+static PyObject *pack_csr(PyObject *self, PyObject *args) {
+    PyObject *flatobj, *offobj, *outobj;
+    Py_ssize_t nE;
+    if (!PyArg_ParseTuple(args, "OOnO", &flatobj, &offobj, &nE, &outobj)) return NULL;
+    if (nE <= 0) { PyErr_SetString(PyExc_ValueError, "nE must be positive"); return NULL; }
+    Py_buffer fb, ofb, ob;
+    if (PyObject_GetBuffer(flatobj, &fb, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) return NULL;
+    if (PyObject_GetBuffer(offobj, &ofb, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) { PyBuffer_Release(&fb); return NULL; }
+    if (PyObject_GetBuffer(outobj, &ob, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) { PyBuffer_Release(&fb); PyBuffer_Release(&ofb); return NULL; }
+    int ok = 0;
+    const Py_ssize_t W = (nE + 31) / 32;
+    const Py_ssize_t B = ofb.itemsize == 8 ? ofb.len / 8 - 1 : -1;
+    if (fb.itemsize != 8 || ofb.itemsize != 8 || B < 0 || ob.len != (Py_ssize_t)(B * W * 4)) {
+        PyErr_SetString(PyExc_ValueError, "pack_csr: int64 flat ids, int64 offsets [B+1], output of B*ceil(nE/32) uint32 words");
+    } else {
+        const int64_t *flat = (const int64_t *)fb.buf, *off = (const int64_t *)ofb.buf;
+        const int64_t n_flat = fb.len / 8;
+        uint32_t *out = (uint32_t *)ob.buf;
+        memset(out, 0, (size_t)ob.len);
+        ok = 1;
+        for (Py_ssize_t b = 0; b < B && ok; ++b) {
+            uint32_t *row = out + b * W;
+            if (off[b] < 0 || off[b + 1] < off[b] || off[b + 1] > n_flat) {
+                PyErr_SetString(PyExc_ValueError, "pack_csr: offsets must be non-decreasing and within the id array");
+                ok = 0;
+                break;
+            }
+            if (off[b + 1] == off[b]) { set_all(row, nE); continue; }
+            for (int64_t i = off[b]; i < off[b + 1]; ++i)
+                if (set_bit(row, (Py_ssize_t)flat[i], nE) < 0) { ok = 0; break; }
+        }
+    }
+    PyBuffer_Release(&fb); PyBuffer_Release(&ofb); PyBuffer_Release(&ob);
+    if (!ok) return NULL;
+    Py_RETURN_NONE;
+}
+
 static PyMethodDef methods[] = {
+    {"pack_csr", pack_csr, METH_VARARGS, "pack_csr(flat_ids, offsets, nE, out): CSR id arrays -> uint32 subset bit masks"},
     {"pack", pack, METH_VARARGS, "pack(list_of_ids, nE, out): element-id sequences -> uint32 subset bit masks"},
     {NULL, NULL, 0, NULL}};
 

@@ -317,6 +317,12 @@ class CudaStiffness(StiffnessBase):
         _capi.check(rc[0])
         return res
 
+    def solve_many_csr(self, flat_ids, offsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):
+        """``solve_many`` for subsets kept as two arrays: subset b = ``flat_ids[offsets[b]:offsets[b+1]]``
+        (an empty range = the full structure).  No Python object per id: packing costs ~2 ns per id."""
+        from .masks import pack_masks_csr
+        return self.solve_many(pack_masks_csr(flat_ids, offsets, self.nE), want=want, out=out)
+
     PIPELINE_CHUNK = 2048          # subsets per pipelined chunk of solve_many (id lists only)
 
     def solve_many_device(self, masks, want=('flag', 'status', 'max_trans', 'compliance'), out=None,

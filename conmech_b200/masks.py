@@ -70,6 +70,28 @@ def pack_masks(list_of_ids, nE, out=None):
     return packed
 
 
+def pack_masks_csr(flat_ids, offsets, nE, out=None):
+    """Masks for subsets given as two arrays: subset b = ``flat_ids[offsets[b]:offsets[b+1]]``
+    (an empty range = the full structure).  The cheapest host format next to the masks
+    themselves: no Python object per id (about 1 ns per id in the native packer)."""
+    flat = np.ascontiguousarray(flat_ids, dtype=np.int64)
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    B, W = off.size - 1, (nE + 31) // 32
+    if B < 0:
+        raise ValueError('offsets must have B+1 entries')
+    dst = out if (out is not None and out.dtype == np.uint32 and out.flags.c_contiguous and out.shape == (B, W)) \
+        else np.empty((B, W), dtype=np.uint32)
+    native = _native_packer()
+    if native is not None:
+        native.pack_csr(flat, off, int(nE), dst)
+    else:
+        dst[...] = pack_masks([flat[off[b]:off[b + 1]] for b in range(B)], nE)
+    if out is not None and dst is not out:
+        out[...] = dst
+        return out
+    return dst
+
+
 def mask_to_ids(mask, nE):
     bits = np.unpackbits(np.ascontiguousarray(mask).view(np.uint8), bitorder='little')[:nE]
     return np.flatnonzero(bits)

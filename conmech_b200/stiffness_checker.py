@@ -86,6 +86,12 @@ class StiffnessChecker(object):
             return flags, {k: r[k][:, 0].copy() for k in names}
         return flags
 
+    def solve_many_csr(self, flat_ids, offsets, return_details=False):
+        """``solve_many`` for subsets kept as two integer arrays (flat element ids + offsets, an empty
+        range = the full structure): the cheapest host format next to pre-packed bit masks."""
+        from .masks import pack_masks_csr
+        return self.solve_many(pack_masks_csr(flat_ids, offsets, len(self.model.elements)), return_details=return_details)
+
     def get_sigma_max_per_element_many(self, list_of_existing_ids):
         """``get_sigma_max_per_element`` for many subsets at once, computed on the device: a
         (B, nE) array (first load case), 0 for elements that are not in the subset."""

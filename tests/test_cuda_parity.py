@@ -319,6 +319,9 @@ def test_solve_many_from_id_lists_pipelined():
         assert_array_equal(r_lists[k], r_masks[k])
     flags = sc.solve_many(lists)
     assert flags == [bool(f) for f in r_masks['flag'][:, 0]]
+    flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in lists])
+    off = np.concatenate([[0], np.cumsum([len(x) for x in lists])])
+    assert sc.solve_many_csr(flat, off) == flags
     with pytest.raises(IndexError):
         eng.solve_many(lists[:B - 1] + [[len(model.elements)]], want=('flag',))
     assert eng.solve_many(lists[:3], want=('flag',))['flag'].shape == (3, 1)     # the handle is still usable

@@ -97,6 +97,15 @@ def test_native_mask_packer_matches_numpy():
     for bad in ([[0, nE]], [[-1]], [np.array([5, 5000])]):
         with pytest.raises(IndexError):
             masks.pack_masks(bad, nE)
+    # the same subsets as two arrays (flat ids + offsets)
+    lists = [list(x) for x in subs]
+    flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in lists])
+    off = np.concatenate([[0], np.cumsum([len(x) for x in lists])])
+    assert (masks.pack_masks_csr(flat, off, nE) == ref).all()
+    with pytest.raises(IndexError):
+        masks.pack_masks_csr(np.array([0, nE]), np.array([0, 2]), nE)
+    with pytest.raises(ValueError):
+        masks.pack_masks_csr(np.array([1, 2]), np.array([0, 3]), nE)
 
 
 def test_model_io_roundtrip(models_dir):
