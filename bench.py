@@ -4,13 +4,27 @@ the ~1k-element space frame (config 3: grid 7x7x8, 931 elements, 2058 free DOFs,
 element subsets of 20-90 %, gravity load, trans_tol 1e-3), subsets range-partitioned over GPUs.
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+    python bench.py --impl reference --gpus N --steps K ...  # the reference itself on the host CPU
 
-One "step" = one pass of the hot path (assembly -> factorisation -> recovery) over one batch of
-B subsets per GPU (default 12 500, i.e. 100 000 across 8 GPUs).  `value` is device-resident
-throughput (masks already in HBM, CUDA events on the launching stream, max over ranks);
-`e2e` goes through the host-buffer C-ABI call with pinned host masks in and flags / status /
-max_trans / compliance out, host<->device copies inside the timed region.
+One "step" = one pass of the hot path (assembly -> factorisation -> recovery) over one batch of B
+subsets per GPU (default 12 500, i.e. 100 000 across 8 GPUs), with the FULL result of every solve -
+displacements U, fixity reactions Rf, element end forces eR and the scalars flag / status /
+max_trans / compliance - materialised, as the reference does on every solve
+(numpy_stiffness.py:366-391).
+
+  value             device-resident throughput: masks already in HBM, full results written to HBM,
+                    CUDA events on the launching stream, max over ranks
+  value_flags_only  the same with only the four scalars per solve requested (the stiffness-CHECK
+                    variant: no U / Rf / eR stores, no reaction recovery)
+  e2e               through the host-buffer C-ABI call (cm_solve_many_host): pinned host masks in,
+                    full results out to pinned host arrays, host<->device copies inside the timed
+                    region; e2e.flags_only_value = the four scalars out only; e2e.id_lists_value =
+                    StiffnessChecker.solve_many(list of Python id lists) -> list of bools (the facade
+                    call, packing included)
+  roofline          the dominant kernel (K3, FP64 tensor pipe) + roofline.kernels = K2 / K3 / K4
+  other_configs     (N = 1) BASELINE configs 1, 2, 4, 5 on the GPU next to the CPU rate of each
+  single_process    (N > 1, rank 0 after the SPMD legs) ONE process driving all N GPUs through
+                    cm_solve_many_host_multi, host gather inside the timed region
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -29,9 +43,13 @@ TRANS_TOL = 1e-3
 METRIC = 'partial-structure solves/sec (1k-elem frame)'
 UNIT = 'solves/s'
 FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool's B200 (round 1)
-# DRAM bytes (read + write) of ONE k3_factor_flow launch over 4096 config-3 subsets, from the ncu --set full
-# capture summarised in profiles/r01c_ncu_k2_k3_k4.txt (24.30 GB read + 9.52 GB written)
-K3_DRAM_BYTES_PER_SUBSET = (24.302537e9 + 9.517715e9) / 4096
+HBM_FALLBACK_GBS = 6549.8        # MEASURED_PEAKS.json of this pool (round 1)
+# DRAM bytes (read + write) per subset of ONE launch over 4096 config-3 subsets, from the ncu --set full
+# capture summarised in profiles/ (file named in `traffic_source`)
+NCU_DRAM_BYTES_PER_SUBSET = {'k2': 8.75e9 / 4096, 'k3': (24.302537e9 + 9.517715e9) / 4096, 'k4': 11.28e9 / 4096}
+NCU_SOURCE = 'profiles/r01c_ncu_k2_k3_k4.txt'
+FULL = ('flag', 'status', 'max_trans', 'compliance', 'U', 'Rf', 'eR')
+SCALARS = ('flag', 'status', 'max_trans', 'compliance')
 
 
 def parse():
@@ -43,6 +61,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=12500, help='subsets per GPU per step')
     ap.add_argument('--cpu-sample', type=int, default=0, help='subsets in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--distinct-batches', type=int, default=2)
     return ap.parse_args()
 
@@ -53,6 +72,7 @@ def workload_config(args, extra=None):
            'subsets_per_gpu_per_step': args.batch,
            'global_subsets_per_step': args.batch * args.gpus,
            'load_cases': 1,
+           'results': 'full: U, Rf, eR + flag/status/max_trans/compliance per solve (127 KB per solve)',
            'partition': 'contiguous seed ranges per GPU, no collective on the solve path',
            'l2': 'per-step streamed working set (block-band factors, ~4.8 MB/subset) is >> 126 MB L2; '
                  'consecutive steps use different subset batches; element tables (1.1 MB) stay L2-resident by design'}
@@ -117,18 +137,21 @@ class ClockSampler(object):
 
 
 def run_reference(args):
-    """The reference algorithm on the host CPU (oracle port; the Python reference cannot travel to
-    the GPU box).  Rank 0 only; every step solves a bounded sample of the same workload."""
+    """The reference's own CPU implementation of the path on the box's host cores: the unmodified
+    reference from baseline/_ref (kind "reference"), else the oracle port (kind "port").  Rank 0 only;
+    every step solves a bounded sample of the same workload on all cores."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     from oracle import cpu_bench
     n_procs = os.cpu_count() or 1
-    per_step = args.cpu_sample or 100 * n_procs                          # ~3 s per step
+    kind = 'reference' if cpu_bench.reference_available() else 'port'
+    per_step = args.cpu_sample or (30 if kind == 'reference' else 100) * n_procs          # ~3 s per step
     import multiprocessing as mp
     ctx = mp.get_context('spawn')
     seeds_all = list(range((args.warmup + args.steps) * per_step))
-    with ctx.Pool(n_procs, initializer=cpu_bench._init_worker, initargs=(GRID, TRANS_TOL)) as pool:
+    spec = dict(cpu_bench.CONFIG3, model=('grid',) + GRID + (False,), trans_tol=TRANS_TOL)
+    with ctx.Pool(n_procs, initializer=cpu_bench._init_worker, initargs=(spec, kind)) as pool:
         def step(k):
             seeds = seeds_all[k * per_step:(k + 1) * per_step]
             chunks = [c for c in (seeds[i::n_procs] for i in range(n_procs)) if c]
@@ -140,16 +163,128 @@ def run_reference(args):
         dts = [step(args.warmup + k) for k in range(args.steps)]
     total = sum(dts)
     value = per_step * args.steps / total
+    what = ('unmodified reference: pyconmech StiffnessChecker(checker_engine="numpy").solve(ids) from baseline/_ref'
+            if kind == 'reference' else 'oracle port oracle/frame_oracle.py (baseline/_ref absent)')
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(args, {'reference_sample_per_step': per_step}),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_procs, 'kind': 'port',
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_procs, 'kind': kind, 'what': what,
                              'sample': '{} subsets per step (seeds 0..), {} processes, {}'.format(
                                  per_step, n_procs, cpu_bench.cpu_model_name())},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(REPO, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (burst copy rate; driver-written)'
+    except (OSError, KeyError, ValueError):
+        return HBM_FALLBACK_GBS, 'fallback: the copy rate MEASURED_PEAKS.json held in round 1 (file absent)'
+
+
+def other_configs_gpu(torch, np, dev, cpu_rates):
+    """BASELINE configs 1, 2, 4 and 5 on one GPU (full results on the device, CUDA events), each
+    next to the CPU rate of the same workload."""
+    from conmech_b200 import StiffnessChecker, LoadCase, GravityLoad, Model
+    from conmech_b200 import synthetic as syn
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    def with_cpu(name, rec):
+        if cpu_rates and name in cpu_rates:
+            rec['cpu'] = cpu_rates[name]
+        out[name] = rec
+
+    # config 1 / 2: the bundled tower, single solve() latency through the facade and the prefix batch
+    path = os.path.join(REPO, 'tests', 'golden', 'models', 'tower_3D.json')
+    model = Model.from_json(path)
+    sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    sc.set_nodal_displacement_tol(trans_tol=1e-3)
+    for _ in range(5):
+        sc.solve([])
+    t0 = time.perf_counter()
+    n = 200
+    for _ in range(n):
+        ok = sc.solve([])
+    lat = (time.perf_counter() - t0) / n
+    with_cpu('config1_tower_full_solve', {'value': 1.0 / lat, 'unit': UNIT, 'latency_ms': 1e3 * lat, 'flag': bool(ok),
+                                           'what': 'StiffnessChecker.solve([]) on tower_3D (24 elements), host wall clock per call, '
+                                                   'nD / fR / eR stored like the reference'})
+    order = syn.bfs_sequence(model)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        flags = sc.solve_sequence(order)
+    dt = (time.perf_counter() - t0) / 50
+    with_cpu('config2_tower_bfs_prefixes', {'value': len(order) / dt, 'unit': UNIT, 'ms_per_sequence': 1e3 * dt,
+                                             'flags': ''.join('1' if f else '0' for f in flags),
+                                             'what': 'solve_sequence(order): all 24 prefixes of the BFS construction sequence in one call'})
+    del sc
+
+    # config 4: joints on horizontals, four load cases per subset, height-field subsets
+    model = syn.grid_frame(7, 7, 8, joints=True)
+    sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)
+    sc.set_load_cases(syn.config4_loadcases(model))
+    eng = sc._sc_ins
+    B4 = 4096
+    masks = syn.pack_masks([syn.heightfield_subset(model, 7, 7, 8, seed=s) for s in range(B4)], len(model.elements))
+    dm = torch.from_numpy(masks.view(np.int32)).to(dev)
+    r = {}
+
+    def run4():
+        r['o'] = eng.solve_many_device(dm, want=FULL, out=r.get('o'))
+    ms = timed(run4, 3)
+    n_lc = r['o']['flag'].shape[1]
+    with_cpu('config4_joints_4_loadcases', {'value': B4 * n_lc / ms * 1e3, 'unit': UNIT, 'subsets': B4, 'load_cases': n_lc,
+                                             'ms_per_batch': ms, 'status_ok': int((r['o']['status'] == 0).sum().item()),
+                                             'what': 'grid 7x7x8 + joint releases, 4 load cases per subset (one factorisation serves '
+                                                     'all four), solve = (subset, load case), full results on device'})
+    del sc, eng, r, dm
+    torch.cuda.empty_cache()
+
+    # config 5: 10k-element frame, 512 subsets, factorisation-bound
+    model = syn.grid_frame(15, 15, 16)
+    sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    eng = sc._sc_ins
+    B5 = 512
+    masks = syn.pack_masks([syn.connected_subset(model, s) for s in range(B5)], len(model.elements))
+    dm = torch.from_numpy(masks.view(np.int32)).to(dev)
+    r = {}
+
+    def run5():
+        r['o'] = eng.solve_many_device(dm, want=FULL + ('profile_flops',), out=r.get('o'), max_in_flight=B5)
+    eng.enable_timing(True)
+    run5()
+    torch.cuda.synchronize(dev)
+    run5()
+    torch.cuda.synchronize(dev)
+    st = eng.last_stage_ms()
+    eng.enable_timing(False)
+    ms = timed(run5, 2)
+    fl = float(r['o']['profile_flops'].sum().item())
+    with_cpu('config5_10k_frame', {'value': B5 / ms * 1e3, 'unit': UNIT, 'subsets': B5, 'ms_per_batch': ms,
+                                    'k3_tflops_algorithmic': fl / st[1] / 1e9, 'stage_ms': [float(x) for x in st],
+                                    'status_ok': int((r['o']['status'] == 0).sum().item()),
+                                    'what': 'grid 15x15x16 (9675 elements / 20 250 free DOFs, band of 35 tiles), random connected subsets, '
+                                            'full results on device'})
+    del sc, eng, r, dm
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -163,12 +298,16 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only) in a child process of its own, before the GPU work starts
     cpu_baseline = None
+    cpu_others = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = subprocess.run([sys.executable, '-m', 'oracle.cpu_bench', str(GRID[0]), str(GRID[1]), str(GRID[2]),
-                            str(TRANS_TOL), str(args.batch), str(args.cpu_sample)],
-                           cwd=REPO, capture_output=True, text=True)
+        cmd = [sys.executable, '-m', 'oracle.cpu_bench', str(GRID[0]), str(GRID[1]), str(GRID[2]),
+               str(TRANS_TOL), str(args.batch), str(args.cpu_sample)]
+        if not args.no_other_configs:
+            cmd.append('others')
+        r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True)
         if r.returncode == 0 and r.stdout.strip():
             cpu_baseline = json.loads(r.stdout.strip().splitlines()[-1])
+            cpu_others = cpu_baseline.pop('other_configs', None)
         else:
             sys.stderr.write('cpu baseline failed: ' + r.stderr[-2000:] + '\n')
 
@@ -177,6 +316,7 @@ def main():
     import torch.distributed as dist
     from conmech_b200 import StiffnessChecker, LoadCase, GravityLoad
     from conmech_b200 import synthetic as syn
+    from conmech_b200 import masks as cm_masks
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -188,8 +328,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        tns = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
     model = syn.grid_frame(*GRID)
-    nE = len(model.elements)
+    nE, nV = len(model.elements), len(model.nodes)
     sc = StiffnessChecker(model, checker_engine='cuda', device=local)
     sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
     sc.set_nodal_displacement_tol(trans_tol=TRANS_TOL)
@@ -205,12 +351,26 @@ def main():
         m = syn.pack_masks([syn.connected_subset(model, base + s) for s in range(B)], nE)
         host_masks.append(torch.from_numpy(m.view(np.int32)).pin_memory())
     dev_masks = [m.to(dev) for m in host_masks]
-    want = ('flag', 'status', 'max_trans', 'compliance')
-    out_dev = None
+    outs = {}
 
-    def step_device(k):
-        nonlocal out_dev
-        out_dev = eng.solve_many_device(dev_masks[k % n_batches], want=want, out=out_dev)
+    def step_device(k, want):
+        outs[want] = eng.solve_many_device(dev_masks[k % n_batches], want=want, out=outs.get(want))
+
+    def timed_device(want):
+        for k in range(args.warmup):
+            step_device(k, want)
+        barrier()
+        eng.reset_counters()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for k in range(args.steps):
+            step_device(args.warmup + k, want)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        n_launch = eng.kernel_launches()
+        ms = ev0.elapsed_time(ev1)
+        barrier()
+        return max_over_ranks(ms), n_launch
 
     # ---- FP64 peak (cuBLAS DGEMM) measured live: the roofline denominator for the factorisation
     a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
@@ -224,113 +384,197 @@ def main():
     fp64_peak = 2 * 8192 ** 3 / best / 1e9
     del a, b
     torch.cuda.empty_cache()
+    hbm_peak, hbm_source = measured_peaks()
 
-    # ---- device-resident timed region
-    for k in range(args.warmup):
-        step_device(k)
-    barrier()
+    # ---- device-resident timed regions: full results (the headline), then the scalars-only variant
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    barrier()
-    eng.reset_counters()
     t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for k in range(args.steps):
-        step_device(args.warmup + k)
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    launches = eng.kernel_launches()
-    ms = ev0.elapsed_time(ev1)
-    barrier()
+    ms_max, launches = timed_device(FULL)
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
     value = world * B * args.steps / (ms_max * 1e-3)
-    flags_true = int(out_dev['flag'].sum().item())
-    status_ok = int((out_dev['status'] == 0).sum().item())
+    flags_true = int(outs[FULL]['flag'].sum().item())
+    status_ok = int((outs[FULL]['status'] == 0).sum().item())
+    ms_flags, _ = timed_device(SCALARS)
+    value_flags = world * B * args.steps / (ms_flags * 1e-3)
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host masks in, host results out)
+    # ---- end to end through the host-buffer C-ABI call (pinned host masks in, pinned host results out)
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
     out_host = {'flag': pin((B, 1), torch.uint8), 'status': pin((B, 1), torch.uint8),
-                'max_trans': pin((B, 1), torch.float64), 'compliance': pin((B, 1), torch.float64)}
+                'max_trans': pin((B, 1), torch.float64), 'compliance': pin((B, 1), torch.float64),
+                'U': pin((B, 1, 6 * nV), torch.float64), 'Rf': pin((B, 1, 6 * nV), torch.float64),
+                'eR': pin((B, 1, nE, 12), torch.float64)}
     host_np = [m.numpy().view(np.uint32) for m in host_masks]
-    for k in range(max(1, args.warmup)):
-        eng.solve_many(host_np[k % n_batches], want=want, out=out_host)
-    barrier()
-    t0 = time.perf_counter()
-    step_times = []
-    for k in range(args.steps):
-        ts = time.perf_counter()
-        eng.solve_many(host_np[(args.warmup + k) % n_batches], want=want, out=out_host)
-        step_times.append(time.perf_counter() - ts)
-    e2e_s = time.perf_counter() - t0
-    if os.environ.get('CM_BENCH_DEBUG'):
-        sys.stderr.write('rank {} e2e step ms {}\n'.format(rank, ['{:.1f}'.format(1e3 * x) for x in step_times]))
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(te.item())
-    h2d = int(host_np[0].nbytes)
-    d2h = int(sum(v.nbytes for v in out_host.values()))
-    assert np.array_equal(out_host['flag'], out_dev['flag'].cpu().numpy()) or n_batches > 1
 
-    # ---- per-stage device times (CUDA events on the launching stream, inside the library) and
-    # the algorithmic work of the same batch -> roofline of the dominant kernel (factorisation)
+    def timed_host(fn):
+        for k in range(max(1, args.warmup)):
+            fn(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            fn(args.warmup + k)
+        dt = time.perf_counter() - t0
+        barrier()
+        return world * B * args.steps / max_over_ranks(dt)
+
+    e2e_full = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=FULL, out=out_host))
+    d2h_full = int(sum(out_host[n].nbytes for n in FULL))
+    # the host path and the device path deliver the same bits
+    eng.solve_many(host_np[0], want=FULL, out=out_host)
+    step_device(0, FULL)
+    torch.cuda.synchronize(dev)
+    for n in FULL:
+        assert np.array_equal(out_host[n], outs[FULL][n].cpu().numpy(), equal_nan=(n in ('max_trans',))), n
+    e2e_flags = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=SCALARS, out=out_host))
+    d2h_flags = int(sum(out_host[n].nbytes for n in SCALARS))
+    # the facade's own calling convention: Python id lists in, list of bools out
+    id_lists = [[cm_masks.mask_to_ids(row, nE).tolist() for row in hm] for hm in host_np[:1]]
+    e2e_lists = timed_host(lambda k: sc.solve_many(id_lists[0]))
+    h2d = int(host_np[0].nbytes)
+
+    # ---- per-stage device times (CUDA events on the launching stream, inside the library) and the
+    # algorithmic work of the same batches -> roofline per kernel
     eng.enable_timing(True)
     stage_ms = np.zeros(3)
     n_waves = 0
     for k in range(args.steps):
-        eng.solve_many_device(dev_masks[(args.warmup + k) % n_batches], want=want, out=out_dev)
+        eng.solve_many_device(dev_masks[(args.warmup + k) % n_batches], want=FULL, out=outs[FULL])
         torch.cuda.synchronize(dev)
         stage_ms += eng.last_stage_ms()
         n_waves += eng.last_wave_count()
     eng.enable_timing(False)
-    flops_batches = 0.0
-    nfree_mean = 0.0
+    flops = entries = tiles = nfree = elems = nfixed = 0.0
     for k in range(args.steps):              # algorithmic work of exactly the batches that were timed
-        pf = eng.solve_many_device(dev_masks[(args.warmup + k) % n_batches], want=('profile_flops', 'n_free'))
+        pf = eng.solve_many_device(dev_masks[(args.warmup + k) % n_batches],
+                                   want=('profile_flops', 'profile_entries', 'envelope_tiles', 'n_free', 'n_fixed'))
         torch.cuda.synchronize(dev)
-        flops_batches += float(pf['profile_flops'].sum().item())
-        nfree_mean += float(pf['n_free'].double().mean().item()) / args.steps
-    # achieved = algorithmic flops of the timed batches / device time of their K3 launches
-    k3_ms_per_launch = stage_ms[1] / n_waves
-    flops_per_launch = flops_batches / n_waves
-    subsets_per_launch = B * args.steps / n_waves
-    achieved = flops_per_launch / (k3_ms_per_launch * 1e-3) / 1e12
-    roofline = {'kernel': 'k3_factor_flow (block-band LDL^T, FP64 DMMA m8n8k4, dataflow rows)', 'bound': 'tensor',
-                'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
-                'traffic': K3_DRAM_BYTES_PER_SUBSET * subsets_per_launch,
-                'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum of one k3_factor_flow launch '
-                                  '(4096 subsets), scaled to this launch size; profiles/r01c_ncu_k2_k3_k4.txt',
-                'peak_source': 'cuBLAS DGEMM 8192^3 fp64 measured live in this run (MEASURED_PEAKS.json has no '
-                               'fp64 entry; earlier measurement on this pool {} TFLOP/s)'.format(FP64_FALLBACK_TFLOPS),
-                'algorithmic_flops_per_launch': flops_per_launch,
-                'flops_definition': 'sum_j h_j^2 over the active DOFs of each subset (envelope LDL^T, multiply-add = 2)',
-                'avg_launch_ms': k3_ms_per_launch, 'subsets_per_launch': subsets_per_launch,
-                'stage_ms_per_step': {'k2_dofmap_assemble': stage_ms[0] / args.steps,
-                                      'k3_factor': stage_ms[1] / args.steps,
-                                      'k4_solve_recover': stage_ms[2] / args.steps}}
+        flops += float(pf['profile_flops'].sum().item())
+        entries += float(pf['profile_entries'].sum().item())
+        tiles += float(pf['envelope_tiles'].sum().item())
+        nfree += float(pf['n_free'].double().sum().item())
+        hm = host_np[(args.warmup + k) % n_batches]
+        elems += float(np.unpackbits(hm.view(np.uint8), axis=1).sum())
+        nfixed += float(pf['n_fixed'].double().sum().item())
+    n_sub = B * args.steps
+    spl = n_sub / n_waves                                   # subsets per launch
+    mask_bytes = info['mask_words'] * 4
+    # algorithmic bytes per subset: S_K = 8 bytes x scalar-profile entries of K_mm (the smallest
+    # of the listed formats; the tile format actually stored is given beside it)
+    sk_profile = 8.0 * entries / n_sub
+    sk_tiles = 8192.0 * tiles / n_sub
+    k2_bytes = mask_bytes + sk_profile + 8.0 * nfree / n_sub
+    k4_bytes = sk_profile + 8.0 * (6 * nV + nfixed / n_sub + 12.0 * elems / n_sub) + 18
+    k2_ms, k3_ms, k4_ms = (stage_ms / n_waves)
+
+    def hbm(name, bytes_per_subset, ms, extra):
+        ach = bytes_per_subset * spl / (ms * 1e-3) / 1e9
+        d = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+             'traffic': NCU_DRAM_BYTES_PER_SUBSET[name] * spl, 'algorithmic_bytes_per_subset': bytes_per_subset,
+             'avg_launch_ms': ms, 'subsets_per_launch': spl}
+        d.update(extra)
+        return d
+    k3_ach = flops / n_waves / (k3_ms * 1e-3) / 1e12
+    k3 = {'kernel': 'k3_factor_flow (block-band LDL^T, FP64 DMMA m8n8k4, dataflow rows)', 'bound': 'tensor',
+          'achieved': k3_ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': k3_ach / fp64_peak,
+          'traffic': NCU_DRAM_BYTES_PER_SUBSET['k3'] * spl,
+          'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over 4096 subsets, scaled to this '
+                            'launch size; ' + NCU_SOURCE,
+          'peak_source': 'cuBLAS DGEMM 8192^3 fp64 measured live in this run (MEASURED_PEAKS.json has no '
+                         'fp64 entry; earlier measurement on this pool {} TFLOP/s)'.format(FP64_FALLBACK_TFLOPS),
+          'algorithmic_flops_per_launch': flops / n_waves,
+          'flops_definition': 'sum_j h_j^2 over the active DOFs of each subset (envelope LDL^T, multiply-add = 2)',
+          'algorithmic_bytes_per_subset': 2 * sk_profile,
+          'avg_launch_ms': k3_ms, 'subsets_per_launch': spl}
+    roofline = dict(k3)
+    roofline['stage_ms_per_step'] = {'k2_dofmap_assemble': stage_ms[0] / args.steps, 'k3_factor': stage_ms[1] / args.steps,
+                                     'k4_solve_recover': stage_ms[2] / args.steps}
+    roofline['kernels'] = {
+        'k2_dofmap_assemble': hbm('k2', k2_bytes, k2_ms, {
+            'bytes_definition': 'mask + S_K + 8 n_s per subset, S_K = 8 x scalar-profile entries of K_mm (SURVEY 8d)',
+            'achieved_tile_format': (mask_bytes + sk_tiles + 8.0 * nfree / n_sub) * spl / (k2_ms * 1e-3) / 1e9,
+            'includes': 'k2_schedule (largest-first rank of the wave, ~60 us)'}),
+        'k3_factor_flow': k3,
+        'k4_solve_recover': hbm('k4', k4_bytes, k4_ms, {
+            'bytes_definition': 'S_K (forward sweep fused into K3) + 8 (6nV + n_fixed + 12 #S) + 18 per solve, full results stored',
+            'achieved_tile_format': (sk_tiles + k4_bytes - sk_profile) * spl / (k4_ms * 1e-3) / 1e9}),
+    }
+    roofline['peak_hbm_source'] = hbm_source
+    roofline['s_k_bytes_per_subset'] = {'profile': sk_profile, 'tile_format': sk_tiles}
+
+    # ---- the other BASELINE configurations (one GPU)
+    others = None
+    outs.clear()
+    out_host = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        eng.close()                      # frees the handle's workspace and staging: config 5 needs the memory
+        torch.cuda.empty_cache()
+        try:
+            others = other_configs_gpu(torch, np, dev, cpu_others)
+        except Exception as ex:          # never lose the headline line to a secondary leg
+            others = {'error': repr(ex)}
+
+    # ---- one process, all GPUs (N > 1): rank 0 drives every device through cm_solve_many_host_multi
+    single = None
+    if world > 1:
+        eng._ws_cache = {}
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                scm = StiffnessChecker(model, checker_engine='cuda', devices=list(range(world)))
+                scm.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+                scm.set_nodal_displacement_tol(trans_tol=TRANS_TOL)
+                em = scm._sc_ins
+                BG = B * world
+                mm = syn.pack_masks([syn.connected_subset(model, s) for s in range(BG)], nE)
+                mm = torch.from_numpy(mm.view(np.int32)).pin_memory().numpy().view(np.uint32)
+                oh = {'flag': pin((BG, 1), torch.uint8), 'status': pin((BG, 1), torch.uint8),
+                      'max_trans': pin((BG, 1), torch.float64), 'compliance': pin((BG, 1), torch.float64)}
+                res = {}
+                for want, name in ((SCALARS, 'flags_only_value'),):
+                    for _ in range(2):
+                        em.solve_many(mm, want=want, out=oh)
+                    t0 = time.perf_counter()
+                    reps = max(2, args.steps // 2)
+                    for _ in range(reps):
+                        em.solve_many(mm, want=want, out=oh)
+                    res[name] = BG * reps / (time.perf_counter() - t0)
+                single = {'n_gpus': world, 'unit': UNIT, 'subsets_per_call': BG, 'value': res['flags_only_value'],
+                          'outputs': 'flag,status,max_trans,compliance',
+                          'what': 'ONE process, one handle and one host thread per GPU (cm_solve_many_host_multi): pinned host '
+                                  'masks in, results written by every device straight into the caller\'s arrays (the host '
+                                  'gather) inside the timed region; host wall clock'}
+                del scm, em
+            except Exception as ex:
+                single = {'error': repr(ex)}
+        barrier()
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': workload_config(args, {'mean_free_dofs_per_subset': nfree_mean,
+                'config': workload_config(args, {'mean_free_dofs_per_subset': nfree / n_sub,
                                                  'half_bandwidth_full': info['half_bandwidth'],
                                                  'flags_true_last_step_rank0': flags_true,
                                                  'status_ok_last_step_rank0': status_ok}),
+                'value_flags_only': value_flags,
                 'clocks': clocks,
-                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'outputs': 'flag,status,max_trans,compliance per subset'},
+                'e2e': {'value': e2e_full, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_full,
+                        'outputs': 'U, Rf, eR, flag, status, max_trans, compliance per subset (pinned host arrays)',
+                        'd2h_gbs': d2h_full * e2e_full / (world * B) / 1e9,
+                        'flags_only_value': e2e_flags, 'flags_only_d2h_bytes_per_step': d2h_flags,
+                        'id_lists_value': e2e_lists,
+                        'id_lists_what': 'StiffnessChecker.solve_many(list of Python id lists) -> list of bools, packing included'},
                 'gpu_launches': launches, 'roofline': roofline}
         if cpu_baseline is not None:
             line['cpu_baseline'] = cpu_baseline
+        if others is not None:
+            line['other_configs'] = others
+        if single is not None:
+            line['single_process'] = single
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -30,7 +30,8 @@ class ModelInfo(C.Structure):
 
 
 OUT_FIELDS = ('flag', 'status', 'n_free', 'n_fixed', 'dof_map', 'node_exists', 'U', 'Rf', 'eR',
-              'compliance', 'max_trans', 'max_rot', 'min_pivot', 'profile_flops', 'sigma_max', 'max_abs_sigma')
+              'compliance', 'max_trans', 'max_rot', 'min_pivot', 'profile_flops', 'sigma_max', 'max_abs_sigma',
+              'profile_entries', 'envelope_tiles')
 
 
 class SolveOut(C.Structure):
@@ -44,7 +45,7 @@ class SolveOutHost(C.Structure):
 # every symbol include/conmech_b200.h declares
 SYMBOLS = ('cm_create', 'cm_destroy', 'cm_get_info', 'cm_get_element_tables', 'cm_get_node_order',
            'cm_set_loadcases', 'cm_get_element_loads', 'cm_set_tol', 'cm_set_variant', 'cm_debug_k3_phase_cycles',
-           'cm_workspace_bytes', 'cm_solve_many', 'cm_solve_many_host', 'cm_solve_many_host_chunks', 'cm_kernel_launches',
+           'cm_workspace_bytes', 'cm_solve_many', 'cm_solve_many_host', 'cm_solve_many_host_chunks', 'cm_solve_many_host_multi', 'cm_kernel_launches',
            'cm_reset_counters', 'cm_enable_timing', 'cm_last_stage_ms', 'cm_last_wave_count', 'cm_element_kernel_dev',
            'cm_last_error', 'cm_version')
 
@@ -76,6 +77,7 @@ def load():
     lib.cm_solve_many.argtypes = [H, C.c_uint64, C.c_int64, C.POINTER(SolveOut), C.c_uint64, C.c_size_t, C.c_uint64]
     lib.cm_solve_many_host.argtypes = [H, C.c_void_p, C.c_int64, C.POINTER(SolveOutHost)]
     lib.cm_solve_many_host_chunks.argtypes = [H, C.c_void_p, C.c_int64, C.POINTER(SolveOutHost), C.c_int64, C.c_void_p]
+    lib.cm_solve_many_host_multi.argtypes = [C.POINTER(H), C.c_int32, C.c_void_p, C.c_int64, C.POINTER(SolveOutHost)]
     lib.cm_kernel_launches.argtypes = [H]
     lib.cm_kernel_launches.restype = C.c_int64
     lib.cm_reset_counters.argtypes = [H]

@@ -22,6 +22,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(CM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
     } while (0)
 
+#define CM_STAGE_SLOTS 6
 struct cm_handle {
     int device = 0;
     cm_model_dev m{};
@@ -50,6 +51,11 @@ struct cm_handle {
     // of the workspace), so that the drain of one wave's factorisation overlaps the next wave
     cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t lane_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // fork, join per lane
+    // host-buffer entry point: ring of device staging slots for the outputs of one wave each, drained
+    // by a copy stream while the lanes compute the following waves
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t slot_done[CM_STAGE_SLOTS] = {}, slot_free[CM_STAGE_SLOTS] = {};
+    cudaEvent_t copy_ev = nullptr;
     int overlap = 1;
     int n_lanes = 3;                     // CM_LANES=1..4: 2 lanes 250 k, 3 lanes 255 k, 4 lanes 255 k solves/s on config 3
 };
@@ -180,6 +186,10 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     cm_handle *h = new cm_handle();
     h->device = d->device;
     cm_model_dev &m = h->m;
+    m.device = d->device;
+    m.n_sm = 0;
+    cudaDeviceGetAttribute(&m.n_sm, cudaDevAttrMultiProcessorCount, d->device);
+    if (m.n_sm <= 0) m.n_sm = 148;
     m.nV = nV; m.nE = nE; m.nS = nS; m.n_lc = 0;
     m.mask_words = (nE + 31) / 32;
     m.trans_tol = 1e-3;
@@ -331,6 +341,12 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     if (ce == cudaSuccess) for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < CM_STAGE_SLOTS && ce == cudaSuccess; ++i) {
+        ce = cudaEventCreateWithFlags(&h->slot_done[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot_free[i], cudaEventDisableTiming);
+    }
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming);
     if (const char *e = getenv("CM_LANES")) { int n = atoi(e); if (n >= 1 && n <= 4) h->n_lanes = n; }
     if (const char *e = getenv("CM_NO_OVERLAP")) h->overlap = (e[0] == '1') ? 0 : 1;
     if (ce == cudaSuccess) ce = cm_launch_element_tables(m, h->stream);
@@ -357,6 +373,12 @@ int cm_destroy(cm_handle *h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 4; ++i) if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
     for (int i = 0; i < 5; ++i) if (h->lane_ev[i]) cudaEventDestroy(h->lane_ev[i]);
+    for (int i = 0; i < CM_STAGE_SLOTS; ++i) {
+        if (h->slot_done[i]) cudaEventDestroy(h->slot_done[i]);
+        if (h->slot_free[i]) cudaEventDestroy(h->slot_free[i]);
+    }
+    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return CM_OK;
 }
@@ -419,16 +441,15 @@ int cm_set_loadcases(cm_handle *h, int32_t n_lc, const double *nodal, const doub
     CU(cudaSetDevice(h->device));
     cm_model_dev &m = h->m;
     const size_t nE = m.nE, nV = m.nV;
-    if (h->d_q) { cudaFree(h->d_q); h->d_q = nullptr; }
-    if (h->d_pnodal) { cudaFree(h->d_pnodal); h->d_pnodal = nullptr; }
-    CU(cudaMalloc((void **)&h->d_q, n_lc * nE * 12 * sizeof(double)));
-    CU(cudaMalloc((void **)&h->d_pnodal, n_lc * 6 * nV * sizeof(double)));
-    CU(cudaMemcpy(h->d_pnodal, nodal, n_lc * 6 * nV * sizeof(double), cudaMemcpyHostToDevice));
+    // New tables are built beside the old ones and swapped in only when every step succeeded: a
+    // failure leaves the handle exactly as it was (old load cases, old layout).
+    double *nq = nullptr, *npn = nullptr;
     double *d_w = nullptr, *d_g = nullptr;
     unsigned char *d_has = nullptr, *d_on = nullptr;
-    int rc = CM_OK;
-    cudaError_t ce = cudaSuccess;
-    if (has_udl) {
+    cudaError_t ce = cudaMalloc((void **)&nq, n_lc * nE * 12 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&npn, n_lc * 6 * nV * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpy(npn, nodal, n_lc * 6 * nV * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && has_udl) {
         ce = cudaMalloc((void **)&d_w, n_lc * nE * 3 * sizeof(double));
         if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_has, n_lc * nE);
         if (ce == cudaSuccess) ce = cudaMemcpy(d_w, w_udl, n_lc * nE * 3 * sizeof(double), cudaMemcpyHostToDevice);
@@ -438,12 +459,20 @@ int cm_set_loadcases(cm_handle *h, int32_t n_lc, const double *nodal, const doub
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_on, n_lc);
     if (ce == cudaSuccess) ce = cudaMemcpy(d_g, grav_dir, n_lc * 3 * sizeof(double), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMemcpy(d_on, grav_on, n_lc, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cm_launch_element_loads(m, n_lc, d_w, d_has, d_on, d_g, h->d_q, h->stream);
-    h->launches++;
+    if (ce == cudaSuccess) {
+        ce = cm_launch_element_loads(m, n_lc, d_w, d_has, d_on, d_g, nq, h->stream);
+        h->launches++;
+    }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
-    if (ce != cudaSuccess) rc = fail(CM_ERR_CUDA, std::string("cm_set_loadcases: ") + cudaGetErrorString(ce));
     cudaFree(d_w); cudaFree(d_has); cudaFree(d_g); cudaFree(d_on);
-    if (rc != CM_OK) return rc;
+    if (ce != cudaSuccess) {
+        cudaFree(nq); cudaFree(npn);
+        return fail(CM_ERR_CUDA, std::string("cm_set_loadcases: ") + cudaGetErrorString(ce));
+    }
+    if (h->d_q) cudaFree(h->d_q);
+    if (h->d_pnodal) cudaFree(h->d_pnodal);
+    h->d_q = nq;
+    h->d_pnodal = npn;
     m.n_lc = n_lc;
     m.q = h->d_q;
     m.pnodal = h->d_pnodal;
@@ -474,7 +503,7 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
 
 int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
-    if (variant < 0 || variant > 9) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..9");
+    if (variant < 0 || variant > 9) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..9 (7/8/9: 2-/3-/1-warp CTAs, timing experiments)");
     h->variant = variant;
     return CM_OK;
 }
@@ -487,18 +516,31 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
     return CM_OK;
 }
 
-int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *o, uint64_t ws_dev,
-                  size_t ws_bytes, uint64_t stream) {
-    if (!h || !o) return fail(CM_ERR_INVALID, "cm_solve_many: null argument");
-    if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many: call cm_set_loadcases first");
-    if (B <= 0) return CM_OK;
-    if (!masks_dev || !ws_dev) return fail(CM_ERR_INVALID, "cm_solve_many: null device buffer");
+}  // extern "C"
+
+// ---- wave plan.  The batch is cut into equal waves (a short last wave would leave most SMs idle).
+// Outside timing mode, and when the batch needs more than one wave, the workspace is split into
+// n_lanes parts and consecutive waves rotate over as many internal streams forked from / joined to
+// the caller's stream: a factorisation launch drains over roughly one CTA lifetime, and the other
+// lanes' kernels fill the SMs it frees.  Every wave is independent (own subsets, own outputs, own
+// share of the workspace).
+struct WavePlan { bool lanes; int NL; long long cap, n_waves, wsize; };
+static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *p) {
     const size_t per = h->L.per_subset;
     long long wave = (long long)(ws_bytes / per);
     if (wave < 1) return fail(CM_ERR_NOMEM, "cm_solve_many: workspace smaller than one subset (" + std::to_string(per) + " bytes)");
     if (wave > B) wave = B;
-    CU(cudaSetDevice(h->device));
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int sm_fill = getenv("CM_LANE_MIN") ? atoi(getenv("CM_LANE_MIN")) : 8 * h->m.n_sm;     // two full sets of resident factorisation CTAs
+    p->NL = h->n_lanes;
+    p->lanes = !h->timing && h->overlap && p->NL > 1 && h->lane_stream[0] && B > wave / p->NL && wave / p->NL >= sm_fill;
+    p->cap = p->lanes ? wave / p->NL : wave;
+    p->n_waves = (B + p->cap - 1) / p->cap;
+    if (p->lanes && getenv("CM_WAVE_ROUND") && atoi(getenv("CM_WAVE_ROUND")) && p->n_waves % p->NL) p->n_waves += p->NL - p->n_waves % p->NL;   // experiment: same number of waves per lane
+    p->wsize = (B + p->n_waves - 1) / p->n_waves;
+    return CM_OK;
+}
+
+static cm_out_dev out_dev_of(const cm_solve_out *o) {
     cm_out_dev od;
     od.flag = reinterpret_cast<unsigned char *>(o->flag);
     od.status = reinterpret_cast<unsigned char *>(o->status);
@@ -516,30 +558,29 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
     od.profile_flops = reinterpret_cast<double *>(o->profile_flops);
     od.sigma_max = reinterpret_cast<double *>(o->sigma_max);
     od.max_abs_sigma = reinterpret_cast<double *>(o->max_abs_sigma);
-    char *ws = reinterpret_cast<char *>(ws_dev);
-    const uint32_t *masks = reinterpret_cast<const uint32_t *>(masks_dev);
+    od.profile_entries = reinterpret_cast<double *>(o->profile_entries);
+    od.envelope_tiles = reinterpret_cast<double *>(o->envelope_tiles);
+    return od;
+}
+
+// The waves of one call.  `before(w, first, count, lane_stream, &od)` runs before a wave's kernels are
+// enqueued and may redirect the wave's outputs; `after(...)` runs right after its last kernel.
+template <typename Before, typename After>
+static int run_waves(cm_handle *h, const uint32_t *masks, int64_t B, const cm_out_dev &od0, char *ws,
+                     const WavePlan &P, cudaStream_t st, Before before, After after) {
+    const size_t per = h->L.per_subset;
     double acc_ms[3] = {0, 0, 0};
-    // Waves.  The batch is cut into equal waves (a short last wave would leave most SMs idle).
-    // Outside timing mode, and when the batch needs more than one wave, the workspace is split in two
-    // and consecutive waves alternate between two internal streams forked from / joined to `st`:
-    // a factorisation launch drains over roughly one CTA lifetime, and the other lane's kernels fill
-    // the SMs it frees.  Every wave is independent (own subsets, own outputs, own workspace half).
-    const int sm_fill = getenv("CM_LANE_MIN") ? atoi(getenv("CM_LANE_MIN")) : 2 * 592;     // two full sets of resident factorisation CTAs
-    const int NL = h->n_lanes;
-    const bool two_lanes = !h->timing && h->overlap && NL > 1 && h->lane_stream[0] && B > wave / NL && wave / NL >= sm_fill;
-    const long long cap = two_lanes ? wave / NL : wave;
-    long long n_waves = (B + cap - 1) / cap;
-    if (two_lanes && getenv("CM_WAVE_ROUND") && atoi(getenv("CM_WAVE_ROUND")) && n_waves % NL) n_waves += NL - n_waves % NL;   // experiment: same number of waves per lane
-    const long long wsize = (B + n_waves - 1) / n_waves;
-    if (two_lanes) {
+    if (P.lanes) {
         CU(cudaEventRecord(h->lane_ev[0], st));
-        for (int i = 0; i < NL; ++i) CU(cudaStreamWaitEvent(h->lane_stream[i], h->lane_ev[0], 0));
+        for (int i = 0; i < P.NL; ++i) CU(cudaStreamWaitEvent(h->lane_stream[i], h->lane_ev[0], 0));
     }
     long long w = 0;
-    for (long long first = 0; first < B; first += wsize, ++w) {
-        const int count = (int)std::min<long long>(wsize, B - first);
-        cudaStream_t ls = two_lanes ? h->lane_stream[w % NL] : st;
-        char *lws = two_lanes ? ws + (size_t)(w % NL) * (size_t)cap * per : ws;
+    for (long long first = 0; first < B; first += P.wsize, ++w) {
+        const int count = (int)std::min<long long>(P.wsize, B - first);
+        cudaStream_t ls = P.lanes ? h->lane_stream[w % P.NL] : st;
+        char *lws = P.lanes ? ws + (size_t)(w % P.NL) * (size_t)P.cap * per : ws;
+        cm_out_dev od = od0;
+        { int rc = before(w, first, count, ls, od); if (rc != CM_OK) return rc; }
         if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
         CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, h->variant != 0 ? 1 : 0, ls));
         if (h->variant != 0) { CU(cm_launch_schedule(h->L, lws, count, ls)); h->launches += 1; }
@@ -564,45 +605,80 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
                 acc_ms[i] += ms;
             }
         }
+        { int rc = after(w, first, count, ls); if (rc != CM_OK) return rc; }
     }
-    if (two_lanes)
-        for (int i = 0; i < NL; ++i) {
+    if (P.lanes)
+        for (int i = 0; i < P.NL; ++i) {
             CU(cudaEventRecord(h->lane_ev[1 + i], h->lane_stream[i]));
             CU(cudaStreamWaitEvent(st, h->lane_ev[1 + i], 0));
         }
     if (h->timing) for (int i = 0; i < 3; ++i) h->stage_ms[i] = acc_ms[i];
-    h->last_waves = (int)n_waves;
+    h->last_waves = (int)P.n_waves;
     return CM_OK;
 }
 
+extern "C" {
+
+int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *o, uint64_t ws_dev,
+                  size_t ws_bytes, uint64_t stream) {
+    if (!h || !o) return fail(CM_ERR_INVALID, "cm_solve_many: null argument");
+    if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many: call cm_set_loadcases first");
+    if (B <= 0) return CM_OK;
+    if (!masks_dev || !ws_dev) return fail(CM_ERR_INVALID, "cm_solve_many: null device buffer");
+    WavePlan P;
+    { int rc = plan_waves(h, B, ws_bytes, &P); if (rc != CM_OK) return rc; }
+    CU(cudaSetDevice(h->device));
+    return run_waves(h, reinterpret_cast<const uint32_t *>(masks_dev), B, out_dev_of(o), reinterpret_cast<char *>(ws_dev), P,
+                     reinterpret_cast<cudaStream_t>(stream),
+                     [](long long, long long, int, cudaStream_t, cm_out_dev &) { return CM_OK; },
+                     [](long long, long long, int, cudaStream_t) { return CM_OK; });
+}
+
+}  // extern "C"
+
+// per-subset bytes of every output of cm_solve_out_host, in the order of the struct
+namespace {
+struct OutItem { void *host; size_t stride; size_t off; };       // stride = bytes per subset; off = offset inside a staging slot
+constexpr int N_OUT = 18;
+void out_items(const cm_handle *h, const cm_solve_out_host *o, OutItem (&it)[N_OUT]) {
+    const size_t nV = h->m.nV, nE = h->m.nE, Lc = h->m.n_lc;
+    const OutItem t[N_OUT] = {
+        {o->flag, Lc, 0}, {o->status, Lc, 0}, {o->n_free, 4, 0}, {o->n_fixed, 4, 0}, {o->dof_map, 6 * nV * 4, 0},
+        {o->node_exists, nV, 0}, {o->U, Lc * 6 * nV * 8, 0}, {o->Rf, Lc * 6 * nV * 8, 0}, {o->eR, Lc * nE * 12 * 8, 0},
+        {o->compliance, Lc * 8, 0}, {o->max_trans, Lc * 8, 0}, {o->max_rot, Lc * 8, 0}, {o->min_pivot, 8, 0},
+        {o->profile_flops, 8, 0}, {o->sigma_max, Lc * nE * 8, 0}, {o->max_abs_sigma, Lc * 8, 0},
+        {o->profile_entries, 8, 0}, {o->envelope_tiles, 8, 0}};
+    for (int i = 0; i < N_OUT; ++i) it[i] = t[i];
+}
+void out_advance(const cm_handle *h, cm_solve_out_host *o, int64_t b0) {
+    OutItem it[N_OUT];
+    out_items(h, o, it);
+    void **f[N_OUT] = {(void **)&o->flag, (void **)&o->status, (void **)&o->n_free, (void **)&o->n_fixed, (void **)&o->dof_map,
+                       (void **)&o->node_exists, (void **)&o->U, (void **)&o->Rf, (void **)&o->eR, (void **)&o->compliance,
+                       (void **)&o->max_trans, (void **)&o->max_rot, (void **)&o->min_pivot, (void **)&o->profile_flops,
+                       (void **)&o->sigma_max, (void **)&o->max_abs_sigma, (void **)&o->profile_entries,
+                       (void **)&o->envelope_tiles};
+    for (int i = 0; i < N_OUT; ++i)
+        if (it[i].host) *f[i] = static_cast<char *>(it[i].host) + (size_t)b0 * it[i].stride;
+}
+}  // namespace
+
+extern "C" {
+
+// Host buffers.  Masks go up in one copy.  Outputs are staged per WAVE in a ring of device slots: right
+// after a wave's last kernel its slot is drained to the caller's arrays by a copy stream (one
+// cudaMemcpyAsync per requested output, written at the subset's final position), while the lanes
+// compute the following waves; a slot is reused only after its copies have finished.  The device
+// staging is therefore bounded by CM_STAGE_SLOTS waves, not by the batch, and the device->host
+// transfer of full results (U, Rf, eR: 127 KB per subset on the 1k-element frame) overlaps the
+// kernels instead of following them.
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, const cm_solve_out_host *o) {
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host: null argument");
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many_host: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
     CU(cudaSetDevice(h->device));
     const cm_model_dev &m = h->m;
-    const size_t nV = m.nV, nE = m.nE, Lc = m.n_lc, Bn = (size_t)B;
-    // device staging: masks + every requested output
-    struct Item { size_t bytes; size_t off; void *host; };
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    size_t off = 0;
-    auto item = [&](void *host, size_t bytes) { Item it{host ? bytes : 0, off, host}; if (host) off = al(off + bytes); return it; };
-    Item i_mask = item((void *)masks_host, Bn * m.mask_words * 4);
-    Item i_flag = item(o->flag, Bn * Lc), i_status = item(o->status, Bn * Lc);
-    Item i_nfree = item(o->n_free, Bn * 4), i_nfixed = item(o->n_fixed, Bn * 4);
-    Item i_dof = item(o->dof_map, Bn * 6 * nV * 4), i_ex = item(o->node_exists, Bn * nV);
-    Item i_U = item(o->U, Bn * Lc * 6 * nV * 8), i_R = item(o->Rf, Bn * Lc * 6 * nV * 8);
-    Item i_E = item(o->eR, Bn * Lc * nE * 12 * 8);
-    Item i_c = item(o->compliance, Bn * Lc * 8), i_mt = item(o->max_trans, Bn * Lc * 8);
-    Item i_mr = item(o->max_rot, Bn * Lc * 8), i_mp = item(o->min_pivot, Bn * 8);
-    Item i_pf = item(o->profile_flops, Bn * 8);
-    Item i_sg = item(o->sigma_max, Bn * Lc * nE * 8), i_ms = item(o->max_abs_sigma, Bn * Lc * 8);
-    if (off > h->stage_bytes) {
-        if (h->stage) cudaFree(h->stage);
-        h->stage = nullptr; h->stage_bytes = 0;
-        CU(cudaMalloc((void **)&h->stage, off));
-        h->stage_bytes = off;
-    }
+    const size_t Bn = (size_t)B;
     // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
     // (the driver is only asked about free memory when the workspace has to grow)
     const size_t per = h->L.per_subset;
@@ -620,20 +696,57 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
         CU(cudaMalloc((void **)&h->wsbuf, want));
         h->ws_bytes = want;
     }
+    WavePlan P;
+    { int rc = plan_waves(h, B, h->ws_bytes, &P); if (rc != CM_OK) return rc; }
+    // device staging: the masks of the batch, then CM_STAGE_SLOTS slots of one wave's outputs each
+    OutItem it[N_OUT];
+    out_items(h, o, it);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t mask_bytes = al(Bn * m.mask_words * 4);
+    size_t slot_bytes = 0;
+    for (int i = 0; i < N_OUT; ++i)
+        if (it[i].host) { it[i].off = slot_bytes; slot_bytes = al(slot_bytes + (size_t)P.wsize * it[i].stride); }
+    const int n_slots = (int)std::min<long long>(CM_STAGE_SLOTS, P.n_waves);
+    const size_t need = mask_bytes + (size_t)n_slots * slot_bytes;
+    if (need > h->stage_bytes) {
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr; h->stage_bytes = 0;
+        CU(cudaMalloc((void **)&h->stage, need));
+        h->stage_bytes = need;
+    }
     cudaStream_t st = h->stream;
-    CU(cudaMemcpyAsync(h->stage + i_mask.off, masks_host, i_mask.bytes, cudaMemcpyHostToDevice, st));
-    cm_solve_out od;
-    auto dp = [&](const Item &it) { return it.host ? (uint64_t)(h->stage + it.off) : (uint64_t)0; };
-    od.flag = dp(i_flag); od.status = dp(i_status); od.n_free = dp(i_nfree); od.n_fixed = dp(i_nfixed);
-    od.dof_map = dp(i_dof); od.node_exists = dp(i_ex); od.U = dp(i_U); od.Rf = dp(i_R); od.eR = dp(i_E);
-    od.compliance = dp(i_c); od.max_trans = dp(i_mt); od.max_rot = dp(i_mr); od.min_pivot = dp(i_mp);
-    od.profile_flops = dp(i_pf);
-    od.sigma_max = dp(i_sg); od.max_abs_sigma = dp(i_ms);
-    int rc = cm_solve_many(h, (uint64_t)(h->stage + i_mask.off), B, &od, (uint64_t)h->wsbuf, h->ws_bytes, (uint64_t)st);
-    if (rc != CM_OK) return rc;
-    const Item *outs[] = {&i_flag, &i_status, &i_nfree, &i_nfixed, &i_dof, &i_ex, &i_U, &i_R, &i_E, &i_c, &i_mt, &i_mr, &i_mp, &i_pf, &i_sg, &i_ms};
-    for (const Item *it : outs)
-        if (it->host) CU(cudaMemcpyAsync(it->host, h->stage + it->off, it->bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
+    char *slots = h->stage + mask_bytes;
+    auto before = [&](long long w, long long first, int, cudaStream_t ls, cm_out_dev &od) -> int {
+        const int s = (int)(w % n_slots);
+        if (w >= n_slots) CU(cudaStreamWaitEvent(ls, h->slot_free[s], 0));      // the slot's previous copies are done
+        // the kernels index their outputs by the subset's position in the batch: bias the slot pointers
+        char *base = slots + (size_t)s * slot_bytes;
+        auto bp = [&](int i) -> char * { return it[i].host ? base + it[i].off - (size_t)first * it[i].stride : nullptr; };
+        od.flag = (unsigned char *)bp(0); od.status = (unsigned char *)bp(1); od.n_free = (int *)bp(2); od.n_fixed = (int *)bp(3);
+        od.dof_map = (int *)bp(4); od.node_exists = (unsigned char *)bp(5); od.U = (double *)bp(6); od.Rf = (double *)bp(7);
+        od.eR = (double *)bp(8); od.compliance = (double *)bp(9); od.max_trans = (double *)bp(10); od.max_rot = (double *)bp(11);
+        od.min_pivot = (double *)bp(12); od.profile_flops = (double *)bp(13); od.sigma_max = (double *)bp(14);
+        od.max_abs_sigma = (double *)bp(15); od.profile_entries = (double *)bp(16); od.envelope_tiles = (double *)bp(17);
+        return CM_OK;
+    };
+    auto after = [&](long long w, long long first, int count, cudaStream_t ls) -> int {
+        const int s = (int)(w % n_slots);
+        char *base = slots + (size_t)s * slot_bytes;
+        CU(cudaEventRecord(h->slot_done[s], ls));
+        CU(cudaStreamWaitEvent(h->copy_stream, h->slot_done[s], 0));
+        for (int i = 0; i < N_OUT; ++i)
+            if (it[i].host)
+                CU(cudaMemcpyAsync(static_cast<char *>(it[i].host) + (size_t)first * it[i].stride, base + it[i].off,
+                                   (size_t)count * it[i].stride, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(cudaEventRecord(h->slot_free[s], h->copy_stream));
+        return CM_OK;
+    };
+    cm_out_dev od0{};
+    int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), B, od0, h->wsbuf, P, st, before, after);
+    if (rc != CM_OK) { cudaDeviceSynchronize(); return rc; }
+    CU(cudaEventRecord(h->copy_ev, h->copy_stream));
+    CU(cudaStreamWaitEvent(st, h->copy_ev, 0));
     CU(cudaStreamSynchronize(st));
     return CM_OK;
 }
@@ -642,8 +755,6 @@ int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t 
                               int64_t chunk, const volatile int32_t *ready) {
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: null argument");
     if (chunk <= 0) return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: chunk must be positive");
-    const cm_model_dev &m = h->m;
-    const size_t nV = m.nV, nE = m.nE, Lc = m.n_lc;
     int64_t k = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
         if (ready) {
@@ -654,14 +765,47 @@ int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t 
         }
         const int64_t n = std::min<int64_t>(chunk, B - b0);
         cm_solve_out_host c = *o;
-        auto adv = [&](auto *&p, size_t per_subset) { if (p) p += (size_t)b0 * per_subset; };
-        adv(c.flag, Lc); adv(c.status, Lc); adv(c.n_free, 1); adv(c.n_fixed, 1); adv(c.dof_map, 6 * nV);
-        adv(c.node_exists, nV); adv(c.U, Lc * 6 * nV); adv(c.Rf, Lc * 6 * nV); adv(c.eR, Lc * nE * 12);
-        adv(c.compliance, Lc); adv(c.max_trans, Lc); adv(c.max_rot, Lc); adv(c.min_pivot, 1);
-        adv(c.profile_flops, 1); adv(c.sigma_max, Lc * nE); adv(c.max_abs_sigma, Lc);
-        int rc = cm_solve_many_host(h, masks_host + (size_t)b0 * m.mask_words, n, &c);
+        out_advance(h, &c, b0);
+        int rc = cm_solve_many_host(h, masks_host + (size_t)b0 * h->m.mask_words, n, &c);
         if (rc != CM_OK) return rc;
     }
+    return CM_OK;
+}
+
+// One process, several GPUs: the batch is range-partitioned over the handles (one per device, same
+// model and load cases), one host thread per device drives its share through cm_solve_many_host, and
+// every thread's copies land at the subsets' final positions in the caller's arrays - that IS the
+// host gather of the partitioned solve; there is no collective.
+int cm_solve_many_host_multi(cm_handle *const *hs, int32_t n_handles, const uint32_t *masks_host, int64_t B,
+                             const cm_solve_out_host *o) {
+    if (!hs || n_handles < 1 || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host_multi: null argument");
+    for (int g = 0; g < n_handles; ++g) {
+        if (!hs[g]) return fail(CM_ERR_INVALID, "cm_solve_many_host_multi: null handle");
+        if (hs[g]->m.nE != hs[0]->m.nE || hs[g]->m.nV != hs[0]->m.nV || hs[g]->m.n_lc != hs[0]->m.n_lc)
+            return fail(CM_ERR_INVALID, "cm_solve_many_host_multi: handles describe different models or load cases");
+        for (int k = 0; k < g; ++k)
+            if (hs[k] == hs[g] || hs[k]->device == hs[g]->device)
+                return fail(CM_ERR_INVALID, "cm_solve_many_host_multi: one handle per device");
+    }
+    if (B <= 0) return CM_OK;
+    if (n_handles == 1) return cm_solve_many_host(hs[0], masks_host, B, o);
+    std::vector<int> rcs(n_handles, CM_OK);
+    std::vector<std::string> msgs(n_handles);
+    std::vector<std::thread> th;
+    const int64_t base = B / n_handles, extra = B % n_handles;
+    for (int g = 0; g < n_handles; ++g) {
+        const int64_t lo = g * base + std::min<int64_t>(g, extra), n = base + (g < extra ? 1 : 0);
+        if (n == 0) continue;
+        th.emplace_back([=, &rcs, &msgs]() {
+            cm_solve_out_host c = *o;
+            out_advance(hs[g], &c, lo);
+            rcs[g] = cm_solve_many_host(hs[g], masks_host + (size_t)lo * hs[g]->m.mask_words, n, &c);
+            if (rcs[g] != CM_OK) msgs[g] = g_err;        // g_err is thread-local: carry the message to the caller's thread
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < n_handles; ++g)
+        if (rcs[g] != CM_OK) return fail(rcs[g], "device " + std::to_string(hs[g]->device) + ": " + msgs[g]);
     return CM_OK;
 }
 

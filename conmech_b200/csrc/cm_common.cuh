@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
+#include <atomic>
 #include <vector>
 #include <string>
 #include "../../include/conmech_b200.h"
@@ -49,6 +50,7 @@ __host__ __device__ __forceinline__ int cm_mtile_off(int r, int k) {
 
 // Model tables on the device (all sizes fixed at cm_create).
 struct cm_model_dev {
+    int device, n_sm;      // CUDA device the tables live on and its SM count (fixed at cm_create)
     int nV, nE, nS, n_lc;
     int mask_words;
     int n_tile_rows_max;   // tile rows of the full structure
@@ -86,6 +88,23 @@ struct cm_model_dev {
     double trans_tol;
 };
 
+// Opt-in dynamic shared memory of a kernel.  The attribute is PER DEVICE (and per kernel), handles on
+// several devices may live in one process and be driven from several host threads: the cache is keyed
+// by device and atomic; setting the attribute twice is harmless.  Always requested (not only above
+// 48 KB): the no-opt-in limit counts static + dynamic shared memory.
+#define CM_MAX_DEVICES 64
+struct cm_smem_cache { std::atomic<size_t> bytes[CM_MAX_DEVICES]; };
+template <typename K>
+static inline cudaError_t cm_ensure_smem(K kernel, size_t bytes, cm_smem_cache &c, int device) {
+    // (the cache holds bytes + 1: 0 = never set on that device)
+    if (device >= 0 && device < CM_MAX_DEVICES && c.bytes[device].load(std::memory_order_acquire) > bytes)
+        return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (device >= 0 && device < CM_MAX_DEVICES) c.bytes[device].store(bytes + 1, std::memory_order_release);
+    return cudaSuccess;
+}
+
 // Per-subset workspace layout: byte offsets inside one subset's slab.
 struct cm_ws_layout {
     size_t per_subset;
@@ -111,6 +130,7 @@ struct cm_out_dev {
     int *n_free, *n_fixed, *dof_map;
     unsigned char *node_exists;
     double *U, *Rf, *eR, *compliance, *max_trans, *max_rot, *min_pivot, *profile_flops, *sigma_max, *max_abs_sigma;
+    double *profile_entries, *envelope_tiles;
 };
 
 // kernel launchers (one per stage); all enqueue on `st` and return the launch error

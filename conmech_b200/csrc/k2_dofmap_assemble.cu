@@ -81,7 +81,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_zero[i] = 0.0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // (ordered before the first bulk copy by the barriers below)
 #endif
-    __shared__ unsigned long long s_work;
+    __shared__ unsigned long long s_work, s_ent;
+    __shared__ int s_ntile;
     __shared__ double s_dred[K2_THREADS / 32];
 
     const int t = threadIdx.x, T = blockDim.x;
@@ -122,7 +123,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 
     for (int w = t; w < m.mask_words; w += T) s_mask[w] = gmask[w];
     if (t < 8) s_red[t] = 0;
-    if (t == 0) s_work = 0ull;
+    if (t == 0) { s_work = 0ull; s_ent = 0ull; s_ntile = 0; }
     __syncthreads();
 
     // ---- node existence, support status (numpy_stiffness.py:156-184)
@@ -155,6 +156,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         if (out.n_free) out.n_free[gs] = status == CM_ST_OK ? n_free : 0;
         if (out.n_fixed) out.n_fixed[gs] = status == CM_ST_OK ? n_fixed : 0;
         if (out.profile_flops && status != CM_ST_OK) out.profile_flops[gs] = 0.0;
+        if (out.profile_entries && status != CM_ST_OK) out.profile_entries[gs] = 0.0;
+        if (out.envelope_tiles && status != CM_ST_OK) out.envelope_tiles[gs] = 0.0;
         info[CM_INFO_STATUS] = status;
         info[CM_INFO_NS] = status == CM_ST_OK ? n_free : 0;
         info[CM_INFO_NT] = status == CM_ST_OK ? (n_free + CM_TILE - 1) / CM_TILE : 0;
@@ -253,11 +256,21 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         unsigned long long w = 0;      // algorithmic work: sum over rows of (row - first column)^2
         for (int i = 0; i < nf; ++i) { unsigned long long hgt = (unsigned long long)(base + i - cmin); w += hgt * hgt; }
         atomicAdd(&s_work, w);
+        if (out.profile_entries)       // sum over the node's rows of (row - first column + 1)
+            atomicAdd(&s_ent, (unsigned long long)nf * (unsigned long long)(base - cmin + 1) + (unsigned long long)(nf * (nf - 1) / 2));
     }
     __syncthreads();
     if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
     if (t == 0) info[CM_INFO_COST] = __float_as_int((float)s_work + 1.0f);      // > 0, monotone in the work
-    for (int I = t; I < NT; I += T) { kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1; }
+    for (int I = t; I < NT; I += T) {
+        kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1;
+        if (out.envelope_tiles) atomicAdd(&s_ntile, I - s_kfirst[I] + 1);
+    }
+    if (out.profile_entries || out.envelope_tiles) {
+        __syncthreads();
+        if (t == 0 && out.profile_entries) out.profile_entries[gs] = (double)s_ent;
+        if (t == 0 && out.envelope_tiles) out.envelope_tiles[gs] = (double)s_ntile;
+    }
     for (int i = t; i < NT * m.band_tiles; i += T) aflag_g[i] = s_aflag[i];
 
     // ---- diagonal of K_mm and the Jacobi scale (numpy_stiffness.py:283-290)
@@ -532,13 +545,10 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
     // tables in shared memory while five CTAs still fit an SM (the 1k-element frame needs 35 KB per CTA)
     const bool ts = base + 16 + (size_t)m.k2_blob_bytes <= 44 * 1024;
     const size_t smem = ts ? base + 16 + (size_t)m.k2_blob_bytes : base;
-    static size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[ts]) {
-        cudaError_t e = ts ? cudaFuncSetAttribute(k2_dofmap_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(k2_dofmap_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[ts] = smem;
-    }
+    static cm_smem_cache cache[2];
+    cudaError_t e = ts ? cm_ensure_smem(k2_dofmap_assemble<true>, smem, cache[1], m.device)
+                       : cm_ensure_smem(k2_dofmap_assemble<false>, smem, cache[0], m.device);
+    if (e != cudaSuccess) return e;
     if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out, ktilde_rowmajor);
     else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out, ktilde_rowmajor);
     return cudaGetLastError();

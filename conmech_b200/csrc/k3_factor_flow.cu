@@ -258,13 +258,10 @@ size_t flow_smem(const cm_model_dev &m, int nw) {
 
 template <int NW, bool PROF>
 static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
-    static size_t configured = 0;
+    static cm_smem_cache cache;
     const size_t smem = flow_smem(m, NW);
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k3_factor_flow<NW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = cm_ensure_smem(k3_factor_flow<NW, PROF>, smem, cache, m.device);
+    if (e != cudaSuccess) return e;
     k3_factor_flow<NW, PROF><<<count, NW * 32, smem, st>>>(m, L, ws);
     return cudaGetLastError();
 }
@@ -276,13 +273,7 @@ static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, cha
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                                   int config, int prof, cudaStream_t st) {
     if (config == 0) {
-        static int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (n_sm <= 0) n_sm = 148;
-        }
+        const int n_sm = m.n_sm > 0 ? m.n_sm : 148;
         config = 2;
         if (count <= 2 * n_sm && m.band_tiles > 8) config = 1;
         if (m.band_tiles > 16) config = 3;       // config 5 (band of 35 tiles), 512 subsets, largest first: 16 warps 142 ms, 8 warps 147 ms, 4 warps 209 ms

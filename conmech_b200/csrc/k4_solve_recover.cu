@@ -382,12 +382,9 @@ template <int NB>
 static cudaError_t launch_k4_xs(const cm_model_dev &m, const cm_ws_layout &L, char *ws, const uint32_t *masks,
                                 long long first, int count, const cm_out_dev &out, cudaStream_t st) {
     const size_t xs_bytes = (size_t)(NB + 1) * L.n_pad * sizeof(double);      // NB solutions and the pivots
-    static size_t configured = 0;
-    if (xs_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k4_solve_recover<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes);
-        if (e != cudaSuccess) return e;
-        configured = xs_bytes;
-    }
+    static cm_smem_cache cache;
+    cudaError_t e = cm_ensure_smem(k4_solve_recover<true, NB>, xs_bytes, cache, m.device);
+    if (e != cudaSuccess) return e;
     k4_solve_recover<true, NB><<<count, K4_THREADS, xs_bytes, st>>>(m, L, ws, masks, first, out);
     return cudaGetLastError();
 }

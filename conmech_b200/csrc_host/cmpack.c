@@ -3,7 +3,9 @@
  * The batched solve consumes several hundred thousand subsets per second and GPU; converting
  * Python lists through numpy costs ~70 ns per id, this loop ~5 ns.  An empty sequence means the
  * full structure (reference numpy_stiffness.py:230-231); an id outside [0, nE) raises IndexError
- * with the reference's message (stiffness_checker.py:178-181).
+ * with the reference's message (stiffness_checker.py:178-181); a repeated id raises ValueError.
+ * publish(ready, k, value): release-store into an int32 flag array (the hand-over of a packed chunk to
+ * the solving thread, cm_solve_many_host_chunks).
  *
  *   _cmpack.pack(list_of_ids, nE, out)      out: writable C-contiguous buffer of B*ceil(nE/32) uint32
  */
@@ -17,7 +19,15 @@ static int set_bit(uint32_t *row, Py_ssize_t e, Py_ssize_t nE) {
         PyErr_SetString(PyExc_IndexError, "element id not within range!");
         return -1;
     }
-    row[e >> 5] |= (uint32_t)1u << (e & 31);
+    const uint32_t bit = (uint32_t)1u << (e & 31);
+    if (row[e >> 5] & bit) {
+        /* The reference assembles a repeated id twice (numpy_stiffness_assembly.py:371-388 has no
+         * de-duplication: the element's stiffness is double counted).  A bit mask is a set and cannot
+         * carry that; rather than silently solving a different structure, reject the input. */
+        PyErr_Format(PyExc_ValueError, "duplicate element id %zd in a subset (the reference would double count it)", e);
+        return -1;
+    }
+    row[e >> 5] |= bit;
     return 0;
 }
 
@@ -135,7 +145,27 @@ static PyObject *pack_csr(PyObject *self, PyObject *args) {
     Py_RETURN_NONE;
 }
 
+/* publish(flags, k, value): flags[k] = value with release ordering - everything this thread wrote
+ * before (the chunk's masks) is visible to a thread that acquire-loads the flag, on any host ISA. */
+static PyObject *publish(PyObject *self, PyObject *args) {
+    PyObject *fobj;
+    Py_ssize_t k;
+    int value;
+    if (!PyArg_ParseTuple(args, "Oni", &fobj, &k, &value)) return NULL;
+    Py_buffer fb;
+    if (PyObject_GetBuffer(fobj, &fb, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) return NULL;
+    if (fb.itemsize != 4 || k < 0 || k >= fb.len / 4) {
+        PyBuffer_Release(&fb);
+        PyErr_SetString(PyExc_ValueError, "publish: int32 flag array and an index inside it");
+        return NULL;
+    }
+    __atomic_store_n((int32_t *)fb.buf + k, (int32_t)value, __ATOMIC_RELEASE);
+    PyBuffer_Release(&fb);
+    Py_RETURN_NONE;
+}
+
 static PyMethodDef methods[] = {
+    {"publish", publish, METH_VARARGS, "publish(flags, k, value): release-store flags[k] = value (int32 array)"},
     {"pack_csr", pack_csr, METH_VARARGS, "pack_csr(flat_ids, offsets, nE, out): CSR id arrays -> uint32 subset bit masks"},
     {"pack", pack, METH_VARARGS, "pack(list_of_ids, nE, out): element-id sequences -> uint32 subset bit masks"},
     {NULL, NULL, 0, NULL}};

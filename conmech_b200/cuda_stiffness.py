@@ -9,7 +9,10 @@ kernels reached through the C ABI of ``include/conmech_b200.h``; this module onl
 There is no CPU fallback: without the CUDA library or a CUDA device the constructor raises.
 
 Beyond the reference interface it adds the batched entry points ``solve_many`` (host
-buffers) and ``solve_many_device`` (torch CUDA tensors, caller's stream).
+buffers) and ``solve_many_device`` (torch CUDA tensors, caller's stream).  With
+``devices=[0, 1, ...]`` one process drives several GPUs: the model tables are replicated, a batch
+is range-partitioned over the devices (one host thread each, inside the library) and the results
+land directly in the caller's arrays - no collective.
 """
 import ctypes as C
 import os
@@ -18,7 +21,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import OUT_FIELDS, ST_OK, ST_NO_SUPPORT, ST_NO_FIXED_DOF, ST_SINGULAR, ST_ZERO_LOAD
-from .masks import pack_masks
+from .masks import pack_masks, as_mask_matrix, publish
 from .stiffness_base import StiffnessBase
 
 DOUBLE_EPS = 1e-14
@@ -28,7 +31,8 @@ _OUT_DTYPE = {'flag': np.uint8, 'status': np.uint8, 'n_free': np.int32, 'n_fixed
               'dof_map': np.int32, 'node_exists': np.uint8, 'U': np.float64, 'Rf': np.float64,
               'eR': np.float64, 'compliance': np.float64, 'max_trans': np.float64,
               'max_rot': np.float64, 'min_pivot': np.float64, 'profile_flops': np.float64,
-              'sigma_max': np.float64, 'max_abs_sigma': np.float64}
+              'sigma_max': np.float64, 'max_abs_sigma': np.float64, 'profile_entries': np.float64,
+              'envelope_tiles': np.float64}
 
 
 def _ptr(a):
@@ -36,13 +40,20 @@ def _ptr(a):
 
 
 class CudaStiffness(StiffnessBase):
-    def __init__(self, model, verbose=False, output_json=False, device=None):
+    def __init__(self, model, verbose=False, output_json=False, device=None, devices=None):
         super(CudaStiffness, self).__init__(model, verbose, output_json)
         self._lib = _capi.load()
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            if len(devices) == 0 or len(set(devices)) != len(devices):
+                raise ValueError('devices must be a non-empty list of distinct CUDA device ordinals')
+            device = devices[0]
         if device is None:
             device = int(os.environ.get('LOCAL_RANK', 0)) if 'LOCAL_RANK' in os.environ else 0
         self._device = int(device)
+        self._devices = devices or [self._device]
         self._handle = C.c_void_p()
+        self._handles = []                     # one per device; _handle is the first
 
         self._trans_tol = 1e-3
         self._rot_tol = np.pi / 180 * 3
@@ -72,16 +83,23 @@ class CudaStiffness(StiffnessBase):
 
         self._v_id_map = np.arange(6 * nV, dtype=int).reshape(nV, 6)         # numpy_stiffness.py:563-565
         self._flatten_and_create(model)
-        self._lib.cm_set_tol(self._handle, self._trans_tol, self._rot_tol)
+        for h in self._handles:
+            self._lib.cm_set_tol(h, self._trans_tol, self._rot_tol)
+
+    def close(self):
+        """Destroy the device handles (model tables, workspace, staging) now instead of at collection."""
+        self.__del__()
+        self._ws_cache = {}
 
     def __del__(self):
-        h = getattr(self, '_handle', None)
-        if h is not None and h.value:
-            try:
-                self._lib.cm_destroy(h)
-            except Exception:
-                pass
-            self._handle = C.c_void_p()
+        for h in getattr(self, '_handles', []):
+            if h is not None and h.value:
+                try:
+                    self._lib.cm_destroy(h)
+                except Exception:
+                    pass
+        self._handles = []
+        self._handle = C.c_void_p()
 
     # ------------------------------------------------------------------ model flattening
     @property
@@ -131,11 +149,15 @@ class CudaStiffness(StiffnessBase):
         self._sup_node, self._sup_cond = sup_node, sup_cond
         self._id_map = np.hstack([self._v_id_map[conn[:, 0]], self._v_id_map[conn[:, 1]]])   # :567-570
 
-        desc = _capi.ModelDesc(nV, nE, len(sup_node), self._device,
-                               xyz.ctypes.data_as(_capi.c_double_p), conn.ctypes.data_as(_capi.c_int32_p),
-                               props.ctypes.data_as(_capi.c_double_p), cr.ctypes.data_as(_capi.c_double_p),
-                               sup_node.ctypes.data_as(_capi.c_int32_p), sup_cond.ctypes.data_as(_capi.c_uint8_p))
-        _capi.check(self._lib.cm_create(C.byref(desc), C.byref(self._handle)))
+        for dev in self._devices:
+            desc = _capi.ModelDesc(nV, nE, len(sup_node), dev,
+                                   xyz.ctypes.data_as(_capi.c_double_p), conn.ctypes.data_as(_capi.c_int32_p),
+                                   props.ctypes.data_as(_capi.c_double_p), cr.ctypes.data_as(_capi.c_double_p),
+                                   sup_node.ctypes.data_as(_capi.c_int32_p), sup_cond.ctypes.data_as(_capi.c_uint8_p))
+            h = C.c_void_p()
+            _capi.check(self._lib.cm_create(C.byref(desc), C.byref(h)))
+            self._handles.append(h)
+        self._handle = self._handles[0]
         self._info = _capi.ModelInfo()
         _capi.check(self._lib.cm_get_info(self._handle, C.byref(self._info)))
 
@@ -221,8 +243,9 @@ class CudaStiffness(StiffnessBase):
             on[k] = 1 if sw else 0
             gd[k] = gdir
         any_udl = bool(has.any())
-        _capi.check(self._lib.cm_set_loadcases(self._handle, n_lc, _ptr(nodal), _ptr(w) if any_udl else None,
-                                               _ptr(has) if any_udl else None, _ptr(on), _ptr(gd)))
+        for h in self._handles:
+            _capi.check(self._lib.cm_set_loadcases(h, n_lc, _ptr(nodal), _ptr(w) if any_udl else None,
+                                                   _ptr(has) if any_udl else None, _ptr(on), _ptr(gd)))
         self._n_lc = n_lc
         self._loads_dirty = False
 
@@ -230,7 +253,8 @@ class CudaStiffness(StiffnessBase):
     def set_nodal_displacement_tol(self, transl_tol, rot_tol):
         self._trans_tol = transl_tol
         self._rot_tol = rot_tol
-        self._lib.cm_set_tol(self._handle, float(transl_tol), float(rot_tol))
+        for h in self._handles:
+            self._lib.cm_set_tol(h, float(transl_tol), float(rot_tol))
 
     def get_nodal_deformation_tol(self):
         return (self._trans_tol, self._rot_tol)
@@ -239,21 +263,21 @@ class CudaStiffness(StiffnessBase):
         """1 = FP64 tensor-core factorisation, CTA size chosen per launch (default); 2 / 3 / 6 = pinned to
         4 / 8 / 16-warp CTAs; 4 / 5 = 4 / 8-warp CTAs with activity cycle counters; 0 = scalar
         validation variant."""
-        _capi.check(self._lib.cm_set_variant(self._handle, int(variant)))
+        for h in self._handles:
+            _capi.check(self._lib.cm_set_variant(h, int(variant)))
 
     # ------------------------------------------------------------------ batched solves
     def _as_masks(self, subsets):
-        if isinstance(subsets, np.ndarray) and subsets.dtype == np.uint32 and subsets.ndim == 2:
-            assert subsets.shape[1] == self._info.mask_words
-            return np.ascontiguousarray(subsets)
-        return pack_masks(subsets, self.nE)
+        m = as_mask_matrix(subsets, self._info.mask_words)
+        return m if m is not None else pack_masks(subsets, self.nE)
 
     def _out_shapes(self, B):
         nV, nE, L = self.nV, self.nE, self._n_lc
         return {'flag': (B, L), 'status': (B, L), 'n_free': (B,), 'n_fixed': (B,), 'dof_map': (B, 6 * nV),
                 'node_exists': (B, nV), 'U': (B, L, 6 * nV), 'Rf': (B, L, 6 * nV), 'eR': (B, L, nE, 12),
                 'compliance': (B, L), 'max_trans': (B, L), 'max_rot': (B, L), 'min_pivot': (B,),
-                'profile_flops': (B,), 'sigma_max': (B, L, nE), 'max_abs_sigma': (B, L)}
+                'profile_flops': (B,), 'sigma_max': (B, L, nE), 'max_abs_sigma': (B, L),
+                'profile_entries': (B,), 'envelope_tiles': (B,)}
 
     def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):
         """Solve B element subsets (list of id lists, [] = full structure, or a (B, words)
@@ -262,8 +286,11 @@ class CudaStiffness(StiffnessBase):
         in include/conmech_b200.h for names and shapes.  ``out`` may hold preallocated
         (e.g. pinned) arrays to write into."""
         self._push_loads()
-        prepacked = isinstance(subsets, np.ndarray) and subsets.dtype == np.uint32 and subsets.ndim == 2
-        B = len(subsets)
+        masks0 = as_mask_matrix(subsets, self._info.mask_words)
+        prepacked = masks0 is not None
+        if not prepacked and not isinstance(subsets, (list, tuple)):
+            subsets = list(subsets)            # generators, sets of tuples, id-row arrays
+        B = len(masks0) if prepacked else len(subsets)
         shapes = self._out_shapes(B)
         res = {}
         for name in OUT_FIELDS:
@@ -272,49 +299,74 @@ class CudaStiffness(StiffnessBase):
                 assert a.flags['C_CONTIGUOUS'] and a.dtype == _OUT_DTYPE[name] and a.size == int(np.prod(shapes[name]))
                 res[name] = a.reshape(shapes[name])
 
-        def run(masks, b0, b1):
+        def out_struct(b0=0):
             oh = _capi.SolveOutHost()
             for name in OUT_FIELDS:
-                setattr(oh, name, res[name][b0:b1].ctypes.data if name in res else None)
-            _capi.check(self._lib.cm_solve_many_host(self._handle, _ptr(masks), b1 - b0, C.byref(oh)))
+                setattr(oh, name, res[name][b0:].ctypes.data if name in res and b0 < B else None)
+            return oh
 
-        if not prepacked and not isinstance(subsets, (list, tuple)):
-            subsets = list(subsets)
+        if B == 0:
+            return res
         if prepacked or B < 2 * self.PIPELINE_CHUNK:
-            run(self._as_masks(subsets), 0, B)
+            masks = masks0 if prepacked else pack_masks(subsets, self.nE)
+            oh = out_struct()
+            if len(self._handles) > 1:
+                hs = (C.c_void_p * len(self._handles))(*[h.value for h in self._handles])
+                _capi.check(self._lib.cm_solve_many_host_multi(hs, len(self._handles), _ptr(masks), B, C.byref(oh)))
+            else:
+                _capi.check(self._lib.cm_solve_many_host(self._handle, _ptr(masks), B, C.byref(oh)))
             return res
         # Python id lists, large batch: packing (this thread, GIL held, ~5 ns per id) is pipelined with
-        # the GPU work chunk by chunk.  ONE worker thread makes ONE call into the library for the whole
-        # batch (cm_solve_many_host_chunks); inside it waits per chunk - without the GIL - for the
-        # 'ready' flag this thread sets after writing the chunk's masks.
+        # the GPU work chunk by chunk.  ONE worker thread per device makes ONE call into the library for
+        # its share of the batch (cm_solve_many_host_chunks); inside it waits per chunk - without the
+        # GIL - for the 'ready' flag this thread release-stores after writing the chunk's masks.
         import threading
-        n_chunks = min(8, B // self.PIPELINE_CHUNK)
-        step = -(-B // n_chunks)
-        n_chunks = -(-B // step)
+        from .sharding import shard_range
+        G = len(self._handles)
         masks = np.empty((B, self._info.mask_words), dtype=np.uint32)
-        ready = np.zeros(n_chunks, dtype=np.int32)
-        oh = _capi.SolveOutHost()
-        for name in OUT_FIELDS:
-            setattr(oh, name, res[name].ctypes.data if name in res else None)
-        rc = []
+        jobs = []                              # (handle, lo, hi, step, ready flags)
+        for g, h in enumerate(self._handles):
+            lo, hi = shard_range(B, G, g)
+            if hi == lo:
+                continue
+            n_chunks = max(1, min(8, (hi - lo) // self.PIPELINE_CHUNK))
+            step = -(-(hi - lo) // n_chunks)
+            n_chunks = -(-(hi - lo) // step)
+            jobs.append((h, lo, hi, step, np.zeros(n_chunks, dtype=np.int32)))
+        results = [None] * len(jobs)
 
-        def worker():
-            rc.append(self._lib.cm_solve_many_host_chunks(self._handle, _ptr(masks), B, C.byref(oh), step,
-                                                          ready.ctypes.data))
+        def worker(j):
+            h, lo, hi, step, ready = jobs[j]
+            oh = out_struct(lo)
+            rc = self._lib.cm_solve_many_host_chunks(h, masks[lo:].ctypes.data, hi - lo, C.byref(oh), step,
+                                                     ready.ctypes.data)
+            # the library's error message is thread-local: read it on THIS thread
+            results[j] = (rc, self._lib.cm_last_error().decode() if rc != _capi.CM_OK else '')
 
-        th = threading.Thread(target=worker, name='conmech-b200-solve', daemon=True)
-        th.start()
+        threads = [threading.Thread(target=worker, args=(j,), name='conmech-b200-solve-{}'.format(j), daemon=True)
+                   for j in range(len(jobs))]
+        for th in threads:
+            th.start()
         try:
-            for k in range(n_chunks):
-                b0, b1 = k * step, min(B, (k + 1) * step)
+            # chunks are packed round-robin over the devices so that every device starts early
+            order = sorted((k, j) for j, job in enumerate(jobs) for k in range(len(job[4])))
+            for k, j in order:
+                h, lo, hi, step, ready = jobs[j]
+                b0, b1 = lo + k * step, min(hi, lo + (k + 1) * step)
                 pack_masks(subsets[b0:b1], self.nE, out=masks[b0:b1])
-                ready[k] = 1
+                publish(ready, k, 1)
         except BaseException:
-            ready[ready == 0] = -1          # cancel the chunks that were not handed over
-            th.join()
+            for job in jobs:                   # cancel the chunks that were not handed over
+                for k in np.flatnonzero(job[4] == 0):
+                    publish(job[4], int(k), -1)
+            for th in threads:
+                th.join()
             raise
-        th.join()
-        _capi.check(rc[0])
+        for th in threads:
+            th.join()
+        for rc, msg in results:
+            if rc != _capi.CM_OK:
+                raise _capi.CmError('conmech_b200 error {}: {}'.format(rc, msg))
         return res
 
     def solve_many_csr(self, flat_ids, offsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):

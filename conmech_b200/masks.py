@@ -30,6 +30,9 @@ def ids_to_mask(ids, nE):
 def pack_masks(list_of_ids, nE, out=None):
     """(B, ceil(nE/32)) uint32 masks for a list of id lists.  An empty list means the full
     structure (reference ``numpy_stiffness.py:230-231``).  Ids out of range raise IndexError.
+    A repeated id inside one subset raises ValueError: the reference assembles such an element
+    twice (``numpy_stiffness_assembly.py:371-388``, no de-duplication), a bit mask is a set and
+    cannot express that, and silently solving a different structure is not an option.
 
     Vectorised over the whole batch (one flat id array, one scatter, one packbits): the batched
     solve consumes several hundred thousand subsets per second and GPU, a Python loop over the
@@ -60,6 +63,8 @@ def pack_masks(list_of_ids, nE, out=None):
     bits = np.zeros((B, W * 32), dtype=np.uint8)
     if total:
         bits.reshape(-1)[np.repeat(np.arange(B, dtype=np.int64) * (W * 32), lens) + flat] = 1
+        if int(bits.sum()) != total:
+            raise ValueError('duplicate element id in a subset (the reference would double count it)')
     if (lens == 0).any():
         bits[lens == 0, :nE] = 1
     packed = np.packbits(bits.reshape(B, W, 32), axis=2, bitorder='little')      # (B, W, 4) bytes
@@ -90,6 +95,28 @@ def pack_masks_csr(flat_ids, offsets, nE, out=None):
         out[...] = dst
         return out
     return dst
+
+
+def publish(flags, k, value=1):
+    """``flags[k] = value`` with release ordering (int32 array shared with a native consumer thread)."""
+    native = _native_packer()
+    if native is not None and hasattr(native, 'publish'):
+        native.publish(flags, int(k), int(value))
+    else:
+        flags[k] = value
+
+
+def as_mask_matrix(a, mask_words):
+    """A 2-D array of 4-byte integers with ``mask_words`` columns is a pre-packed mask matrix
+    (uint32, or int32 - what torch tensors hold); returns it as C-contiguous uint32.  A 2-D array of
+    4-byte integers with another column count is ambiguous (masks of another model? rows of ids?) and
+    raises; anything else (lists, int64 id rows) returns None = "a sequence of id sequences"."""
+    if not isinstance(a, np.ndarray) or a.ndim != 2 or a.dtype.kind not in 'iu' or a.dtype.itemsize != 4:
+        return None
+    if a.shape[1] == mask_words:
+        return np.ascontiguousarray(a).view(np.uint32)
+    raise ValueError('2-D {} array of shape {} is not a mask matrix of this model ((B, {}) uint32/int32); pass id rows '
+                     'as int64 or as lists'.format(a.dtype, a.shape, mask_words))
 
 
 def mask_to_ids(mask, nE):

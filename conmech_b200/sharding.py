@@ -28,7 +28,11 @@ def solve_many_sharded(engine, masks, want=('flag', 'status', 'max_trans', 'comp
     gather moves B*n_lc bytes per output, it is not on the solve path)."""
     import torch
     import torch.distributed as dist
-    masks = np.ascontiguousarray(masks)
+    from .masks import as_mask_matrix
+    m = as_mask_matrix(np.asarray(masks), engine.info['mask_words'])
+    if m is None:
+        raise ValueError('solve_many_sharded takes a (B, mask_words) uint32/int32 mask matrix')
+    masks = m
     B = masks.shape[0]
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -38,11 +42,31 @@ def solve_many_sharded(engine, masks, want=('flag', 'status', 'max_trans', 'comp
     local = engine.solve_many(masks[lo:hi], want=want) if hi > lo else {}
     if world == 1 or not gather:
         return local
+    # final gather: one all_gather per output over equally padded tensors (shares differ by at most one
+    # subset); NCCL ranks gather on their device, gloo ranks on the host.  Not on the solve path.
+    use_cuda = dist.get_backend(group) == 'nccl'
+    n_max = -(-B // world)
     out = {}
     for name in want:
-        mine = local.get(name)
-        parts = [None] * world
-        dist.all_gather_object(parts, None if mine is None else np.ascontiguousarray(mine), group=group)
-        parts = [p for p in parts if p is not None and len(p)]
-        out[name] = np.concatenate(parts, axis=0) if parts else np.zeros((0,))
+        mine = np.ascontiguousarray(local[name]) if hi > lo else None
+        # every rank needs the trailing shape and dtype: rank 0 always has a non-empty share when B > 0
+        meta = [None]
+        if rank == 0:
+            meta = [(mine.shape[1:], mine.dtype.str)]
+        dist.broadcast_object_list(meta, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        tail, dt = meta[0]
+        buf = np.zeros((n_max,) + tuple(tail), dtype=np.dtype(dt))
+        if mine is not None:
+            buf[:hi - lo] = mine
+        tns = torch.from_numpy(buf.view(np.uint8).reshape(-1))
+        if use_cuda:
+            tns = tns.cuda()
+        parts = [torch.empty_like(tns) for _ in range(world)]
+        dist.all_gather(parts, tns, group=group)
+        rows = []
+        for r, p in enumerate(parts):
+            rlo, rhi = shard_range(B, world, r)
+            a = p.cpu().numpy().view(np.dtype(dt)).reshape((n_max,) + tuple(tail))
+            rows.append(a[:rhi - rlo])
+        out[name] = np.concatenate(rows, axis=0)
     return out

@@ -22,9 +22,11 @@ DEFAULT_ENGINE = 'cuda'
 
 
 class StiffnessChecker(object):
-    def __init__(self, model, verbose=False, checker_engine=DEFAULT_ENGINE, device=None):
+    def __init__(self, model, verbose=False, checker_engine=DEFAULT_ENGINE, device=None, devices=None):
+        """``device``: CUDA ordinal (default: LOCAL_RANK or 0).  ``devices=[0, 1, ...]``: one process
+        drives several GPUs - ``solve_many`` range-partitions every batch over them."""
         if checker_engine == 'cuda':
-            engine = CudaStiffness(model, verbose=verbose, device=device)
+            engine = CudaStiffness(model, verbose=verbose, device=device, devices=devices)
         else:
             raise NotImplementedError('Engine not exist: {}'.format(checker_engine))
         self._sc_ins = engine
@@ -34,9 +36,9 @@ class StiffnessChecker(object):
             raise RuntimeError('there needs to be at least one support (fixed) vertex in the model!')
 
     @classmethod
-    def from_json(cls, json_file_path=None, verbose=False, checker_engine=DEFAULT_ENGINE, device=None):
+    def from_json(cls, json_file_path=None, verbose=False, checker_engine=DEFAULT_ENGINE, device=None, devices=None):
         return cls(Model.from_json(json_file_path, verbose=verbose), verbose=verbose,
-                   checker_engine=checker_engine, device=device)
+                   checker_engine=checker_engine, device=device, devices=devices)
 
     # ---------------------------------------------------------------- properties
     @property

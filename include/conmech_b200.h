@@ -19,8 +19,8 @@
  *     Tensor.data_ptr() returns); "host" pointers are ordinary pointers.
  *   - the caller owns every input/output buffer and the workspace; the library owns only the
  *     opaque handle (model tables, load tables, small scratch) on the device it was created on.
- *   - one handle per device; a handle is not thread-safe; different handles may be used
- *     concurrently.
+ *   - one handle per device; a handle is not thread-safe; different handles (on the same or on
+ *     different devices) may be used concurrently from different host threads.
  *   - all floating point is IEEE fp64; indices are int32; DOF numbering is 6*node + {0..5}
  *     (numpy_stiffness.py:563-570).
  */
@@ -132,13 +132,17 @@ typedef struct cm_solve_out {
                           /*                get_sigma_max_per_element (stiffness_checker.py:330-365: solid */
                           /*                round sections, both section moduli from Iy); 0 when absent    */
     uint64_t max_abs_sigma; /* f64 [B*L]    max over the subset's elements of |sigma_max|                  */
+    uint64_t profile_entries; /* f64 [B]    sum_j (h_j + 1): entries of the scalar profile (lower, with diagonal)  */
+                          /*                of the subset's K_mm; 8x this = S_K of SURVEY.md section 8d (profile)  */
+    uint64_t envelope_tiles; /* f64 [B]     32x32 tiles of the block-band envelope that is factorised (8 KB each)  */
 } cm_solve_out;
 
 /* Factorisation kernel variant: 1 (default) = FP64 tensor-core block-band LDL^T, dataflow
  * kernel (csrc/k3_factor_flow.cu), CTA size chosen per launch (4 warps x 4 CTAs/SM when the
  * launch fills the GPU, 8 or 16 warps per subset for few subsets of a wide band); 2 / 3 / 6 = the
  * same kernel pinned to 4 / 8 / 16-warp CTAs; 4 / 5 = 4 / 8-warp CTAs instrumented with
- * per-activity cycle counters; 0 = scalar validation variant of the same algorithm
+ * per-activity cycle counters; 7 / 8 / 9 = 2 / 3 / 1-warp CTAs (timing experiments, parity-clean);
+ * 0 = scalar validation variant of the same algorithm
  * (csrc/k3_factor.cu; slow, used by the parity tests to cross-check the tensor-core path). */
 int cm_set_variant(cm_handle *h, int32_t variant);
 
@@ -157,9 +161,12 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t subsets_in_flight);
 int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *out,
                   uint64_t workspace_dev, size_t workspace_bytes, uint64_t stream);
 
-/* Same, with HOST buffers: masks and every non-NULL output are host arrays (pinned or not).
- * The call copies masks host->device, runs the kernels, copies the requested outputs back and
- * returns when they are complete.  It manages its own device staging and workspace. */
+/* Same, with HOST buffers: masks and every non-NULL output are host arrays (pinned memory lets
+ * the copies overlap the kernels; pageable memory works, serialised by the driver).  The call
+ * copies the masks host->device, runs the kernels wave by wave and drains every finished wave's
+ * outputs to the caller's arrays on a copy stream while the next waves compute; it returns when
+ * all outputs are complete.  It manages its own workspace and a bounded device staging ring
+ * (a few waves of outputs, not the whole batch). */
 typedef struct cm_solve_out_host {
     uint8_t *flag;
     uint8_t *status;
@@ -177,6 +184,8 @@ typedef struct cm_solve_out_host {
     double *profile_flops;
     double *sigma_max;
     double *max_abs_sigma;
+    double *profile_entries;
+    double *envelope_tiles;
 } cm_solve_out_host;
 
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,
@@ -191,6 +200,16 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,
  * are written at the subset's position in the full arrays, exactly as cm_solve_many_host does. */
 int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t B,
                               const cm_solve_out_host *out, int64_t chunk, const volatile int32_t *ready);
+
+/* One process, several GPUs (reference: none - the reference is single-threaded,
+ * stiffness_base.py:8-155): `handles` are n_handles handles created from the
+ * SAME model on DIFFERENT devices, with the same load cases and tolerances set on each.  The batch is
+ * range-partitioned over them (handle g gets the g-th contiguous share, the first B % n_handles
+ * shares one subset longer), one host thread per device runs its share like cm_solve_many_host, and
+ * every result is written at the subset's position in the caller's arrays - the host gather of the
+ * partitioned solve; no collective, no second copy.  Returns the first failing device's error. */
+int cm_solve_many_host_multi(cm_handle *const *handles, int32_t n_handles, const uint32_t *masks_host,
+                             int64_t B, const cm_solve_out_host *out);
 
 /* Counters since the last cm_reset_counters: kernels launched by this library, and device
  * milliseconds (CUDA events on the launching stream) per stage of the last cm_solve_many*

@@ -1,57 +1,129 @@
-"""CPU timing of the oracle (test/bench infrastructure only): the reference algorithm restated
-in oracle/frame_oracle.py, run on the host cores over a bounded sample of a workload.
+"""CPU timing of the reference's path (test/bench infrastructure only) on the host cores over a
+bounded sample of a workload.  Used by bench.py for the ``cpu_baseline`` object, the CPU rates of
+``other_configs`` and for ``--impl reference``.
 
-Used by bench.py for the ``cpu_baseline`` object and for ``--impl reference``.  The reference
-itself (a Python package under /root/reference) cannot travel to the GPU box, so the oracle
-port stands in for it (kind = "port").  The port vectorises the reference's interpreted
-triple loop in ``assemble_global_stiffness_matrix`` (numpy_stiffness_assembly.py:379-387) and its
-per-DOF Python loops; everything else (scipy csc products, SuperLU with the same options) is
-the same call sequence, so the port is FASTER than the reference it stands for - the reported
-CPU baseline is conservative.  DESIGN.md records the ratio measured in the authoring container.
+kind = "reference": the UNMODIFIED reference, ``StiffnessChecker(model, checker_engine="numpy")
+.solve(ids)`` (numpy_stiffness.py:228-397), imported from the git-ignored install under
+``baseline/_ref`` that ``gpurun`` ships to the GPU box (oracle/ref_bridge.py).
+kind = "port": the oracle restatement (oracle/frame_oracle.py) - used when the reference install is
+absent, and always reported beside the reference.  The port vectorises the reference's
+interpreted triple loop in ``assemble_global_stiffness_matrix`` (numpy_stiffness_assembly.py:
+379-387) and its per-DOF Python loops; everything else (scipy csc products, SuperLU with the same
+options) is the same call sequence, so the port is about 2x FASTER than the reference.
+
+A workload is a dict (the same definitions bench.py drives the GPU with):
+    {'model': ('grid', nx, ny, nz, joints) | ('json', file name under tests/golden/models),
+     'loads': 'gravity' | 'config4',
+     'subsets': 'connected' | 'connected:lo:hi' | 'heightfield' | 'full' | 'bfs_prefixes',
+     'trans_tol': float}
+One "solve" = one (subset, load case); the reference solves one load case per call with a fresh
+checker per load case.
 """
 import os
 import time
 
 _STATE = {}
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CONFIG3 = {'model': ('grid', 7, 7, 8, False), 'loads': 'gravity', 'subsets': 'connected', 'trans_tol': 1e-3}
 
 
-def _init_worker(grid, trans_tol):
+def reference_available():
+    from oracle import ref_bridge
+    return ref_bridge.available()
+
+
+def build_workload(spec):
+    """(model, [LoadCase], subset function seed -> ids)"""
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad, Model
+    m = spec['model']
+    if m[0] == 'grid':
+        model = syn.grid_frame(m[1], m[2], m[3], joints=bool(m[4]))
+    else:
+        model = Model.from_json(os.path.join(REPO, 'tests', 'golden', 'models', m[1]))
+    if spec['loads'] == 'config4':
+        lcs = syn.config4_loadcases(model)
+    else:
+        lcs = [LoadCase(gravity_load=GravityLoad([0, 0, -1]))]
+    kind = spec['subsets']
+    if kind.startswith('connected'):
+        parts = kind.split(':')
+        lo, hi = (float(parts[1]), float(parts[2])) if len(parts) == 3 else (0.2, 0.9)
+        sub = lambda s: syn.connected_subset(model, s, lo=lo, hi=hi)
+    elif kind == 'heightfield':
+        sub = lambda s: syn.heightfield_subset(model, m[1], m[2], m[3], seed=s)
+    elif kind == 'bfs_prefixes':
+        order = syn.bfs_sequence(model)
+        sub = lambda s: order[:(s % len(order)) + 1]
+    else:
+        sub = lambda s: []
+    return model, lcs, sub
+
+
+def _init_worker(spec, kind='port'):
+    """One checker per (worker process, load case): the oracle port, or the reference facade on its
+    numpy engine."""
     import warnings
     warnings.simplefilter('ignore')
-    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
-    from oracle.frame_oracle import FrameOracle
-    model = syn.grid_frame(*grid)
-    orc = FrameOracle(model)
-    orc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
-    orc.set_nodal_displacement_tol(trans_tol)
-    _STATE['orc'] = orc
-    _STATE['model'] = model
-    _STATE['syn'] = syn
+    try:                                  # one BLAS/OpenMP thread per worker: the pool owns the cores
+        from threadpoolctl import threadpool_limits
+        _STATE['tp'] = threadpool_limits(1)
+    except Exception:
+        pass
+    model, lcs, sub = build_workload(spec)
+    solvers = []
+    for lc in lcs:
+        if kind == 'reference':
+            from oracle import ref_bridge
+            sc = ref_bridge.make_ref_checker(model, lc, spec['trans_tol'])
+
+            def solve(ids, sc=sc):                              # the reference's public call, stock code path
+                try:
+                    return bool(sc.solve(ids))
+                except TypeError:                               # bare False from compute_dof_permutation
+                    return False
+        else:
+            from oracle.frame_oracle import FrameOracle
+            orc = FrameOracle(model)
+            orc.set_loads(lc)
+            orc.set_nodal_displacement_tol(spec['trans_tol'])
+
+            def solve(ids, orc=orc):
+                return orc.solve(ids).success
+        solvers.append(solve)
+    _STATE['solvers'] = solvers
+    _STATE['sub'] = sub
 
 
 def _solve_seeds(seeds):
-    orc, model, syn = _STATE['orc'], _STATE['model'], _STATE['syn']
-    subsets = [syn.connected_subset(model, s) for s in seeds]      # not timed
-    t0 = time.perf_counter()
+    import contextlib
+    import io
+    solvers, sub = _STATE['solvers'], _STATE['sub']
+    subsets = [sub(s) for s in seeds]                              # not timed
     n_ok = 0
-    for ids in subsets:
-        n_ok += 1 if orc.solve(ids).success else 0
-    return time.perf_counter() - t0, len(seeds), n_ok
+    with contextlib.redirect_stdout(io.StringIO()):                # the reference prints per solve
+        t0 = time.perf_counter()
+        for ids in subsets:
+            for solve in solvers:
+                n_ok += 1 if solve(ids) else 0
+        dt = time.perf_counter() - t0
+    return dt, len(seeds) * len(solvers), n_ok
 
 
-def time_oracle(grid, seeds, n_procs=1, trans_tol=1e-3):
-    """Solve the subsets of ``seeds`` on ``n_procs`` processes (one oracle per worker).
+def time_workload(spec, seeds, n_procs=1, kind='port'):
+    """Solve the subsets of ``seeds`` (every load case each) on ``n_procs`` processes.
     Returns (solves_per_second, wall_seconds_of_the_solve_phase, n_true_flags)."""
     seeds = list(seeds)
     if n_procs <= 1:
-        _init_worker(grid, trans_tol)
+        _init_worker(spec, kind)
+        _solve_seeds(seeds[:1])
         dt, n, ok = _solve_seeds(seeds)
         return n / dt, dt, ok
     import multiprocessing as mp
     ctx = mp.get_context('spawn')
     chunks = [seeds[i::n_procs] for i in range(n_procs)]
     chunks = [c for c in chunks if c]
-    with ctx.Pool(len(chunks), initializer=_init_worker, initargs=(grid, trans_tol)) as pool:
+    with ctx.Pool(len(chunks), initializer=_init_worker, initargs=(spec, kind)) as pool:
         pool.map(_solve_seeds, [[s] for s in seeds[:len(chunks)]])          # warm-up: imports, first solve
         t0 = time.perf_counter()
         res = pool.map(_solve_seeds, chunks)
@@ -59,6 +131,11 @@ def time_oracle(grid, seeds, n_procs=1, trans_tol=1e-3):
     n = sum(r[1] for r in res)
     ok = sum(r[2] for r in res)
     return n / wall, wall, ok
+
+
+def time_oracle(grid, seeds, n_procs=1, trans_tol=1e-3, kind='port'):
+    spec = dict(CONFIG3, model=('grid', grid[0], grid[1], grid[2], False), trans_tol=trans_tol)
+    return time_workload(spec, seeds, n_procs, kind)
 
 
 def cpu_model_name():
@@ -72,22 +149,64 @@ def cpu_model_name():
     return 'unknown'
 
 
+def _rate_record(spec, n_sample, n_procs, kind, with_single=False):
+    rate, wall, n_true = time_workload(spec, range(n_sample), n_procs=n_procs, kind=kind)
+    rec = {'value': rate, 'unit': 'solves/s', 'cores': n_procs, 'kind': kind,
+           'sample': '{} subsets on {} process(es), {:.1f} s'.format(n_sample, n_procs, wall), 'flags_true': n_true}
+    if with_single:
+        rate1, _, _ = time_workload(spec, range(min(n_sample, 24)), n_procs=1, kind=kind)
+        rec['single_core_value'] = rate1
+    return rec
+
+
 def baseline_record(grid, trans_tol, batch, sample=0):
-    """The ``cpu_baseline`` object of bench.py: the oracle on all host cores over a bounded sample."""
+    """The ``cpu_baseline`` object of bench.py: the reference (when installed, else the port) on all
+    host cores over a bounded sample of the config-3 workload; the other implementation's rate beside it."""
     n_procs = os.cpu_count() or 1
-    n_sample = sample or min(batch, 400 * n_procs)          # ~10-15 s of CPU work
-    rate, wall, _ = time_oracle(grid, range(n_sample), n_procs=n_procs, trans_tol=trans_tol)
-    rate1, wall1, _ = time_oracle(grid, range(min(n_sample, 48)), n_procs=1, trans_tol=trans_tol)
-    return {'value': rate, 'unit': 'solves/s', 'cores': n_procs, 'kind': 'port',
-            'sample': 'first {} subsets of the same workload on {} processes ({:.1f} s); '
-                      'single process: {:.1f} solves/s; {}'.format(n_sample, n_procs, wall, rate1, cpu_model_name()),
-            'single_core_value': rate1}
+    have_ref = reference_available()
+    kind = 'reference' if have_ref else 'port'
+    spec = dict(CONFIG3, model=('grid', grid[0], grid[1], grid[2], False), trans_tol=trans_tol)
+    n_sample = sample or min(batch, (40 if have_ref else 100) * n_procs)          # ~5 s per process either way
+    rec = _rate_record(spec, n_sample, n_procs, kind, with_single=True)
+    rec['sample'] = 'first {}; single process: {:.1f} solves/s; {}'.format(rec['sample'], rec['single_core_value'], cpu_model_name())
+    if have_ref:
+        rec['what'] = 'StiffnessChecker(checker_engine="numpy").solve of the unmodified reference (baseline/_ref)'
+        prate, _, _ = time_workload(spec, range(min(batch, 100 * n_procs)), n_procs=n_procs, kind='port')
+        rec['port_value'] = prate
+        rec['port_note'] = 'oracle/frame_oracle.py (vectorised restatement) on the same cores: faster than the reference'
+    else:
+        rec['what'] = 'oracle port (reference install baseline/_ref absent)'
+    return rec
+
+
+# the other BASELINE.json configurations, as bench.py's `other_configs` runs them on the GPU
+OTHER_CONFIGS = {
+    'config1_tower_full_solve': {'model': ('json', 'tower_3D.json'), 'loads': 'gravity', 'subsets': 'full', 'trans_tol': 1e-3},
+    'config2_tower_bfs_prefixes': {'model': ('json', 'tower_3D.json'), 'loads': 'gravity', 'subsets': 'bfs_prefixes', 'trans_tol': 1e-3},
+    'config4_joints_4_loadcases': {'model': ('grid', 7, 7, 8, True), 'loads': 'config4', 'subsets': 'heightfield', 'trans_tol': 1e-3},
+    'config5_10k_frame': {'model': ('grid', 15, 15, 16, False), 'loads': 'gravity', 'subsets': 'connected', 'trans_tol': 1e-3},
+}
+
+
+def other_configs_record():
+    """CPU rates of configs 1, 2, 4 and 5 on bounded samples (a few seconds each)."""
+    n_procs = os.cpu_count() or 1
+    kind = 'reference' if reference_available() else 'port'
+    out = {}
+    out['config1_tower_full_solve'] = _rate_record(OTHER_CONFIGS['config1_tower_full_solve'], 50, 1, kind)
+    out['config2_tower_bfs_prefixes'] = _rate_record(OTHER_CONFIGS['config2_tower_bfs_prefixes'], 24, 1, kind)
+    out['config4_joints_4_loadcases'] = _rate_record(OTHER_CONFIGS['config4_joints_4_loadcases'], 6 * n_procs, n_procs, kind)
+    out['config5_10k_frame'] = _rate_record(OTHER_CONFIGS['config5_10k_frame'], n_procs, n_procs, kind)
+    return out
 
 
 if __name__ == '__main__':
-    # python -m oracle.cpu_bench nx ny nz trans_tol batch sample  ->  one JSON line (used by bench.py in a
-    # child process so that the CPU run shares no state - threads, allocator - with the GPU process)
+    # python -m oracle.cpu_bench nx ny nz trans_tol batch sample [others]  ->  one JSON line (used by bench.py
+    # in a child process so that the CPU run shares no state - threads, allocator - with the GPU process)
     import json
     import sys
     a = sys.argv[1:]
-    print(json.dumps(baseline_record((int(a[0]), int(a[1]), int(a[2])), float(a[3]), int(a[4]), int(a[5]))))
+    rec = baseline_record((int(a[0]), int(a[1]), int(a[2])), float(a[3]), int(a[4]), int(a[5]))
+    if len(a) > 6 and a[6] == 'others':
+        rec['other_configs'] = other_configs_record()
+    print(json.dumps(rec))

@@ -26,7 +26,7 @@ def test_capi_loads_and_exports_header_symbols():
     assert b'sm_100a' in lib.cm_version()
     # struct layouts the header promises
     import ctypes as C
-    assert C.sizeof(_capi.SolveOut) == 16 * 8 and C.sizeof(_capi.SolveOutHost) == 16 * 8
+    assert C.sizeof(_capi.SolveOut) == 18 * 8 and C.sizeof(_capi.SolveOutHost) == 18 * 8
     assert C.sizeof(_capi.ModelDesc) == 16 + 6 * 8
 
 
@@ -83,7 +83,7 @@ def test_native_mask_packer_matches_numpy():
     subs[7] = np.array(subs[7], dtype=np.int32)
     subs[8] = np.array(subs[8], dtype=np.int64)
     subs[9] = np.array(subs[9], dtype=np.uint16)
-    subs[10] = [nE - 1, 0, 0, 31, 32]
+    subs[10] = [nE - 1, 0, 31, 32]
     native = masks.pack_masks(subs, nE)
     masks.USE_NATIVE = False
     try:
@@ -97,6 +97,30 @@ def test_native_mask_packer_matches_numpy():
     for bad in ([[0, nE]], [[-1]], [np.array([5, 5000])]):
         with pytest.raises(IndexError):
             masks.pack_masks(bad, nE)
+    # a repeated id is rejected by every packer (the reference would assemble the element twice,
+    # numpy_stiffness_assembly.py:371-388; a bit mask cannot express that)
+    for dup in ([[3, 7, 3]], [np.array([1, 1], dtype=np.int64)], [(5, 6, 5)]):
+        with pytest.raises(ValueError):
+            masks.pack_masks(dup, nE)
+        masks.USE_NATIVE = False
+        try:
+            with pytest.raises(ValueError):
+                masks.pack_masks([list(dup[0])], nE)
+        finally:
+            masks.USE_NATIVE = True
+    with pytest.raises(ValueError):
+        masks.pack_masks_csr(np.array([4, 9, 4]), np.array([0, 3]), nE)
+    # release-store hand-over flag and the mask-matrix detection of solve_many
+    fl = np.zeros(4, dtype=np.int32)
+    masks.publish(fl, 2, 1)
+    masks.publish(fl, 3, -1)
+    assert fl.tolist() == [0, 0, 1, -1]
+    mm = masks.pack_masks([[1, 2], [3]], nE)
+    assert masks.as_mask_matrix(mm, 30) is not None and masks.as_mask_matrix(mm.view(np.int32), 30).dtype == np.uint32
+    assert masks.as_mask_matrix([[1, 2], [3]], 30) is None
+    assert masks.as_mask_matrix(np.zeros((2, 5), dtype=np.int64), 30) is None       # id rows
+    with pytest.raises(ValueError):
+        masks.as_mask_matrix(np.zeros((2, 5), dtype=np.int32), 30)                  # masks of another model?
     # the same subsets as two arrays (flat ids + offsets)
     lists = [list(x) for x in subs]
     flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in lists])
@@ -175,6 +199,8 @@ def test_shard_range_partitions():
 
 class _FakeEngine(object):
     """Stands in for CudaStiffness on a CPU box: deterministic per-subset outputs from the masks."""
+    info = {'mask_words': 30}
+
     def solve_many(self, masks, want):
         pop = np.unpackbits(np.ascontiguousarray(masks).view(np.uint8), axis=1).sum(axis=1)
         res = {'flag': (pop % 2 == 0).astype(np.uint8).reshape(-1, 1), 'status': np.zeros((len(masks), 1), np.uint8),
@@ -189,7 +215,7 @@ def _sharded_worker(rank, world, port, B, ret):
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{}'.format(port), rank=rank, world_size=world)
     rng = np.random.RandomState(0)
     masks = rng.randint(0, 2 ** 32, size=(B, 30), dtype=np.uint64).astype(np.uint32)
-    out = solve_many_sharded(_FakeEngine(), masks)
+    out = solve_many_sharded(_FakeEngine(), masks.view(np.int32) if rank else masks)      # int32 views are masks too
     ret[rank] = {k: v.copy() for k, v in out.items()}
     dist.destroy_process_group()
 
