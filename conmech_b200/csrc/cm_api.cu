@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <numeric>
 #include <queue>
 
@@ -30,6 +31,12 @@ struct cm_handle {
     cm_ws_layout L{};
     std::vector<void *> allocs;          // device allocations owned by the handle
     std::vector<int> order;              // host copy of the ordering
+    // geometry tables (stacked over the geometry variants; replaced as a set by cm_set_geometries)
+    double *d_xyz = nullptr, *d_Kg = nullptr, *d_R3 = nullptr, *d_elen = nullptr;
+    std::vector<int32_t> conn;           // host copy of the connectivity (length checks of new geometries)
+    int *d_geom = nullptr;               // staging of the per-subset geometry indices of the host entry point
+    size_t geom_cap = 0;
+    double k1_ms = 0.0;                  // device time of the most recent element-table launch
     // load tables
     double *d_q = nullptr, *d_pnodal = nullptr;
     double rot_tol = 0.0;
@@ -191,6 +198,8 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     cudaDeviceGetAttribute(&m.n_sm, cudaDevAttrMultiProcessorCount, d->device);
     if (m.n_sm <= 0) m.n_sm = 148;
     m.nV = nV; m.nE = nE; m.nS = nS; m.n_lc = 0;
+    m.n_geom = 1;
+    h->conn.assign(d->conn, d->conn + 2 * (size_t)nE);
     m.mask_words = (nE + 31) / 32;
     m.trans_tol = 1e-3;
     h->rot_tol = 3.14159265358979323846 / 180 * 3;
@@ -279,11 +288,10 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     I.profile_flops_full = use_rcm ? fl1 : fl0;
 
     int rc;
-    double *xyz, *props, *cr; int *conn, *d_ne_ptr, *d_ne_elem, *d_sup_node, *d_node_sup, *d_order, *d_pos;
+    double *props, *cr; int *conn, *d_ne_ptr, *d_ne_elem, *d_sup_node, *d_node_sup, *d_order, *d_pos;
     int *d_lp_ptr, *d_lp_node, *d_lp_eptr, *d_lp_elem;
     unsigned char *d_ne_end, *d_sup_cond, *d_lp_end;
 #define UP(expr) do { rc = (expr); if (rc != CM_OK) { cm_destroy(h); return rc; } } while (0)
-    UP(dev_upload(h, d->xyz, (size_t)3 * nV, &xyz));
     UP(dev_upload(h, d->conn, (size_t)2 * nE, &conn));
     UP(dev_upload(h, d->props, (size_t)7 * nE, &props));
     UP(dev_upload(h, d->cr, (size_t)6 * nE, &cr));
@@ -326,11 +334,17 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
         m.k2_blob = d_blob;
         m.k2_blob_bytes = (int)blob.size();
     }
-    UP(dev_upload<double>(h, nullptr, (size_t)144 * nE, &m.Kg));
-    UP(dev_upload<double>(h, nullptr, (size_t)9 * nE, &m.R3));
-    UP(dev_upload<double>(h, nullptr, (size_t)nE, &m.elen));
 #undef UP
-    m.xyz = xyz; m.conn = conn; m.props = props; m.cr = cr;
+    {   // geometry 0: the model's own node coordinates
+        cudaError_t ce = cudaMalloc((void **)&h->d_xyz, (size_t)3 * nV * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_Kg, (size_t)144 * nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_R3, (size_t)9 * nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_elen, (size_t)nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMemcpy(h->d_xyz, d->xyz, (size_t)3 * nV * sizeof(double), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) { std::string msg = std::string("cm_create: ") + cudaGetErrorString(ce); cm_destroy(h); return fail(CM_ERR_CUDA, msg); }
+    }
+    m.xyz = h->d_xyz; m.Kg = h->d_Kg; m.R3 = h->d_R3; m.elen = h->d_elen;
+    m.conn = conn; m.props = props; m.cr = cr;
     m.ne_ptr = d_ne_ptr; m.ne_elem = d_ne_elem; m.ne_end = d_ne_end;
     m.sup_node = d_sup_node; m.sup_cond = d_sup_cond; m.node_sup = d_node_sup;
     m.order = d_order; m.pos = d_pos;
@@ -349,9 +363,12 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming);
     if (const char *e = getenv("CM_LANES")) { int n = atoi(e); if (n >= 1 && n <= 4) h->n_lanes = n; }
     if (const char *e = getenv("CM_NO_OVERLAP")) h->overlap = (e[0] == '1') ? 0 : 1;
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev[0], h->stream);
     if (ce == cudaSuccess) ce = cm_launch_element_tables(m, h->stream);
     h->launches++;
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev[1], h->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    if (ce == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->k1_ms = ms; }
     if (ce != cudaSuccess) {
         std::string msg = std::string("cm_create: ") + cudaGetErrorString(ce);
         cm_destroy(h);
@@ -367,6 +384,7 @@ int cm_destroy(cm_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->d_q) cudaFree(h->d_q);
     if (h->d_pnodal) cudaFree(h->d_pnodal);
+    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_R3); cudaFree(h->d_elen); cudaFree(h->d_geom);
     if (h->stage) cudaFree(h->stage);
     if (h->wsbuf) cudaFree(h->wsbuf);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -411,6 +429,94 @@ int cm_get_node_order(const cm_handle *h, int32_t *order) {
     return CM_OK;
 }
 
+// Per-element property SoA from per-tag tables (host side of cm_create's input): what the reference's
+// engine constructor does element by element in Python (numpy_stiffness.py:579-614).
+int cm_pack_elements(int32_t n_elems, const int32_t *sec_of, const int32_t *mat_of, const int32_t *joint_of,
+                     const uint8_t *bending_stiff, int32_t n_sec, const double *sections, int32_t n_mat,
+                     const double *materials, int32_t n_joint, const double *joints, double *props, double *cr) {
+    if (n_elems < 0 || !sec_of || !mat_of || !sections || !materials || !props || !cr)
+        return fail(CM_ERR_INVALID, "cm_pack_elements: null argument");
+    if (n_joint > 0 && !joints) return fail(CM_ERR_INVALID, "cm_pack_elements: joints table missing");
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int32_t e = 0; e < n_elems; ++e) {
+        const int32_t s = sec_of[e], mt = mat_of[e], j = joint_of ? joint_of[e] : -1;
+        if (s < 0 || s >= n_sec || mt < 0 || mt >= n_mat || j >= n_joint)
+            return fail(CM_ERR_INVALID, "cm_pack_elements: element " + std::to_string(e) + " refers to a table entry that does not exist");
+        const double *cs = sections + 4 * (size_t)s, *ma = materials + 3 * (size_t)mt;
+        if (!(std::fabs(ma[0]) > CM_EPS) || !(std::fabs(cs[3]) > CM_EPS))            // numpy_stiffness_assembly.py:146
+            return fail(CM_ERR_INVALID, "E#" + std::to_string(e) + " - E and Iz must be non-zero");
+        double *p = props + 7 * (size_t)e, *c = cr + 6 * (size_t)e;
+        p[0] = cs[0]; p[1] = cs[1]; p[2] = cs[2]; p[3] = cs[3]; p[4] = ma[0]; p[5] = ma[1]; p[6] = ma[2];
+        for (int i = 0; i < 6; ++i) c[i] = j >= 0 ? joints[6 * (size_t)j + i] : inf;     // None -> rigid (:592-597)
+        if (bending_stiff && !bending_stiff[e])
+            for (int i = 0; i < 6; ++i) c[i] = 0.0;                                      // truss member (:598-601)
+    }
+    return CM_OK;
+}
+
+int cm_set_geometries(cm_handle *h, int32_t n_geom, const double *xyz) {
+    if (!h || !xyz) return fail(CM_ERR_INVALID, "cm_set_geometries: null argument");
+    if (n_geom < 1) return fail(CM_ERR_INVALID, "cm_set_geometries: at least one geometry");
+    cm_model_dev &m = h->m;
+    const size_t nV = m.nV, nE = m.nE, G = (size_t)n_geom;
+    for (size_t g = 0; g < G; ++g)                  // numpy_stiffness_assembly.py:288-289, per variant
+        for (size_t e = 0; e < nE; ++e) {
+            const double *pu = xyz + (g * nV + h->conn[2 * e]) * 3, *pv = xyz + (g * nV + h->conn[2 * e + 1]) * 3;
+            const double dx = pu[0] - pv[0], dy = pu[1] - pv[1], dz = pu[2] - pv[2];
+            if (!(std::sqrt(dx * dx + dy * dy + dz * dz) >= CM_EPS))
+                return fail(CM_ERR_INVALID, "geometry " + std::to_string(g) + ": E#" + std::to_string(e) + " - Bar length too small!");
+        }
+    CU(cudaSetDevice(h->device));
+    // new tables beside the old ones, swapped in on success
+    double *nx = nullptr, *nK = nullptr, *nR = nullptr, *nL = nullptr;
+    cudaError_t ce = cudaMalloc((void **)&nx, G * 3 * nV * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nK, G * 144 * nE * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nR, G * 9 * nE * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nL, G * nE * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpy(nx, xyz, G * 3 * nV * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        cm_model_dev t = m;
+        t.n_geom = n_geom; t.xyz = nx; t.Kg = nK; t.R3 = nR; t.elen = nL;
+        ce = cudaEventRecord(h->ev[0], h->stream);
+        if (ce == cudaSuccess) ce = cm_launch_element_tables(t, h->stream);
+        h->launches++;
+        if (ce == cudaSuccess) ce = cudaEventRecord(h->ev[1], h->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+        if (ce == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->k1_ms = ms; }
+    }
+    if (ce != cudaSuccess) {
+        cudaFree(nx); cudaFree(nK); cudaFree(nR); cudaFree(nL);
+        return fail(ce == cudaErrorMemoryAllocation ? CM_ERR_NOMEM : CM_ERR_CUDA, std::string("cm_set_geometries: ") + cudaGetErrorString(ce));
+    }
+    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_R3); cudaFree(h->d_elen);
+    h->d_xyz = nx; h->d_Kg = nK; h->d_R3 = nR; h->d_elen = nL;
+    m.n_geom = n_geom; m.xyz = nx; m.Kg = nK; m.R3 = nR; m.elen = nL;
+    // the lumped element loads depend on the geometry: the load cases have to be set again
+    if (h->d_q) { cudaFree(h->d_q); h->d_q = nullptr; }
+    m.q = nullptr;
+    m.n_lc = 0;
+    h->info.n_loadcases = 0;
+    return CM_OK;
+}
+
+int cm_get_geometry_tables(cm_handle *h, int32_t g, double *Kg, double *R3) {
+    if (!h) return fail(CM_ERR_INVALID, "cm_get_geometry_tables: null handle");
+    if (g < 0 || g >= h->m.n_geom) return fail(CM_ERR_INVALID, "cm_get_geometry_tables: no such geometry");
+    CU(cudaSetDevice(h->device));
+    const size_t nE = h->m.nE;
+    if (Kg) CU(cudaMemcpy(Kg, h->m.Kg + (size_t)g * 144 * nE, 144 * nE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (R3) CU(cudaMemcpy(R3, h->m.R3 + (size_t)g * 9 * nE, 9 * nE * sizeof(double), cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+
+int32_t cm_geometry_count(const cm_handle *h) { return h ? h->m.n_geom : 0; }
+
+int cm_last_element_kernel_ms(const cm_handle *h, double *ms) {
+    if (!h || !ms) return fail(CM_ERR_INVALID, "cm_last_element_kernel_ms: null argument");
+    *ms = h->k1_ms;
+    return CM_OK;
+}
+
 static void make_layout(cm_handle *h) {
     const cm_model_dev &m = h->m;
     cm_ws_layout &L = h->L;
@@ -446,7 +552,7 @@ int cm_set_loadcases(cm_handle *h, int32_t n_lc, const double *nodal, const doub
     double *nq = nullptr, *npn = nullptr;
     double *d_w = nullptr, *d_g = nullptr;
     unsigned char *d_has = nullptr, *d_on = nullptr;
-    cudaError_t ce = cudaMalloc((void **)&nq, n_lc * nE * 12 * sizeof(double));
+    cudaError_t ce = cudaMalloc((void **)&nq, (size_t)m.n_geom * n_lc * nE * 12 * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&npn, n_lc * 6 * nV * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMemcpy(npn, nodal, n_lc * 6 * nV * sizeof(double), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess && has_udl) {
@@ -566,7 +672,7 @@ static cm_out_dev out_dev_of(const cm_solve_out *o) {
 // The waves of one call.  `before(w, first, count, lane_stream, &od)` runs before a wave's kernels are
 // enqueued and may redirect the wave's outputs; `after(...)` runs right after its last kernel.
 template <typename Before, typename After>
-static int run_waves(cm_handle *h, const uint32_t *masks, int64_t B, const cm_out_dev &od0, char *ws,
+static int run_waves(cm_handle *h, const uint32_t *masks, const int *geom, int64_t B, const cm_out_dev &od0, char *ws,
                      const WavePlan &P, cudaStream_t st, Before before, After after) {
     const size_t per = h->L.per_subset;
     double acc_ms[3] = {0, 0, 0};
@@ -582,7 +688,7 @@ static int run_waves(cm_handle *h, const uint32_t *masks, int64_t B, const cm_ou
         cm_out_dev od = od0;
         { int rc = before(w, first, count, ls, od); if (rc != CM_OK) return rc; }
         if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
-        CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, first, count, od, h->variant != 0 ? 1 : 0, ls));
+        CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, geom, first, count, od, h->variant != 0 ? 1 : 0, ls));
         if (h->variant != 0) { CU(cm_launch_schedule(h->L, lws, count, ls)); h->launches += 1; }
         if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
         if (h->variant == 0)
@@ -594,7 +700,7 @@ static int run_waves(cm_handle *h, const uint32_t *masks, int64_t B, const cm_ou
             CU(cm_launch_factor_flow(h->m, h->L, lws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, ls));
         }
         if (h->timing) CU(cudaEventRecord(h->ev[2], ls));
-        CU(cm_launch_solve_recover(h->m, h->L, lws, masks, first, count, od, ls));
+        CU(cm_launch_solve_recover(h->m, h->L, lws, masks, geom, first, count, od, ls));
         h->launches += 3;
         if (h->timing) {
             CU(cudaEventRecord(h->ev[3], ls));
@@ -621,6 +727,11 @@ extern "C" {
 
 int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *o, uint64_t ws_dev,
                   size_t ws_bytes, uint64_t stream) {
+    return cm_solve_many_g(h, masks_dev, 0, B, o, ws_dev, ws_bytes, stream);
+}
+
+int cm_solve_many_g(cm_handle *h, uint64_t masks_dev, uint64_t geom_dev, int64_t B, const cm_solve_out *o, uint64_t ws_dev,
+                    size_t ws_bytes, uint64_t stream) {
     if (!h || !o) return fail(CM_ERR_INVALID, "cm_solve_many: null argument");
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
@@ -628,7 +739,8 @@ int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_ou
     WavePlan P;
     { int rc = plan_waves(h, B, ws_bytes, &P); if (rc != CM_OK) return rc; }
     CU(cudaSetDevice(h->device));
-    return run_waves(h, reinterpret_cast<const uint32_t *>(masks_dev), B, out_dev_of(o), reinterpret_cast<char *>(ws_dev), P,
+    return run_waves(h, reinterpret_cast<const uint32_t *>(masks_dev), reinterpret_cast<const int *>(geom_dev), B, out_dev_of(o),
+                     reinterpret_cast<char *>(ws_dev), P,
                      reinterpret_cast<cudaStream_t>(stream),
                      [](long long, long long, int, cudaStream_t, cm_out_dev &) { return CM_OK; },
                      [](long long, long long, int, cudaStream_t) { return CM_OK; });
@@ -673,10 +785,26 @@ extern "C" {
 // transfer of full results (U, Rf, eR: 127 KB per subset on the 1k-element frame) overlaps the
 // kernels instead of following them.
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, const cm_solve_out_host *o) {
+    return cm_solve_many_host_g(h, masks_host, nullptr, B, o);
+}
+
+int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, int64_t B,
+                         const cm_solve_out_host *o) {
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host: null argument");
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many_host: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
+    if (geom_host)
+        for (int64_t b = 0; b < B; ++b)
+            if (geom_host[b] < 0 || geom_host[b] >= h->m.n_geom)
+                return fail(CM_ERR_INVALID, "cm_solve_many_host: geometry index " + std::to_string(geom_host[b]) + " of subset " +
+                                            std::to_string(b) + " not in [0, " + std::to_string(h->m.n_geom) + ")");
     CU(cudaSetDevice(h->device));
+    if (geom_host && (size_t)B > h->geom_cap) {
+        cudaFree(h->d_geom);
+        h->d_geom = nullptr; h->geom_cap = 0;
+        CU(cudaMalloc((void **)&h->d_geom, (size_t)B * sizeof(int)));
+        h->geom_cap = (size_t)B;
+    }
     const cm_model_dev &m = h->m;
     const size_t Bn = (size_t)B;
     // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
@@ -716,6 +844,7 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
     }
     cudaStream_t st = h->stream;
     CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
+    if (geom_host) CU(cudaMemcpyAsync(h->d_geom, geom_host, Bn * sizeof(int), cudaMemcpyHostToDevice, st));
     char *slots = h->stage + mask_bytes;
     auto before = [&](long long w, long long first, int, cudaStream_t ls, cm_out_dev &od) -> int {
         const int s = (int)(w % n_slots);
@@ -743,7 +872,7 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
         return CM_OK;
     };
     cm_out_dev od0{};
-    int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), B, od0, h->wsbuf, P, st, before, after);
+    int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), geom_host ? h->d_geom : nullptr, B, od0, h->wsbuf, P, st, before, after);
     if (rc != CM_OK) { cudaDeviceSynchronize(); return rc; }
     CU(cudaEventRecord(h->copy_ev, h->copy_stream));
     CU(cudaStreamWaitEvent(st, h->copy_ev, 0));

@@ -52,16 +52,18 @@ __host__ __device__ __forceinline__ int cm_mtile_off(int r, int k) {
 struct cm_model_dev {
     int device, n_sm;      // CUDA device the tables live on and its SM count (fixed at cm_create)
     int nV, nE, nS, n_lc;
+    int n_geom;            // geometry variants of the frame (same topology, different node coordinates): the tables marked
+                           // [n_geom x ...] below are stacked, a subset picks its variant by index
     int mask_words;
     int n_tile_rows_max;   // tile rows of the full structure
     int band_tiles;        // tiles stored per tile row: columns I-band_tiles+1 .. I
-    const double *xyz;     // [nV*3]
+    const double *xyz;     // [n_geom x nV*3]
     const int *conn;       // [nE*2]
     const double *props;   // [nE*7] A,Jx,Iy,Iz,E,mu,rho
     const double *cr;      // [nE*6]
-    double *Kg;            // [nE*144] row major global element stiffness
-    double *R3;            // [nE*9]
-    double *elen;          // [nE]
+    double *Kg;            // [n_geom x nE*144] row major global element stiffness
+    double *R3;            // [n_geom x nE*9]
+    double *elen;          // [n_geom x nE]
     const int *ne_ptr;     // [nV+1] node -> incident elements (ascending ids)
     const int *ne_elem;    // [2nE]
     const unsigned char *ne_end;   // [2nE] which end of that element the node is
@@ -83,7 +85,7 @@ struct cm_model_dev {
     const char *k2_blob;
     int k2_blob_bytes;
     int k2_off[12];
-    const double *q;       // [n_lc*nE*12] lumped element loads
+    const double *q;       // [n_geom x n_lc*nE*12] lumped element loads
     const double *pnodal;  // [n_lc*6nV]
     double trans_tol;
 };
@@ -147,8 +149,9 @@ cudaError_t cm_launch_element_generic(const double *xyz_u, const double *xyz_v, 
 // so the layout K2 writes is free, and row-major makes the six entries of a block row contiguous
 // (2 sectors instead of 6 partial-sector writes).  The tensor-core factorisation reads it that way
 // (acc_load_rm); the scalar validation kernel wants fragment-major.
+// geom: per-subset geometry index (device, indexed like masks) or nullptr = geometry 0
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
-                                      const uint32_t *masks, long long first, int count,
+                                      const uint32_t *masks, const int *geom, long long first, int count,
                                       const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st);
 cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
@@ -157,5 +160,5 @@ cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, 
                                   int config, int prof, cudaStream_t st);
 cudaError_t cm_factor_flow_read_prof(unsigned long long *out16);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
-                                    const uint32_t *masks, long long first, int count,
+                                    const uint32_t *masks, const int *geom, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st);

@@ -40,10 +40,21 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(x, e, x);             // below one ulp
 }
 
+// Progress flags live in shared memory, the data they guard in global memory (written by other warps of the
+// SAME CTA, i.e. through the same L1).  Consumer: an acquire load of the flag - on sm_100a a plain LDS; the loads
+// that follow cannot issue before it has returned (in-order issue, control dependence) - and NO fence: a
+// __threadfence_block() there is a MEMBAR.SC.CTA that also drains the polling warp's OWN outstanding stores (the 8 KB
+// tile it has just written).  Producer: release fence (fence.acq_rel.cta = MEMBAR.ALL.CTA) after its stores, then the
+// flag store.  (9.95 -> 9.91 ms per 4096 subsets against __threadfence_block() on both sides.)
+__device__ __forceinline__ int flag_acquire(const volatile int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(const_cast<const int *>(p))) : "memory");
+    return v;
+}
+__device__ __forceinline__ void release_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ int wait_prog_gt(volatile int *prog, int J, int K) {
-    int p = prog[J];
-    while (p <= K) { __nanosleep(CM_SLEEP_NS); p = prog[J]; }
-    __threadfence_block();
+    int p = flag_acquire(prog + J);
+    while (p <= K) { __nanosleep(CM_SLEEP_NS); p = flag_acquire(prog + J); }
     return p;
 }
 

@@ -217,15 +217,18 @@ __device__ __forceinline__ void lump_udl(const double w[3], const double *R3, do
     }
 }
 
+// blockIdx.y = geometry variant: node coordinates of variant g, tables of variant g (stacked)
 __global__ void __launch_bounds__(K1_THREADS) k1_element_tables(cm_model_dev m) {
     __shared__ double s_stage[36 * K1_SSTR];
     const int e0 = blockIdx.x * K1_THREADS;
     const int e = e0 + threadIdx.x;
+    const size_t g = blockIdx.y;
     const bool valid = e < m.nE;
     const int ec = valid ? e : 0;
     const int u = m.conn[2 * ec], v = m.conn[2 * ec + 1];
-    element_tables(m.xyz + 3 * u, m.xyz + 3 * v, m.props + 7 * ec, m.cr + 6 * ec, valid, m.Kg + 144 * (size_t)e0,
-                   min(K1_THREADS, m.nE - e0), m.R3 + 9 * (size_t)ec, m.elen + ec, s_stage);
+    const double *xyz = m.xyz + g * 3 * m.nV;
+    element_tables(xyz + 3 * u, xyz + 3 * v, m.props + 7 * ec, m.cr + 6 * ec, valid, m.Kg + 144 * (g * m.nE + e0),
+                   min(K1_THREADS, m.nE - e0), m.R3 + 9 * (g * m.nE + ec), m.elen + g * m.nE + ec, s_stage);
 }
 
 __global__ void __launch_bounds__(K1_THREADS) k1_element_generic(const double *xyz_u, const double *xyz_v,
@@ -246,9 +249,11 @@ __global__ void __launch_bounds__(128) k1_element_loads(cm_model_dev m, int n_lc
                                                         const double *grav_dir, double *q) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     int lc = blockIdx.y;
+    const size_t g = blockIdx.z;                                // geometry variant
     if (e >= m.nE) return;
-    const double *R3 = m.R3 + 9 * (size_t)e;
-    double L = m.elen[e];
+    const double *R3 = m.R3 + 9 * (g * m.nE + e);
+    double L = m.elen[g * m.nE + e];
+    q += g * n_lc * m.nE * 12;
     double out[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) out[i] = 0.0;
@@ -275,7 +280,8 @@ __global__ void __launch_bounds__(128) k1_element_loads(cm_model_dev m, int n_lc
 }  // namespace
 
 cudaError_t cm_launch_element_tables(const cm_model_dev &m, cudaStream_t st) {
-    k1_element_tables<<<(m.nE + 127) / 128, 128, 0, st>>>(m);
+    dim3 grid((m.nE + 127) / 128, m.n_geom);
+    k1_element_tables<<<grid, 128, 0, st>>>(m);
     return cudaGetLastError();
 }
 
@@ -288,7 +294,7 @@ cudaError_t cm_launch_element_generic(const double *xyz_u, const double *xyz_v, 
 cudaError_t cm_launch_element_loads(const cm_model_dev &m, int n_lc, const double *w_udl,
                                     const unsigned char *has_udl, const unsigned char *grav_on,
                                     const double *grav_dir, double *q, cudaStream_t st) {
-    dim3 grid((m.nE + 127) / 128, n_lc);
+    dim3 grid((m.nE + 127) / 128, n_lc, m.n_geom);
     k1_element_loads<<<grid, 128, 0, st>>>(m, n_lc, w_udl, has_udl, grav_on, grav_dir, q);
     return cudaGetLastError();
 }

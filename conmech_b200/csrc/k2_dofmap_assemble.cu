@@ -44,8 +44,8 @@ __device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (m
 
 // solver row of local DOF i of node v (-1 if fixed); base = first solver row of the node
 __device__ __forceinline__ int node_row(const int *node_sup, const unsigned char *sup_cond, int v, int i, int base) {
-    int s = node_sup[v];
-    if (s < 0) return base + i;
+    const int s = node_sup[v];
+    if (s < 0) return base + i;            // (the common case: not a support node)
     const unsigned char *c = sup_cond + 6 * s;
     if (c[i]) return -1;
     int r = base;
@@ -61,7 +61,7 @@ __device__ __forceinline__ int node_row(const int *node_sup, const unsigned char
 #endif
 template <bool TS>      // TS: the index tables are staged in shared memory
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
-k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
+k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, const int *geom, long long first,
                    cm_out_dev out, int ktilde_rm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout
@@ -100,6 +100,10 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     int *info = reinterpret_cast<int *>(slab + L.off_info);
     const uint32_t *gmask = masks + (size_t)gs * m.mask_words;
     const int nV = m.nV;
+    // geometry variant of this subset: its slice of the stacked stiffness / load tables
+    const size_t gv = geom ? (size_t)min(max(geom[gs], 0), m.n_geom - 1) : 0;
+    const double *Kg = m.Kg + gv * m.nE * 144;
+    const double *qtab = m.q + gv * m.n_lc * m.nE * 12;
 
     // index tables: shared-memory copies when they fit (one coalesced pass), the global blob otherwise
     const char *blob = TS ? s_blob : m.k2_blob;
@@ -287,7 +291,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) {
             const int e = ne_elem[p];
             const int l = 6 * ne_end[p] + i;
-            const double kv = thr(m.Kg[(size_t)e * 144 + l * 12 + l]);
+            const double kv = thr(Kg[(size_t)e * 144 + l * 12 + l]);
             kii += elem_on(s_mask, e) ? kv : 0.0;
         }
         dinv[r] = kii;
@@ -380,7 +384,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     for (int p = p0; p < p1; ++p) {
                         const int e = ne_elem[p];
                         const int o = 6 * ne_end[p];
-                        const double2 *kp = reinterpret_cast<const double2 *>(m.Kg + (size_t)e * 144 + (o + i) * 12 + o);
+                        const double2 *kp = reinterpret_cast<const double2 *>(Kg + (size_t)e * 144 + (o + i) * 12 + o);
 #if defined(K2_EXP) && K2_EXP == 4          // timing experiment (wrong results): no stiffness-table reads
                         const double2 v0 = make_double2(1.0 + e, 2.0), v1 = v0, v2 = v0; (void)kp;
 #else
@@ -401,7 +405,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     for (int pe = lp_eptr[q]; pe < pe1; ++pe) {
                         const int e = lp_elem[pe];
                         const int ea = lp_end[pe];
-                        const double2 *kp = reinterpret_cast<const double2 *>(m.Kg + (size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea));
+                        const double2 *kp = reinterpret_cast<const double2 *>(Kg + (size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea));
 #if defined(K2_EXP) && K2_EXP == 4
                         const double2 v0 = make_double2(1.0 + e, 2.0), v1 = v0, v2 = v0; (void)kp;
 #else
@@ -415,39 +419,53 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     }
                     if (!any) continue;          // no existing element joins the pair: the tile may be unassembled
                 }
-                // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only):
-                // `cnt` consecutive columns from base_c on
+                // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only).
+                // Every index into the value array is a compile-time constant (a run-time index puts the array
+                // into local memory: that was 1.3 GB of L1-missing local loads per 4096 subsets).
                 const double dr = dinv[r];
                 const int sc = node_sup[c];
                 const int jmax = blk == 0 ? i : 5;
                 const int I = r >> 5;
-                double vals[6];
-                int cnt = 0;
+                auto tile_of = [&](int K) { return tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS; };
+                if (sc < 0) {
+                    // node c is not a support: its six DOFs are the columns base_c .. base_c + 5
+                    double v[6];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    if (sc >= 0 && sup_cond[6 * sc + j]) continue;        // fixed DOF: no solver column
-                    if (j <= jmax) { vals[cnt] = (dr * s6[j]) * dinv[base_c + cnt]; ++cnt; }
-                }
-                if (cnt == 0) continue;
-                const int K0 = base_c >> 5, K1 = (base_c + cnt - 1) >> 5;
-                if (ktilde_rm && K0 == K1) {
-                    // row-major K~ tile: the row's entries are contiguous - 16-byte stores where aligned
+                    for (int j = 0; j < 6; ++j) v[j] = (dr * s6[j]) * dinv[base_c + j];
+                    const int K0 = base_c >> 5;
+                    if (ktilde_rm && K0 == ((base_c + jmax) >> 5)) {
+                        // row-major K~ tile: the row's entries are contiguous - 16-byte stores where aligned
 #if defined(K2_EXP) && K2_EXP == 5          // timing experiment (wrong results): all entry stores into one 8 KB tile of the slab
-                    double *dst = tiles + (r & 31) * 32 + (base_c & 31);       // (same alignment as the real destination)
+                        double *dst = tiles + (r & 31) * 32 + (base_c & 31);       // (same alignment as the real destination)
 #else
-                    double *dst = tiles + ((size_t)I * bt + (K0 - I + bt - 1)) * CM_TILE_ELEMS + (r & 31) * 32 + (base_c & 31);
+                        double *dst = tile_of(K0) + (r & 31) * 32 + (base_c & 31);
 #endif
-                    int x = 0;
-                    if ((base_c & 1) && x < cnt) { dst[0] = vals[0]; x = 1; }
+                        if (base_c & 1) {
+                            dst[0] = v[0];
+                            if (jmax >= 2) *reinterpret_cast<double2 *>(dst + 1) = make_double2(v[1], v[2]); else if (jmax == 1) dst[1] = v[1];
+                            if (jmax >= 4) *reinterpret_cast<double2 *>(dst + 3) = make_double2(v[3], v[4]); else if (jmax == 3) dst[3] = v[3];
+                            if (jmax == 5) dst[5] = v[5];
+                        } else {
+                            if (jmax >= 1) *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]); else dst[0] = v[0];
+                            if (jmax >= 3) *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]); else if (jmax == 2) dst[2] = v[2];
+                            if (jmax == 5) *reinterpret_cast<double2 *>(dst + 4) = make_double2(v[4], v[5]); else if (jmax == 4) dst[4] = v[4];
+                        }
+                    } else {
 #pragma unroll
-                    for (int y = 0; y < 3; ++y)
-                        if (x + 1 < cnt) { *reinterpret_cast<double2 *>(dst + x) = make_double2(vals[x], vals[x + 1]); x += 2; }
-                    if (x < cnt) dst[x] = vals[x];
+                        for (int j = 0; j < 6; ++j)
+                            if (j <= jmax) {
+                                const int cc = base_c + j;
+                                tile_of(cc >> 5)[ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31)] = v[j];
+                            }
+                    }
                 } else {
-                    for (int x = 0; x < cnt; ++x) {
-                        const int cc = base_c + x, K = cc >> 5;
-                        tiles[((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS +
-                              (ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31))] = vals[x];
+                    // support node with some free DOFs: compact the columns (rare; entry by entry)
+                    int cc = base_c;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        if (sup_cond[6 * sc + j]) continue;        // fixed DOF: no solver column
+                        if (j <= jmax) tile_of(cc >> 5)[ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31)] = (dr * s6[j]) * dinv[cc];
+                        ++cc;
                     }
                 }
             }
@@ -475,7 +493,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 #pragma unroll 4
             for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) {
                 const int e = ne_elem[p];
-                const double qv = m.q[((size_t)lc * m.nE + e) * 12 + 6 * ne_end[p] + i];
+                const double qv = qtab[((size_t)lc * m.nE + e) * 12 + 6 * ne_end[p] + i];
                 qs += elem_on(s_mask, e) ? qv : 0.0;
             }
             pv += qs;
@@ -538,7 +556,7 @@ cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaS
 }
 
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
-                                      const uint32_t *masks, long long first, int count,
+                                      const uint32_t *masks, const int *geom, long long first, int count,
                                       const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st) {
     const size_t base = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
                         (size_t)m.n_tile_rows_max * m.band_tiles + 16;
@@ -549,7 +567,7 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
     cudaError_t e = ts ? cm_ensure_smem(k2_dofmap_assemble<true>, smem, cache[1], m.device)
                        : cm_ensure_smem(k2_dofmap_assemble<false>, smem, cache[0], m.device);
     if (e != cudaSuccess) return e;
-    if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out, ktilde_rowmajor);
-    else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, first, out, ktilde_rowmajor);
+    if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, first, out, ktilde_rowmajor);
+    else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, first, out, ktilde_rowmajor);
     return cudaGetLastError();
 }

@@ -85,9 +85,8 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     // share of this tile in the forward substitution of row I:  s_I += L(I,J) y_J
     {
         volatile int *yprog = CTX(yprog);
-        int y = *yprog;
-        while (y <= J) { __nanosleep(CM_SLEEP_NS); y = *yprog; }
-        __threadfence_block();
+        int y = flag_acquire(yprog);
+        while (y <= J) { __nanosleep(CM_SLEEP_NS); y = flag_acquire(yprog); }
     }
     FP_ADD(pc, 7);
     double2 dk[4];                                // pivots of block J for the diagonal term below: in flight with the y loads
@@ -211,7 +210,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
         for (int J = kfI; J < I; ++J) {
             handed = offdiag_tile<PROF>(I, J, kcI, lane);
-            __threadfence_block();
+            release_fence();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
         }
@@ -219,19 +218,18 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         if (!handed && I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
         FP_ADD(pc, 5);
         diag_factor_blk(I, handed, lane);
-        __threadfence_block();
+        release_fence();
         __syncwarp();
         if (lane == 0) { if (PROF) s_tpub = clock64(); prog[I] = I + 1; }
         FP_ADD(pc, 6);
         // forward substitution of row I once rows < I are done (they finish one chain step earlier)
         {
-            int y = *yprog;
-            while (y < I) { __nanosleep(CM_SLEEP_NS); y = *yprog; }
-            __threadfence_block();
+            int y = flag_acquire(yprog);
+            while (y < I) { __nanosleep(CM_SLEEP_NS); y = flag_acquire(yprog); }
         }
         FP_ADD(pc, 7);
         forward_row_w(I, lane);
-        __threadfence_block();
+        release_fence();
         __syncwarp();
         if (lane == 0) *yprog = I + 1;
         FP_ADD(pc, 8);

@@ -105,7 +105,7 @@ __device__ double block_nanmax(double v, double *s_red) {
 // the NB right-hand sides); the recovery below then runs per load case.
 template <bool XS, int NB>
 __global__ void __launch_bounds__(K4_THREADS)
-k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, long long first,
+k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, const int *geom, long long first,
                  cm_out_dev out) {
     static_assert(XS || NB == 1, "several right-hand sides per pass need the shared-memory vectors");
     __shared__ double s_red[K4_WARPS];
@@ -126,6 +126,9 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
     double *X = reinterpret_cast<double *>(slab + L.off_x);
     const double *P = reinterpret_cast<const double *>(slab + L.off_p);
     const uint32_t *mask = masks + (size_t)gs * m.mask_words;
+    const size_t gv = geom ? (size_t)min(max(geom[gs], 0), m.n_geom - 1) : 0;      // geometry variant of this subset
+    const double *Kg = m.Kg + gv * m.nE * 144;
+    const double *R3g = m.R3 + gv * m.nE * 9;
     const int bt = m.band_tiles, nV = m.nV, nE = m.nE, n_lc = m.n_lc;
     const int zero_bits = info[CM_INFO_ZERO_LOAD];
     const int n_pad = L.n_pad;
@@ -292,7 +295,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     int e = m.ne_elem[p];
                     if (!elem_on(mask, e)) continue;
                     ex = true;
-                    const double *krow = m.Kg + (size_t)e * 144 + (6 * m.ne_end[p] + i) * 12;
+                    const double *krow = Kg + (size_t)e * 144 + (6 * m.ne_end[p] + i) * 12;
                     int n0 = m.conn[2 * e], n1 = m.conn[2 * e + 1];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) acc += thr(krow[j]) * u_at(6 * n0 + j);
@@ -324,13 +327,13 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     double tv[3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        const double *krow = m.Kg + (size_t)e * 144 + (3 * pblk + a) * 12;
+                        const double *krow = Kg + (size_t)e * 144 + (3 * pblk + a) * 12;
                         double s = 0.0;
 #pragma unroll
                         for (int j = 0; j < 12; ++j) s += krow[j] * ue[j];
                         tv[a] = s;
                     }
-                    const double *R3 = m.R3 + (size_t)e * 9;
+                    const double *R3 = R3g + (size_t)e * 9;
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
                         d3[a] = -(R3[3 * a] * tv[0] + R3[3 * a + 1] * tv[1] + R3[3 * a + 2] * tv[2]);
@@ -379,20 +382,20 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
 }  // namespace
 
 template <int NB>
-static cudaError_t launch_k4_xs(const cm_model_dev &m, const cm_ws_layout &L, char *ws, const uint32_t *masks,
+static cudaError_t launch_k4_xs(const cm_model_dev &m, const cm_ws_layout &L, char *ws, const uint32_t *masks, const int *geom,
                                 long long first, int count, const cm_out_dev &out, cudaStream_t st) {
     const size_t xs_bytes = (size_t)(NB + 1) * L.n_pad * sizeof(double);      // NB solutions and the pivots
     static cm_smem_cache cache;
     cudaError_t e = cm_ensure_smem(k4_solve_recover<true, NB>, xs_bytes, cache, m.device);
     if (e != cudaSuccess) return e;
-    k4_solve_recover<true, NB><<<count, K4_THREADS, xs_bytes, st>>>(m, L, ws, masks, first, out);
+    k4_solve_recover<true, NB><<<count, K4_THREADS, xs_bytes, st>>>(m, L, ws, masks, geom, first, out);
     return cudaGetLastError();
 }
 
 // Load cases per pass over L: as many as keep the shared-memory vectors within 64 KB per CTA (the
 // kernel is HBM-bound through many resident CTAs), at most 4.  CM_K4_NB overrides (timing).
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
-                                    const uint32_t *masks, long long first, int count,
+                                    const uint32_t *masks, const int *geom, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st) {
     const size_t vec = (size_t)L.n_pad * sizeof(double);
     static const int nb_env = getenv("CM_K4_NB") ? atoi(getenv("CM_K4_NB")) : 0;
@@ -403,9 +406,9 @@ cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L
         if (m.n_lc >= 3 && 5 * vec <= 64 * 1024) nb = 4;
         if (nb_env == 1 || (nb_env == 2 && 3 * vec <= 200 * 1024) || (nb_env == 4 && 5 * vec <= 200 * 1024)) nb = nb_env;
     }
-    if (nb == 4) return launch_k4_xs<4>(m, L, ws, masks, first, count, out, st);
-    if (nb == 2) return launch_k4_xs<2>(m, L, ws, masks, first, count, out, st);
-    if (nb == 1) return launch_k4_xs<1>(m, L, ws, masks, first, count, out, st);
-    k4_solve_recover<false, 1><<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, first, out);
+    if (nb == 4) return launch_k4_xs<4>(m, L, ws, masks, geom, first, count, out, st);
+    if (nb == 2) return launch_k4_xs<2>(m, L, ws, masks, geom, first, count, out, st);
+    if (nb == 1) return launch_k4_xs<1>(m, L, ws, masks, geom, first, count, out, st);
+    k4_solve_recover<false, 1><<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, geom, first, out);
     return cudaGetLastError();
 }

@@ -68,6 +68,7 @@ class CudaStiffness(StiffnessBase):
         self._loadcase_list = None             # set_load_cases(): explicit multi load case table
         self._loads_dirty = True
         self._n_lc = 1
+        self._n_geom = 1
 
         self._has_stored_deformation = False
         self._stored_existing_ids = []
@@ -117,26 +118,40 @@ class CudaStiffness(StiffnessBase):
         nV, nE = self.nV, self.nE
         xyz = np.array([n.point for n in self._nodes], dtype=np.float64).reshape(nV, 3)
         conn = np.array([e.end_node_inds for e in self._elements], dtype=np.int32).reshape(nE, 2)
-        props = np.zeros((nE, 7))
-        cr = np.full((nE, 6), np.inf)
+        lengths = np.linalg.norm(xyz[conn[:, 0]] - xyz[conn[:, 1]], axis=1)
+        if (lengths < DOUBLE_EPS).any():
+            i = int(np.argmax(lengths < DOUBLE_EPS))
+            raise ValueError('E#{} - Bar length too small!: Node {} - Node {}'.format(i, xyz[conn[i, 0]], xyz[conn[i, 1]]))
+        # tag -> table row once per TAG (stiffness_base.py:131-156), then the per-element arrays in C
+        # (cm_pack_elements) instead of the reference's per-element Python loop
+        sec_rows, mat_rows, joint_rows = [], [], []
+        sec_of, mat_of, joint_of = np.empty(nE, np.int32), np.empty(nE, np.int32), np.full(nE, -1, np.int32)
+        by_tag = {}
         for i, element in enumerate(self._elements):
-            u, v = element.end_node_inds
-            L = np.linalg.norm(xyz[u] - xyz[v])
-            if L < DOUBLE_EPS:
-                raise ValueError('E#{} - Bar length too small!: Node {} - Node {}'.format(i, xyz[u], xyz[v]))
-            joint = self.get_element_joint(i)
-            if joint is not None:
-                c = joint.c_conditions
-                assert all([x is None or x == np.inf for x in c[0:3]]) and \
-                       all([x is None or x == np.inf for x in c[6:9]]), "We do not support translational joint now!"
-                cr[i, 0:3] = [np.inf if x is None else x for x in c[3:6]]
-                cr[i, 3:6] = [np.inf if x is None else x for x in c[9:12]]
-            if not element.bending_stiff:
-                cr[i, :] = 0.0
-            cs = self.get_element_crosssec(i)
-            mat = self.get_element_material(i)
-            assert abs(mat.E) > DOUBLE_EPS and abs(cs.Iz) > DOUBLE_EPS
-            props[i] = [cs.A, cs.Jx, cs.Iy, cs.Iz, mat.E, mat.mu, mat.density]
+            tag = element.elem_tag
+            if tag not in by_tag:
+                cs, mat, joint = self.get_element_crosssec(i), self.get_element_material(i), self.get_element_joint(i)
+                assert abs(mat.E) > DOUBLE_EPS and abs(cs.Iz) > DOUBLE_EPS
+                sec_rows.append([cs.A, cs.Jx, cs.Iy, cs.Iz])
+                mat_rows.append([mat.E, mat.mu, mat.density])
+                j = -1
+                if joint is not None:
+                    c = joint.c_conditions
+                    assert all([x is None or x == np.inf for x in c[0:3]]) and \
+                           all([x is None or x == np.inf for x in c[6:9]]), "We do not support translational joint now!"
+                    joint_rows.append([np.inf if x is None else x for x in list(c[3:6]) + list(c[9:12])])
+                    j = len(joint_rows) - 1
+                by_tag[tag] = (len(sec_rows) - 1, len(mat_rows) - 1, j)
+            sec_of[i], mat_of[i], joint_of[i] = by_tag[tag]
+        stiff = np.array([1 if e.bending_stiff else 0 for e in self._elements], dtype=np.uint8)
+        sections = np.array(sec_rows, dtype=np.float64).reshape(-1, 4)
+        materials = np.array(mat_rows, dtype=np.float64).reshape(-1, 3)
+        joints = np.array(joint_rows, dtype=np.float64).reshape(-1, 6)
+        props = np.zeros((nE, 7))
+        cr = np.zeros((nE, 6))
+        _capi.check(self._lib.cm_pack_elements(nE, _ptr(sec_of), _ptr(mat_of), _ptr(joint_of), _ptr(stiff), len(sections),
+                                               _ptr(sections), len(materials), _ptr(materials), len(joints),
+                                               _ptr(joints) if len(joints) else None, _ptr(props), _ptr(cr)))
         sup_node = np.array(list(self._supports.keys()), dtype=np.int32)
         sup_cond = np.zeros((len(sup_node), 6), dtype=np.uint8)
         for k, v in enumerate(sup_node):
@@ -249,6 +264,35 @@ class CudaStiffness(StiffnessBase):
         self._n_lc = n_lc
         self._loads_dirty = False
 
+    # ------------------------------------------------------------------ geometry variants
+    def set_geometries(self, node_points_list):
+        """Many models of ONE topology (e.g. the iterates of a shape optimisation): ``node_points_list`` is
+        a (G, nV, 3) array (or list of (nV, 3) arrays) of node coordinates in metres.  One launch of the
+        element kernel builds the tables of all G variants on the device; ``solve_many(...,
+        geometry=ids)`` then picks a variant per subset.  Replaces constructing one engine per shape
+        (``Model.from_data`` io_base.py:107-144 + numpy_stiffness.py:579-614)."""
+        xyz = np.ascontiguousarray(np.asarray(node_points_list, dtype=np.float64))
+        if xyz.ndim != 3 or xyz.shape[1:] != (self.nV, 3):
+            raise ValueError('node_points_list must have shape (G, {}, 3)'.format(self.nV))
+        for h in self._handles:
+            try:
+                _capi.check(self._lib.cm_set_geometries(h, xyz.shape[0], _ptr(xyz)))
+            except _capi.CmError as ex:
+                if 'Bar length too small' in str(ex):
+                    raise ValueError(str(ex))
+                raise
+        self._n_geom = xyz.shape[0]
+        self._element_k_list = self._rot_list = None
+        self._loads_dirty = True               # lumped element loads depend on the geometry
+
+    def n_geometries(self):
+        return int(self._lib.cm_geometry_count(self._handle))
+
+    def last_element_kernel_ms(self):
+        ms = C.c_double()
+        _capi.check(self._lib.cm_last_element_kernel_ms(self._handle, C.byref(ms)))
+        return ms.value
+
     # ------------------------------------------------------------------ tolerances
     def set_nodal_displacement_tol(self, transl_tol, rot_tol):
         self._trans_tol = transl_tol
@@ -279,12 +323,13 @@ class CudaStiffness(StiffnessBase):
                 'profile_flops': (B,), 'sigma_max': (B, L, nE), 'max_abs_sigma': (B, L),
                 'profile_entries': (B,), 'envelope_tiles': (B,)}
 
-    def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):
+    def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None, geometry=None):
         """Solve B element subsets (list of id lists, [] = full structure, or a (B, words)
         uint32 mask matrix) with HOST buffers: masks are copied to the GPU, the kernels run, and
         the requested outputs are copied back.  Returns {name: ndarray}; see ``cm_solve_out``
         in include/conmech_b200.h for names and shapes.  ``out`` may hold preallocated
-        (e.g. pinned) arrays to write into."""
+        (e.g. pinned) arrays to write into.  ``geometry``: one geometry-variant index per subset
+        (``set_geometries``), default variant 0."""
         self._push_loads()
         masks0 = as_mask_matrix(subsets, self._info.mask_words)
         prepacked = masks0 is not None
@@ -307,10 +352,19 @@ class CudaStiffness(StiffnessBase):
 
         if B == 0:
             return res
-        if prepacked or B < 2 * self.PIPELINE_CHUNK:
+        geom = None
+        if geometry is not None:
+            geom = np.ascontiguousarray(np.asarray(geometry, dtype=np.int32).reshape(-1))
+            if geom.size != B:
+                raise ValueError('geometry must hold one variant index per subset')
+        if geom is not None or prepacked or B < 2 * self.PIPELINE_CHUNK:
             masks = masks0 if prepacked else pack_masks(subsets, self.nE)
             oh = out_struct()
-            if len(self._handles) > 1:
+            if geom is not None:
+                if len(self._handles) > 1:
+                    raise NotImplementedError('geometry variants on several devices: shard the batch and use one engine per device')
+                _capi.check(self._lib.cm_solve_many_host_g(self._handle, _ptr(masks), _ptr(geom), B, C.byref(oh)))
+            elif len(self._handles) > 1:
                 hs = (C.c_void_p * len(self._handles))(*[h.value for h in self._handles])
                 _capi.check(self._lib.cm_solve_many_host_multi(hs, len(self._handles), _ptr(masks), B, C.byref(oh)))
             else:
@@ -378,7 +432,7 @@ class CudaStiffness(StiffnessBase):
     PIPELINE_CHUNK = 2048          # subsets per pipelined chunk of solve_many (id lists only)
 
     def solve_many_device(self, masks, want=('flag', 'status', 'max_trans', 'compliance'), out=None,
-                          max_in_flight=None):
+                          max_in_flight=None, geometry=None):
         """Same on DEVICE buffers: ``masks`` is a (B, words) int32/uint32 torch CUDA tensor; outputs
         are torch CUDA tensors; kernels are enqueued on torch's current stream and the call
         returns without synchronising."""
@@ -411,8 +465,12 @@ class CudaStiffness(StiffnessBase):
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._ws_cache = {key: ws}
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _capi.check(self._lib.cm_solve_many(self._handle, masks.data_ptr(), B, C.byref(od), ws.data_ptr(),
-                                            ws.numel(), stream))
+        gptr = 0
+        if geometry is not None:              # (B,) int32 CUDA tensor of geometry-variant indices
+            assert geometry.is_cuda and geometry.dtype == torch.int32 and geometry.numel() == B and geometry.is_contiguous()
+            gptr = geometry.data_ptr()
+        _capi.check(self._lib.cm_solve_many_g(self._handle, masks.data_ptr(), gptr, B, C.byref(od), ws.data_ptr(),
+                                              ws.numel(), stream))
         return res
 
     def kernel_launches(self):

@@ -100,6 +100,26 @@ class StiffnessChecker(object):
         r = self._sc_ins.solve_many(list_of_existing_ids, want=('flag', 'sigma_max'))
         return r['sigma_max'][:, 0].copy()
 
+    def solve_shapes(self, node_points_list, existing_ids=None, return_details=False):
+        """Stiffness check of G geometry variants of this frame - same elements, sections, joints and
+        supports, node coordinates ``node_points_list[g]`` ((nV, 3), metres) - in one batched pass; the
+        loop a shape optimiser around the reference runs as "new Model, new StiffnessChecker, solve" per
+        iterate (``Model.from_data`` io_base.py:107-144).  ``existing_ids`` may hold
+        one element subset per variant (default: the full structure).  Loads are those set on this
+        checker; self weight and lumped line loads follow each variant's member lengths and axes.  The
+        variants stay installed (``solve_many(..., )`` afterwards refers to variant 0)."""
+        eng = self._sc_ins
+        eng.set_geometries(node_points_list)
+        G = eng.n_geometries()
+        subsets = list(existing_ids) if existing_ids is not None else [[] for _ in range(G)]
+        if len(subsets) != G:
+            raise ValueError('existing_ids must hold one id list per geometry variant')
+        r = eng.solve_many(subsets, want=('flag', 'status', 'max_trans', 'compliance'), geometry=np.arange(G, dtype=np.int32))
+        flags = [bool(f) for f in r['flag'][:, 0]]
+        if return_details:
+            return flags, {k: r[k][:, 0].copy() for k in ('status', 'max_trans', 'compliance')}
+        return flags
+
     def solve_sequence(self, order, return_details=False):
         """Stiffness check of EVERY prefix of a construction sequence in one batched pass: flag k
         is ``solve(order[:k+1])``.  This is the loop the sequencing planners around the reference

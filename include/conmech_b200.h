@@ -81,6 +81,17 @@ typedef struct cm_model_info {
     int64_t profile_flops_full;/* sum_j h_j^2 of the full structure in the solver ordering       */
 } cm_model_info;
 
+/* Per-element property arrays of cm_model_desc from per-tag tables (host arrays; no GPU involved):
+ * the C side of the reference's per-element Python loop (numpy_stiffness.py:579-614, tag lookups
+ * stiffness_base.py:131-156 done by the caller once per TAG).  sec_of / mat_of [n_elems] index into
+ * sections [n_sec*4] (A, Jx, Iy, Iz) / materials [n_mat*3] (E, mu, density); joint_of [n_elems] (may be
+ * NULL) indexes joints [n_joint*6] (rotational end springs x,y,z at end 0 then end 1, +inf = rigid) or
+ * is -1 = no joint; bending_stiff [n_elems] (may be NULL = all true).  Writes props [n_elems*7] and
+ * cr [n_elems*6] as cm_model_desc wants them. */
+int cm_pack_elements(int32_t n_elems, const int32_t *sec_of, const int32_t *mat_of, const int32_t *joint_of,
+                     const uint8_t *bending_stiff, int32_t n_sec, const double *sections, int32_t n_mat,
+                     const double *materials, int32_t n_joint, const double *joints, double *props, double *cr);
+
 int cm_create(const cm_model_desc *desc, cm_handle **out);
 int cm_destroy(cm_handle *h);
 int cm_get_info(const cm_handle *h, cm_model_info *info);
@@ -93,6 +104,22 @@ int cm_get_element_tables(cm_handle *h, double *Kg /*[nE*144]*/, double *R3 /*[n
 
 /* Static solver ordering (position -> node id), host array [n_nodes]. */
 int cm_get_node_order(const cm_handle *h, int32_t *order);
+
+/* Geometry variants (many models of one topology, e.g. the iterates of a shape
+ * optimisation).  Replaces constructing one reference engine per shape (Model.from_data io_base.py:107-144
+ * + NumpyStiffness._precompute_element_stiffness_matrices numpy_stiffness.py:579-614, a Python loop over the
+ * elements per model): xyz holds n_geom sets of node coordinates [n_geom*n_nodes*3] (host, metres);
+ * connectivity, sections, materials, joints and supports are those of the handle.  ONE launch of the
+ * element kernel builds the stiffness / rotation tables of all n_geom*n_elems elements (HBM-bound for
+ * many variants); every subset of a later cm_solve_many*_g call picks its variant by index.  The
+ * variants replace the handle's geometry (variant 0 need not be the original); the load cases must be
+ * set again afterwards (lumped element loads depend on member lengths and axes). */
+int cm_set_geometries(cm_handle *h, int32_t n_geom, const double *xyz);
+int32_t cm_geometry_count(const cm_handle *h);
+/* element tables of variant g, host arrays (any may be NULL) */
+int cm_get_geometry_tables(cm_handle *h, int32_t g, double *Kg /*[nE*144]*/, double *R3 /*[nE*9]*/);
+/* device milliseconds (CUDA events) of the most recent element-table launch (cm_create / cm_set_geometries) */
+int cm_last_element_kernel_ms(const cm_handle *h, double *ms);
 
 /* Load cases, host pointers.  Replaces set_load / set_uniformly_distributed_loads /
  * set_self_weight_load (numpy_stiffness.py:98-138); n_lc load cases are solved per subset.
@@ -161,6 +188,11 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t subsets_in_flight);
 int cm_solve_many(cm_handle *h, uint64_t masks_dev, int64_t B, const cm_solve_out *out,
                   uint64_t workspace_dev, size_t workspace_bytes, uint64_t stream);
 
+/* cm_solve_many with a geometry variant per subset: geom_dev = i32 [B] device array of variant indices
+ * (0 = all subsets use variant 0; out-of-range indices are clamped - the host entry below rejects them). */
+int cm_solve_many_g(cm_handle *h, uint64_t masks_dev, uint64_t geom_dev, int64_t B, const cm_solve_out *out,
+                    uint64_t workspace_dev, size_t workspace_bytes, uint64_t stream);
+
 /* Same, with HOST buffers: masks and every non-NULL output are host arrays (pinned memory lets
  * the copies overlap the kernels; pageable memory works, serialised by the driver).  The call
  * copies the masks host->device, runs the kernels wave by wave and drains every finished wave's
@@ -190,6 +222,10 @@ typedef struct cm_solve_out_host {
 
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,
                        const cm_solve_out_host *out);
+/* ... with a geometry variant per subset (geom_host i32 [B], NULL = variant 0; an index outside
+ * [0, cm_geometry_count) is CM_ERR_INVALID) */
+int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, int64_t B,
+                         const cm_solve_out_host *out);
 
 /* The same batch in consecutive chunks of `chunk` subsets, for a caller that is still PRODUCING the
  * masks while the first chunks are solved (the Python facade packs id lists - the reference's

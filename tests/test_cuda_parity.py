@@ -480,6 +480,62 @@ def test_two_gpus_one_process_bit_exact():
         assert_array_equal(res[0][k], res[2][k], err_msg=k)
 
 
+def test_geometry_variants_many_models():
+    """many models of one topology.  G jittered shapes of a jointed grid (the element kernel
+    builds all G x nE tables in one launch), a subset per shape, two load cases - against the oracle built
+    from a fresh Model per shape, as a caller of the reference would do it."""
+    import copy
+    from conmech_b200 import synthetic as syn, StiffnessChecker, LoadCase, GravityLoad, PointLoad
+    dims = (4, 4, 5)
+    model = syn.grid_frame(*dims, joints=True, diagonals=True)
+    nV, nE = len(model.nodes), len(model.elements)
+    rng = np.random.RandomState(3)
+    base = np.array([n.point for n in model.nodes], dtype=float)
+    G = 7
+    shapes = np.stack([base] + [base + rng.uniform(-0.12, 0.12, size=base.shape) for _ in range(G - 1)])
+    lcs = [LoadCase(gravity_load=GravityLoad([0, 0, -1])),
+           LoadCase(point_loads=[PointLoad([0.3, -0.2, -1.0], [0, 0, 0], nV - 1)], gravity_load=GravityLoad([0.1, 0, -1]))]
+    sc = StiffnessChecker(model, checker_engine='cuda')
+    sc.set_load_cases(lcs)
+    eng = sc._sc_ins
+    eng.set_geometries(shapes)
+    assert eng.n_geometries() == G
+    subsets = [[]] + [syn.heightfield_subset(model, *dims, seed=s) for s in range(40, 40 + G - 1)]
+    geom = np.arange(G, dtype=np.int32)
+    r = eng.solve_many(subsets, want=ALL, geometry=geom)
+    # the same batch on device buffers, variants in reverse order
+    import torch
+    masks = syn.pack_masks(subsets, nE)[::-1].copy()
+    rd = eng.solve_many_device(torch.from_numpy(masks.view(np.int32)).cuda(), want=('U', 'flag'),
+                               geometry=torch.from_numpy(geom[::-1].copy()).cuda())
+    torch.cuda.synchronize()
+    assert_array_equal(rd['U'].cpu().numpy()[::-1], r['U'])
+    n_checked = 0
+    for g in range(G):
+        mg = copy.deepcopy(model)
+        for n, pt in zip(mg.nodes, shapes[g]):
+            n.point = [float(x) for x in pt]
+        for li, lc in enumerate(lcs):
+            orc = FrameOracle(mg)
+            orc.set_loads(lc)
+            rg = {k: v[g:g + 1] for k, v in r.items()}
+            check_against_oracle(eng, orc, [subsets[g]], rg, lc=li, tag='shapes-g{}-lc{}'.format(g, li))
+            n_checked += 1
+    assert n_checked == 2 * G
+    # facade: one flag per shape; a collapsed member is a programmer error like in the reference (ValueError)
+    sc2 = StiffnessChecker(model, checker_engine='cuda')
+    sc2.set_loads(lcs[0])
+    flags, det = sc2.solve_shapes(shapes, return_details=True)
+    assert len(flags) == G and det['max_trans'][0] == r['max_trans'][0, 0]      # shape 0, full structure, load case 0
+    assert_array_equal(det['status'], np.zeros(G, dtype=np.uint8))
+    bad = shapes.copy()
+    bad[2, model.elements[0].end_node_inds[0]] = bad[2, model.elements[0].end_node_inds[1]]
+    with pytest.raises(ValueError):
+        sc2.solve_shapes(bad)
+    with pytest.raises(Exception):
+        eng.solve_many([[]], geometry=[G])          # no such variant
+
+
 @pytest.mark.parametrize('n_lc', [4, 3, 2])
 def test_config4_multi_loadcase(n_lc):
     """BASELINE config 4: joints on horizontals, height-field subsets, several load cases solved

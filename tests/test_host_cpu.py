@@ -132,6 +132,45 @@ def test_native_mask_packer_matches_numpy():
         masks.pack_masks_csr(np.array([1, 2]), np.array([0, 3]), nE)
 
 
+def test_pack_elements_matches_the_reference_rules():
+    """cm_pack_elements (host-only C function of the library): per-element property / spring arrays from
+    per-tag tables, against the per-element rules of numpy_stiffness.py:579-614 written out in Python."""
+    import ctypes as C
+    from conmech_b200 import _capi, synthetic as syn
+    lib = _capi.load()
+    model = syn.grid_frame(4, 4, 4, joints=True)
+    model.elements[5].bending_stiff = False
+    nE = len(model.elements)
+    tags = sorted(set(e.elem_tag for e in model.elements))
+    jt = {j_tag: k for k, j in enumerate(model.joints) for j_tag in j.elem_tags}
+    sections = np.array([[cs.A, cs.Jx, cs.Iy, cs.Iz] for cs in model.crosssecs])
+    materials = np.array([[m.E, m.mu, m.density] for m in model.materials])
+    joints = np.array([[np.inf if x is None else x for x in list(j.c_conditions[3:6]) + list(j.c_conditions[9:12])]
+                       for j in model.joints])
+    sec_of = np.zeros(nE, np.int32)
+    mat_of = np.zeros(nE, np.int32)
+    joint_of = np.array([jt.get(e.elem_tag, -1) for e in model.elements], dtype=np.int32)
+    stiff = np.array([1 if e.bending_stiff else 0 for e in model.elements], dtype=np.uint8)
+    props, cr = np.zeros((nE, 7)), np.zeros((nE, 6))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.cm_pack_elements(nE, p(sec_of), p(mat_of), p(joint_of), p(stiff), len(sections), p(sections), len(materials),
+                              p(materials), len(joints), p(joints), p(props), p(cr))
+    assert rc == 0, lib.cm_last_error()
+    assert len(tags) == 4
+    for i, e in enumerate(model.elements):
+        assert_array_equal(props[i], list(sections[0]) + list(materials[0]))
+        want = np.full(6, np.inf)
+        if joint_of[i] >= 0:
+            want = joints[joint_of[i]]
+        if not e.bending_stiff:
+            want = np.zeros(6)
+        assert_array_equal(cr[i], want)
+    sec_of[3] = 7                                   # out-of-range table row
+    assert lib.cm_pack_elements(nE, p(sec_of), p(mat_of), p(joint_of), p(stiff), len(sections), p(sections), len(materials),
+                                p(materials), len(joints), p(joints), p(props), p(cr)) == -1
+    assert b'does not exist' in lib.cm_last_error()
+
+
 def test_model_io_roundtrip(models_dir):
     from conmech_b200 import Model, LoadCase
     for f in sorted(os.listdir(models_dir)):

@@ -22,7 +22,7 @@ for ln in open(disasm):
     if m:
         name = m.group(1)
         mm = re.findall(r'\d+([a-z_]+[a-z0-9_]*)', name.split('$')[-1])
-        func = next((x for x in mm if x in ('offdiag_tile', 'diag_factor_blk', 'forward_row_w', 'k3_factor_flow')), name[-40:])
+        func = next((x for x in mm if x in ('offdiag_tile', 'diag_factor_blk', 'forward_row_w', 'k3_factor_flow', 'k2_dofmap_assemble', 'k4_solve_recover')), name[-40:])
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
