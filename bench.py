@@ -284,6 +284,38 @@ def other_configs_gpu(torch, np, dev, cpu_rates):
                                             'full results on device'})
     del sc, eng, r, dm
     torch.cuda.empty_cache()
+
+    # SURVEY 8f-4, many models of one topology: G shape variants of the config-3 frame, the element kernel over
+    # all G x nE elements in one launch (HBM-bound), then one full-structure solve per variant
+    model = syn.grid_frame(7, 7, 8)
+    nE, nV = len(model.elements), len(model.nodes)
+    base = np.array([n.point for n in model.nodes], dtype=float)
+    G = 4096
+    shapes = np.stack([syn.shape_variant(base, s) for s in range(G)])
+    sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)
+    eng = sc._sc_ins
+    t0 = time.perf_counter()
+    eng.set_geometries(shapes)
+    t_set = time.perf_counter() - t0
+    k1_ms = eng.last_element_kernel_ms()
+    sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    masks = torch.from_numpy(syn.pack_masks([[]] * G, nE).view(np.int32)).to(dev)
+    gidx = torch.arange(G, dtype=torch.int32, device=dev)
+    r = {}
+
+    def run_shapes():
+        r['o'] = eng.solve_many_device(masks, want=FULL, out=r.get('o'), geometry=gidx)
+    ms = timed(run_shapes, 3)
+    k1_bytes = G * nE * (152 + 153 * 8 + 8)                    # 152 B in, (144 + 9) doubles out (+ the member length)
+    hbm_peak, _ = measured_peaks()
+    with_cpu('many_shapes_one_topology', {
+        'value': G / (ms * 1e-3 + t_set), 'unit': 'shapes/s', 'shapes': G, 'solve_ms': ms, 'set_geometries_ms': 1e3 * t_set,
+        'k1_ms': k1_ms, 'k1_elements': G * nE, 'k1_gbs': k1_bytes / (k1_ms * 1e-3) / 1e9, 'k1_frac_of_hbm': k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak,
+        'status_ok': int((r['o']['status'] == 0).sum().item()),
+        'what': '4096 geometry variants (node coordinates jittered) of the 7x7x8 frame: cm_set_geometries (host upload + ONE element-kernel '
+                'launch over 3.8 M elements) + one full-structure solve per variant, full results on device; value counts both'})
+    del sc, eng, r
+    torch.cuda.empty_cache()
     return out
 
 
@@ -420,6 +452,16 @@ def main():
         barrier()
         return world * B * args.steps / max_over_ranks(dt)
 
+    # raw device->host rate of this box for pinned memory (one 1 GiB copy): what bounds the full-result leg
+    probe_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    probe_h = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    probe_h.copy_(probe_d, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); probe_h.copy_(probe_d, non_blocking=True); e1.record(); torch.cuda.synchronize(dev)
+    pcie_d2h_gbs = (1 << 30) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del probe_d, probe_h
+    torch.cuda.empty_cache()
     e2e_full = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=FULL, out=out_host))
     d2h_full = int(sum(out_host[n].nbytes for n in FULL))
     # the host path and the device path deliver the same bits
@@ -565,6 +607,10 @@ def main():
                 'e2e': {'value': e2e_full, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_full,
                         'outputs': 'U, Rf, eR, flag, status, max_trans, compliance per subset (pinned host arrays)',
                         'd2h_gbs': d2h_full * e2e_full / (world * B) / 1e9,
+                        'pcie_d2h_gbs_measured': pcie_d2h_gbs,
+                        'fraction_of_device_resident': e2e_full / value,
+                        'note': 'every wave\'s results are copied to the host by a copy stream while later waves compute; what is left '
+                                'is the copy of the last waves, which finish together',
                         'flags_only_value': e2e_flags, 'flags_only_d2h_bytes_per_step': d2h_flags,
                         'id_lists_value': e2e_lists,
                         'id_lists_what': 'StiffnessChecker.solve_many(list of Python id lists) -> list of bools, packing included'},

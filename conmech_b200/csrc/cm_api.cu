@@ -353,6 +353,8 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
 
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    // (lanes of descending stream priority - so that the waves of a call finish staggered - were measured: slower,
+    // 55.3 against 49.0 ms per 12 500 full-result subsets; profiles/r02_experiments.txt)
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -631,7 +633,9 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
 // lanes' kernels fill the SMs it frees.  Every wave is independent (own subsets, own outputs, own
 // share of the workspace).
 struct WavePlan { bool lanes; int NL; long long cap, n_waves, wsize; };
-static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *p) {
+// max_wave > 0: upper bound for the subsets of one wave (the host entry point with large outputs wants waves whose
+// device->host copy is short, see cm_solve_many_host_g)
+static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *p, long long max_wave = 0) {
     const size_t per = h->L.per_subset;
     long long wave = (long long)(ws_bytes / per);
     if (wave < 1) return fail(CM_ERR_NOMEM, "cm_solve_many: workspace smaller than one subset (" + std::to_string(per) + " bytes)");
@@ -640,6 +644,7 @@ static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *
     p->NL = h->n_lanes;
     p->lanes = !h->timing && h->overlap && p->NL > 1 && h->lane_stream[0] && B > wave / p->NL && wave / p->NL >= sm_fill;
     p->cap = p->lanes ? wave / p->NL : wave;
+    if (max_wave > 0 && p->cap > std::max<long long>(max_wave, sm_fill)) p->cap = std::max<long long>(max_wave, sm_fill);
     p->n_waves = (B + p->cap - 1) / p->cap;
     if (p->lanes && getenv("CM_WAVE_ROUND") && atoi(getenv("CM_WAVE_ROUND")) && p->n_waves % p->NL) p->n_waves += p->NL - p->n_waves % p->NL;   // experiment: same number of waves per lane
     p->wsize = (B + p->n_waves - 1) / p->n_waves;
@@ -824,11 +829,19 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
         CU(cudaMalloc((void **)&h->wsbuf, want));
         h->ws_bytes = want;
     }
-    WavePlan P;
-    { int rc = plan_waves(h, B, h->ws_bytes, &P); if (rc != CM_OK) return rc; }
     // device staging: the masks of the batch, then CM_STAGE_SLOTS slots of one wave's outputs each
     OutItem it[N_OUT];
     out_items(h, o, it);
+    // A wave's results leave for the host when its last kernel has finished, and the copies of consecutive waves
+    // queue on one copy engine: with full results (127 KB per subset on the 1k-element frame) a wave of 2500 subsets
+    // is a 6 ms copy, and the last waves of all lanes finish together - their copies are an unhidden tail.  Large
+    // outputs therefore run in waves of about 64 MB of results (never below what fills the GPU twice).
+    size_t out_per_subset = 0;
+    for (int i = 0; i < N_OUT; ++i) if (it[i].host) out_per_subset += it[i].stride;
+    static const long long wave_mb = getenv("CM_HOST_WAVE_MB") ? atoll(getenv("CM_HOST_WAVE_MB")) : 64;
+    const long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
+    WavePlan P;
+    { int rc = plan_waves(h, B, h->ws_bytes, &P, max_wave); if (rc != CM_OK) return rc; }
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t mask_bytes = al(Bn * m.mask_words * 4);
     size_t slot_bytes = 0;

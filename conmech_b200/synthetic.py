@@ -150,6 +150,13 @@ def heightfield_subset(model, nx, ny, nz, seed):
     return [e.elem_ind for e in model.elements if exists(e.end_node_inds[0]) and exists(e.end_node_inds[1])]
 
 
+def shape_variant(base_points, seed, amplitude=0.1):
+    """Node coordinates of geometry variant ``seed`` of a frame (many models of one topology):
+    every coordinate of ``base_points`` ((nV, 3), metres) moved by U(-amplitude, amplitude), seeded."""
+    rng = np.random.RandomState(seed)
+    return np.asarray(base_points, dtype=float) + rng.uniform(-amplitude, amplitude, size=np.shape(base_points))
+
+
 def config4_loadcases(model, seed=0):
     """The four load cases of config 4."""
     rng = random.Random(seed)

@@ -188,6 +188,56 @@ OTHER_CONFIGS = {
 }
 
 
+def _shapes_worker(args):
+    """Reference cost of one geometry variant: a new Model (coordinates jittered like bench.py does), a new
+    checker (element tables: numpy_stiffness.py:579-614), loads, one full-structure solve."""
+    seeds, kind = args
+    import contextlib
+    import copy
+    import io
+    import warnings
+    import numpy as np
+    warnings.simplefilter('ignore')
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad
+    model = syn.grid_frame(7, 7, 8)
+    base = np.array([n.point for n in model.nodes], dtype=float)
+    lc = LoadCase(gravity_load=GravityLoad([0, 0, -1]))
+    n_ok = 0
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        for s in seeds:
+            pts = syn.shape_variant(base, s)
+            mg = copy.deepcopy(model)
+            for n, pt in zip(mg.nodes, pts):
+                n.point = [float(x) for x in pt]
+            if kind == 'reference':
+                from oracle import ref_bridge
+                sc = ref_bridge.make_ref_checker(mg, lc, 1e-3)
+                n_ok += 1 if sc.solve([]) else 0
+            else:
+                from oracle.frame_oracle import FrameOracle
+                orc = FrameOracle(mg)
+                orc.set_loads(lc)
+                n_ok += 1 if orc.solve([]).success else 0
+    return time.perf_counter() - t0, len(seeds), n_ok
+
+
+def shapes_record(n_per_proc=3):
+    n_procs = os.cpu_count() or 1
+    kind = 'reference' if reference_available() else 'port'
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    seeds = list(range(n_per_proc * n_procs))
+    with ctx.Pool(n_procs) as pool:
+        pool.map(_shapes_worker, [([s], kind) for s in seeds[:n_procs]])            # warm-up
+        t0 = time.perf_counter()
+        pool.map(_shapes_worker, [(seeds[i::n_procs], kind) for i in range(n_procs)])
+        wall = time.perf_counter() - t0
+    return {'value': len(seeds) / wall, 'unit': 'shapes/s', 'cores': n_procs, 'kind': kind,
+            'sample': '{} shape variants of the 7x7x8 frame on {} processes, {:.1f} s: new Model + new checker + solve([]) each'.format(
+                len(seeds), n_procs, wall)}
+
+
 def other_configs_record():
     """CPU rates of configs 1, 2, 4 and 5 on bounded samples (a few seconds each)."""
     n_procs = os.cpu_count() or 1
@@ -197,6 +247,7 @@ def other_configs_record():
     out['config2_tower_bfs_prefixes'] = _rate_record(OTHER_CONFIGS['config2_tower_bfs_prefixes'], 24, 1, kind)
     out['config4_joints_4_loadcases'] = _rate_record(OTHER_CONFIGS['config4_joints_4_loadcases'], 6 * n_procs, n_procs, kind)
     out['config5_10k_frame'] = _rate_record(OTHER_CONFIGS['config5_10k_frame'], n_procs, n_procs, kind)
+    out['many_shapes_one_topology'] = shapes_record()
     return out
 
 
