@@ -558,41 +558,43 @@ def main():
         except Exception as ex:          # never lose the headline line to a secondary leg
             others = {'error': repr(ex)}
 
-    # ---- one process, all GPUs (N > 1): rank 0 drives every device through cm_solve_many_host_multi
+    # ---- one process, all GPUs (N > 1): rank 0 drives every device through cm_solve_many_host_multi.  The other
+    # ranks leave first (a rank waiting in an NCCL barrier keeps a spinning kernel on its GPU, which is what this leg
+    # would then measure): the process group is torn down on every rank, ranks > 0 exit, rank 0 goes on alone.
     single = None
     if world > 1:
-        eng._ws_cache = {}
+        eng.close()
         torch.cuda.empty_cache()
         barrier()
-        if rank == 0:
-            try:
-                scm = StiffnessChecker(model, checker_engine='cuda', devices=list(range(world)))
-                scm.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
-                scm.set_nodal_displacement_tol(trans_tol=TRANS_TOL)
-                em = scm._sc_ins
-                BG = B * world
-                mm = syn.pack_masks([syn.connected_subset(model, s) for s in range(BG)], nE)
-                mm = torch.from_numpy(mm.view(np.int32)).pin_memory().numpy().view(np.uint32)
-                oh = {'flag': pin((BG, 1), torch.uint8), 'status': pin((BG, 1), torch.uint8),
-                      'max_trans': pin((BG, 1), torch.float64), 'compliance': pin((BG, 1), torch.float64)}
-                res = {}
-                for want, name in ((SCALARS, 'flags_only_value'),):
-                    for _ in range(2):
-                        em.solve_many(mm, want=want, out=oh)
-                    t0 = time.perf_counter()
-                    reps = max(2, args.steps // 2)
-                    for _ in range(reps):
-                        em.solve_many(mm, want=want, out=oh)
-                    res[name] = BG * reps / (time.perf_counter() - t0)
-                single = {'n_gpus': world, 'unit': UNIT, 'subsets_per_call': BG, 'value': res['flags_only_value'],
-                          'outputs': 'flag,status,max_trans,compliance',
-                          'what': 'ONE process, one handle and one host thread per GPU (cm_solve_many_host_multi): pinned host '
-                                  'masks in, results written by every device straight into the caller\'s arrays (the host '
-                                  'gather) inside the timed region; host wall clock'}
-                del scm, em
-            except Exception as ex:
-                single = {'error': repr(ex)}
-        barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+        time.sleep(3.0)                     # the other ranks' contexts are going away
+        try:
+            scm = StiffnessChecker(model, checker_engine='cuda', devices=list(range(world)))
+            scm.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+            scm.set_nodal_displacement_tol(trans_tol=TRANS_TOL)
+            em = scm._sc_ins
+            BG = B * world
+            mm = syn.pack_masks([syn.connected_subset(model, s) for s in range(BG)], nE)
+            mm = torch.from_numpy(mm.view(np.int32)).pin_memory().numpy().view(np.uint32)
+            oh = {'flag': pin((BG, 1), torch.uint8), 'status': pin((BG, 1), torch.uint8),
+                  'max_trans': pin((BG, 1), torch.float64), 'compliance': pin((BG, 1), torch.float64)}
+            for _ in range(2):
+                em.solve_many(mm, want=SCALARS, out=oh)
+            t0 = time.perf_counter()
+            reps = max(2, args.steps // 2)
+            for _ in range(reps):
+                em.solve_many(mm, want=SCALARS, out=oh)
+            rate = BG * reps / (time.perf_counter() - t0)
+            single = {'n_gpus': world, 'unit': UNIT, 'subsets_per_call': BG, 'value': rate,
+                      'outputs': 'flag,status,max_trans,compliance',
+                      'what': 'ONE process, one handle and one host thread per GPU (cm_solve_many_host_multi): pinned host '
+                              'masks in, results written by every device straight into the caller\'s arrays (the host '
+                              'gather) inside the timed region; host wall clock; run after the SPMD ranks have exited'}
+            em.close()
+        except Exception as ex:
+            single = {'error': repr(ex)}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -622,8 +624,6 @@ def main():
         if single is not None:
             line['single_process'] = single
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

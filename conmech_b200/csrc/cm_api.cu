@@ -611,7 +611,7 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
 
 int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
-    if (variant < 0 || variant > 9) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..9 (7/8/9: 2-/3-/1-warp CTAs, timing experiments)");
+    if (variant < 0 || variant > 12) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..12 (7/8/9: 2-/3-/1-warp CTAs; 10/11/12: operand ring)");
     h->variant = variant;
     return CM_OK;
 }
@@ -701,7 +701,8 @@ static int run_waves(cm_handle *h, const uint32_t *masks, const int *geom, int64
         else
         {
             // variant -> CTA configuration of the dataflow kernel (0 automatic, 1: 8 warps, 2: 4 warps, 3: 16 warps)
-            const int cfg = h->variant == 1 ? 0 : (h->variant >= 7 ? h->variant - 3 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2)));   // 7/8/9: 2/3/1 warps
+            const int cfg = h->variant >= 10 ? h->variant :
+                            h->variant == 1 ? 0 : (h->variant >= 7 ? h->variant - 3 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2)));   // 7/8/9: 2/3/1 warps; 10-12: operand ring
             CU(cm_launch_factor_flow(h->m, h->L, lws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, ls));
         }
         if (h->timing) CU(cudaEventRecord(h->ev[2], ls));

@@ -26,6 +26,8 @@ struct K3Ctx {
     const int *kcol; const unsigned long long *arow; int *prog; int *yprog;
     double *s_part; double *s_rhs; double *s_scr; double *s_minpiv; int *s_fail; double2 *s_dacc;
     long long *pc; long long *tpub;
+    unsigned ring0, ringbar0;      // operand ring (OPS builds): shared-window address of warp 0's stages / barriers
+    unsigned *ring_it;             // [NW] pairs each warp has consumed so far (stage index and barrier phase follow from it)
     int bt, n_pad, n_lc, zero_bits;
 };
 __shared__ K3Ctx s_ctx;
@@ -51,7 +53,12 @@ __device__ __forceinline__ int flag_acquire(const volatile int *p) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(const_cast<const int *>(p))) : "memory");
     return v;
 }
-__device__ __forceinline__ void release_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+// (OPS builds read the tiles through the bulk-copy engine, i.e. from L2: their producers fence at GPU scope)
+template <int OPS = 0>
+__device__ __forceinline__ void release_fence() {
+    if (OPS) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    else asm volatile("fence.acq_rel.cta;" ::: "memory");
+}
 __device__ __forceinline__ int wait_prog_gt(volatile int *prog, int J, int K) {
     int p = flag_acquire(prog + J);
     while (p <= K) { __nanosleep(CM_SLEEP_NS); p = flag_acquire(prog + J); }

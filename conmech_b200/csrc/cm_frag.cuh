@@ -174,6 +174,73 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
     }
 }
 
+// ---- operand ring in shared memory, filled by the bulk-copy engine (TMA, cp.async.bulk + mbarrier)
+// The operand streams are linear in memory (one k-step of a tile row = 1 KB of A or B, consecutive k-steps and tiles
+// contiguous), so a stage of the ring - one PAIR of k-steps: 2 KB of A, 2 KB of B, 64 bytes of pivots - is three 1-D
+// bulk copies issued by one lane, completing on the stage's mbarrier.  NST stages per warp run ahead of the MMAs: the
+// L2 / DRAM latency of the operands no longer sits in registers (one k-step of look-ahead), but in shared memory
+// (2 NST k-steps).  Producer and consumer are the same warp, so a stage is refilled in program order after the warp
+// has read it (no "empty" barriers).  Costs 4.1 KB of shared memory per stage and warp.
+#define CM_RING_STAGE_BYTES 4224u       // 2048 A + 2048 B + 64 pivots, padded to a multiple of 128
+struct OpRing { unsigned stage0, bar0, it; };     // shared-window addresses of the warp's stages and barriers; pairs consumed so far
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void lds4a(double (&v)[4], unsigned addr) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "r"(addr) : "memory");
+}
+
+// the update stream of acc_update_stream<false> with its operands taken from the ring
+template <int NST>
+__device__ __forceinline__ void acc_update_stream_ring(TileAcc &acc, const double *__restrict__ A, const double *__restrict__ B,
+                                                       const double *__restrict__ d, int nsteps, int lane, OpRing &R) {
+    const int npairs = nsteps >> 1;
+    auto issue = [&](int p, unsigned it) {          // lane 0: fill the stage of pair p
+        const unsigned s = it & (NST - 1), stage = R.stage0 + s * CM_RING_STAGE_BYTES, bar = R.bar0 + 8 * s;
+        mbar_expect(bar, 4160);
+        bulk_g2s(stage, A + (size_t)p * 256, 2048, bar);
+        bulk_g2s(stage + 2048, B + (size_t)p * 256, 2048, bar);
+        bulk_g2s(stage + 4096, d + (size_t)p * 8, 64, bar);
+    };
+    if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");     // the tiles were written through the generic proxy (by other warps)
+        for (int p = 0; p < NST && p < npairs; ++p) issue(p, R.it + p);
+    }
+#pragma unroll 1
+    for (int p = 0; p < npairs; ++p) {
+        const unsigned it = R.it + p, s = it & (NST - 1);
+        mbar_wait(R.bar0 + 8 * s, (it / NST) & 1);
+        const unsigned st = R.stage0 + s * CM_RING_STAGE_BYTES;
+        double a0[4], b0[4], a1[4], b1[4], d0, d1;
+        lds4a(a0, st + lane * 32);
+        lds4a(b0, st + 2048 + lane * 32);
+        lds4a(a1, st + 1024 + lane * 32);
+        lds4a(b1, st + 3072 + lane * 32);
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(d0) : "r"(st + 4096 + (lane & 3) * 8) : "memory");
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(d1) : "r"(st + 4128 + (lane & 3) * 8) : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { b0[i] *= -d0; b1[i] *= -d1; }
+        __syncwarp();                                        // every lane holds its fragments: the stage may be refilled
+        if (lane == 0 && p + NST < npairs) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the refill (async proxy) follows generic-proxy reads of the stage
+            issue(p + NST, it + NST);
+        }
+        frag_mma<false>(acc, a0, b0);
+        frag_mma<false>(acc, a1, b1);
+    }
+    R.it += npairs;
+}
+
 // acc <- acc * M^T in place, M = D_J^-1 L_JJ^-1 lower triangular in the cm_mtile_off layout (the
 // triangular solve of an off-diagonal tile as a tile product).  The accumulator fragments ARE the A
 // operand: k-slot t of k-step (cj,e) stands for column 8cj + 2t + e, which is exactly the element

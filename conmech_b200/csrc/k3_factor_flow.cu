@@ -40,7 +40,7 @@ __device__ unsigned long long g_flow_prof[16];
 // solve against M_J, the tile's share of the forward substitution and, for the chain tile
 // (J == I-1), the newest term of the diagonal tile, handed to the diagonal factorisation through
 // the shared scratch.  Returns true when the diagonal tile was placed in the scratch.
-template <bool PROF>
+template <bool PROF, int OPS>
 __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     const int bt = CTX(bt);
     long long *pc = PROF ? CTX(pc) + (threadIdx.x >> 5) * 16 : nullptr;
@@ -71,7 +71,15 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
         const double *tiles = CTX(tiles);
         const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
         const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
-        acc_update_stream<false>(acc, A, Bm, CTX(dpiv) + qs * 4, Kend * 8 - qs, lane);
+        if (OPS) {
+            const int w = threadIdx.x >> 5;
+            unsigned *itp = CTX(ring_it) + w;
+            OpRing R{CTX(ring0) + w * (OPS * CM_RING_STAGE_BYTES), CTX(ringbar0) + w * (OPS * 8), *itp};
+            acc_update_stream_ring<OPS ? OPS : 1>(acc, A, Bm, CTX(dpiv) + qs * 4, Kend * 8 - qs, lane, R);
+            if (lane == 0) *itp = R.it;
+            __syncwarp();
+        } else
+            acc_update_stream<false>(acc, A, Bm, CTX(dpiv) + qs * 4, Kend * 8 - qs, lane);
         K = Kend;
         qs = K * 8;
         FP_ADD(pc, 1);
@@ -118,11 +126,12 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     return chain;
 }
 
-template <int NW, bool PROF>
+// OPS: stages of the shared-memory operand ring per warp (0 = operands through registers, one k-step of look-ahead)
+template <int NW, bool PROF, int OPS>
 #ifndef CM_K3_CTAS4
 #define CM_K3_CTAS4 4          // resident 4-warp CTAs per SM the register allocation aims at (timing experiments: 5)
 #endif
-__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 4 ? CM_K3_CTAS4 : (NW <= 16 ? 16 / NW : 1)))
+__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 4 ? (OPS ? 3 : CM_K3_CTAS4) : (NW <= 16 ? 16 / NW : 1)))
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
@@ -137,6 +146,10 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     unsigned long long *s_arow = reinterpret_cast<unsigned long long *>(s_kcol + m.n_tile_rows_max);   // 8-byte aligned: 2n+4 ints after s_prog
                                                                      // [n_tile_rows_max][aw] bit b: tile (I, I-bt+1+b) was assembled by K2
     const int aw = (m.band_tiles + 63) >> 6;
+    // operand ring: [NW][OPS] stages of CM_RING_STAGE_BYTES (128-byte aligned), then [NW][OPS] mbarriers, then [NW] counters
+    unsigned char *s_ring = reinterpret_cast<unsigned char *>((reinterpret_cast<size_t>(s_arow + m.n_tile_rows_max * aw) + 127) & ~(size_t)127);
+    unsigned long long *s_ringbar = reinterpret_cast<unsigned long long *>(s_ring + (size_t)NW * OPS * CM_RING_STAGE_BYTES);
+    unsigned *s_ring_it = reinterpret_cast<unsigned *>(s_ringbar + NW * OPS);
     __shared__ long long s_pc[PROF ? NW : 1][16];
     __shared__ long long s_tpub;
 
@@ -166,6 +179,14 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         s_ctx.s_part = s_part; s_ctx.s_rhs = s_rhs; s_ctx.s_scr = s_scr; s_ctx.s_minpiv = s_minpiv; s_ctx.s_fail = s_fail; s_ctx.s_dacc = s_dacc;
         s_ctx.pc = PROF ? &s_pc[0][0] : nullptr; s_ctx.tpub = &s_tpub;
         s_ctx.bt = bt; s_ctx.n_pad = L.n_pad; s_ctx.n_lc = n_lc; s_ctx.zero_bits = zero_bits;
+        if (OPS) {
+            s_ctx.ring0 = (unsigned)__cvta_generic_to_shared(s_ring);
+            s_ctx.ringbar0 = (unsigned)__cvta_generic_to_shared(s_ringbar);
+            s_ctx.ring_it = s_ring_it;
+            for (int i = 0; i < NW * OPS; ++i) mbar_init((unsigned)__cvta_generic_to_shared(s_ringbar + i), 1);
+            for (int i = 0; i < NW; ++i) s_ring_it[i] = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     for (int I = t; I < NT; I += NW * 32) {
         s_prog[I] = kfirst[I];
@@ -209,8 +230,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         __syncwarp();
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
         for (int J = kfI; J < I; ++J) {
-            handed = offdiag_tile<PROF>(I, J, kcI, lane);
-            release_fence();
+            handed = offdiag_tile<PROF, OPS>(I, J, kcI, lane);
+            release_fence<OPS>();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
         }
@@ -218,7 +239,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         if (!handed && I > 0) wait_prog_gt(prog, I - 1, I - 1);      // one diagonal factorisation at a time (shared scratch)
         FP_ADD(pc, 5);
         diag_factor_blk(I, handed, lane);
-        release_fence();
+        release_fence<OPS>();
         __syncwarp();
         if (lane == 0) { if (PROF) s_tpub = clock64(); prog[I] = I + 1; }
         FP_ADD(pc, 6);
@@ -229,7 +250,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         }
         FP_ADD(pc, 7);
         forward_row_w(I, lane);
-        release_fence();
+        release_fence<OPS>();
         __syncwarp();
         if (lane == 0) *yprog = I + 1;
         FP_ADD(pc, 8);
@@ -247,20 +268,21 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     }
 }
 
-size_t flow_smem(const cm_model_dev &m, int nw) {
+size_t flow_smem(const cm_model_dev &m, int nw, int ops) {
     return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw + (nw & 1) + nw * 640) * sizeof(double) +
-           (size_t)(2 * m.n_tile_rows_max + 8) * sizeof(int) + (size_t)m.n_tile_rows_max * ((m.band_tiles + 63) >> 6) * sizeof(unsigned long long);
+           (size_t)(2 * m.n_tile_rows_max + 8) * sizeof(int) + (size_t)m.n_tile_rows_max * ((m.band_tiles + 63) >> 6) * sizeof(unsigned long long) +
+           (ops ? 128 + (size_t)nw * ops * (CM_RING_STAGE_BYTES + 8) + (size_t)nw * 4 : 0);
 }
 
 }  // namespace
 
-template <int NW, bool PROF>
+template <int NW, bool PROF, int OPS>
 static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
     static cm_smem_cache cache;
-    const size_t smem = flow_smem(m, NW);
-    cudaError_t e = cm_ensure_smem(k3_factor_flow<NW, PROF>, smem, cache, m.device);
+    const size_t smem = flow_smem(m, NW, OPS);
+    cudaError_t e = cm_ensure_smem(k3_factor_flow<NW, PROF, OPS>, smem, cache, m.device);
     if (e != cudaSuccess) return e;
-    k3_factor_flow<NW, PROF><<<count, NW * 32, smem, st>>>(m, L, ws);
+    k3_factor_flow<NW, PROF, OPS><<<count, NW * 32, smem, st>>>(m, L, ws);
     return cudaGetLastError();
 }
 
@@ -276,12 +298,18 @@ cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, 
         if (count <= 2 * n_sm && m.band_tiles > 8) config = 1;
         if (m.band_tiles > 16) config = 3;       // config 5 (band of 35 tiles), 512 subsets, largest first: 16 warps 142 ms, 8 warps 147 ms, 4 warps 209 ms
     }
-    if (config == 1) return prof ? launch_flow<8, true>(m, L, ws, count, st) : launch_flow<8, false>(m, L, ws, count, st);
-    if (config == 3) return launch_flow<16, false>(m, L, ws, count, st);
-    if (config == 4) return launch_flow<2, false>(m, L, ws, count, st);
-    if (config == 5) return launch_flow<3, false>(m, L, ws, count, st);
-    if (config == 6) return launch_flow<1, false>(m, L, ws, count, st);
-    return prof ? launch_flow<4, true>(m, L, ws, count, st) : launch_flow<4, false>(m, L, ws, count, st);
+    // operand ring (cm_set_variant 10 / 11: 4-warp CTAs with one / two stages per warp; 12: 16-warp CTAs, two stages): CM_K3_RING=1 makes the 16-warp
+    // configuration use it by default (one CTA per SM: the shared memory is there)
+    if (config == 10) return launch_flow<4, false, 1>(m, L, ws, count, st);     // 59 KB per CTA: three CTAs per SM
+    if (config == 11) return launch_flow<4, false, 2>(m, L, ws, count, st);     // 76 KB: three CTAs per SM just fit
+    if (config == 12) return launch_flow<8, false, 2>(m, L, ws, count, st);      // 8-warp CTAs (wide bands)
+    static const int ring16 = getenv("CM_K3_RING") ? atoi(getenv("CM_K3_RING")) : 0;
+    if (config == 1) return prof ? launch_flow<8, true, 0>(m, L, ws, count, st) : launch_flow<8, false, 0>(m, L, ws, count, st);
+    if (config == 3) return ring16 ? launch_flow<8, false, 2>(m, L, ws, count, st) : launch_flow<16, false, 0>(m, L, ws, count, st);
+    if (config == 4) return launch_flow<2, false, 0>(m, L, ws, count, st);
+    if (config == 5) return launch_flow<3, false, 0>(m, L, ws, count, st);
+    if (config == 6) return launch_flow<1, false, 0>(m, L, ws, count, st);
+    return prof ? launch_flow<4, true, 0>(m, L, ws, count, st) : launch_flow<4, false, 0>(m, L, ws, count, st);
 }
 
 // read (and clear) the activity counters of the instrumented build

@@ -169,6 +169,10 @@ typedef struct cm_solve_out {
  * launch fills the GPU, 8 or 16 warps per subset for few subsets of a wide band); 2 / 3 / 6 = the
  * same kernel pinned to 4 / 8 / 16-warp CTAs; 4 / 5 = 4 / 8-warp CTAs instrumented with
  * per-activity cycle counters; 7 / 8 / 9 = 2 / 3 / 1-warp CTAs (timing experiments, parity-clean);
+ * 10 / 11 = 4-warp CTAs whose update-stream operands come through a shared-memory ring filled by the
+ * bulk-copy engine (cp.async.bulk + mbarrier, one / two stages of two k-steps per warp, three CTAs per
+ * SM), 12 = the same with 8-warp CTAs for wide bands - parity-clean, measured slower than the register
+ * path at its higher occupancy, kept selectable;
  * 0 = scalar validation variant of the same algorithm
  * (csrc/k3_factor.cu; slow, used by the parity tests to cross-check the tensor-core path). */
 int cm_set_variant(cm_handle *h, int32_t variant);
