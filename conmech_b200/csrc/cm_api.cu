@@ -32,7 +32,7 @@ struct cm_handle {
     std::vector<void *> allocs;          // device allocations owned by the handle
     std::vector<int> order;              // host copy of the ordering
     // geometry tables (stacked over the geometry variants; replaced as a set by cm_set_geometries)
-    double *d_xyz = nullptr, *d_Kg = nullptr, *d_R3 = nullptr, *d_elen = nullptr;
+    double *d_xyz = nullptr, *d_Kg = nullptr, *d_Kt = nullptr, *d_R3 = nullptr, *d_elen = nullptr;
     std::vector<int32_t> conn;           // host copy of the connectivity (length checks of new geometries)
     int *d_geom = nullptr;               // staging of the per-subset geometry indices of the host entry point
     size_t geom_cap = 0;
@@ -338,12 +338,13 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     {   // geometry 0: the model's own node coordinates
         cudaError_t ce = cudaMalloc((void **)&h->d_xyz, (size_t)3 * nV * sizeof(double));
         if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_Kg, (size_t)144 * nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_Kt, (size_t)144 * nE * sizeof(double));
         if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_R3, (size_t)9 * nE * sizeof(double));
         if (ce == cudaSuccess) ce = cudaMalloc((void **)&h->d_elen, (size_t)nE * sizeof(double));
         if (ce == cudaSuccess) ce = cudaMemcpy(h->d_xyz, d->xyz, (size_t)3 * nV * sizeof(double), cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) { std::string msg = std::string("cm_create: ") + cudaGetErrorString(ce); cm_destroy(h); return fail(CM_ERR_CUDA, msg); }
     }
-    m.xyz = h->d_xyz; m.Kg = h->d_Kg; m.R3 = h->d_R3; m.elen = h->d_elen;
+    m.xyz = h->d_xyz; m.Kg = h->d_Kg; m.Kt = h->d_Kt; m.R3 = h->d_R3; m.elen = h->d_elen;
     m.conn = conn; m.props = props; m.cr = cr;
     m.ne_ptr = d_ne_ptr; m.ne_elem = d_ne_elem; m.ne_end = d_ne_end;
     m.sup_node = d_sup_node; m.sup_cond = d_sup_cond; m.node_sup = d_node_sup;
@@ -386,7 +387,7 @@ int cm_destroy(cm_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->d_q) cudaFree(h->d_q);
     if (h->d_pnodal) cudaFree(h->d_pnodal);
-    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_R3); cudaFree(h->d_elen); cudaFree(h->d_geom);
+    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_Kt); cudaFree(h->d_R3); cudaFree(h->d_elen); cudaFree(h->d_geom);
     if (h->stage) cudaFree(h->stage);
     if (h->wsbuf) cudaFree(h->wsbuf);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -470,15 +471,16 @@ int cm_set_geometries(cm_handle *h, int32_t n_geom, const double *xyz) {
         }
     CU(cudaSetDevice(h->device));
     // new tables beside the old ones, swapped in on success
-    double *nx = nullptr, *nK = nullptr, *nR = nullptr, *nL = nullptr;
+    double *nx = nullptr, *nK = nullptr, *nT = nullptr, *nR = nullptr, *nL = nullptr;
     cudaError_t ce = cudaMalloc((void **)&nx, G * 3 * nV * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&nK, G * 144 * nE * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nT, G * 144 * nE * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&nR, G * 9 * nE * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&nL, G * nE * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMemcpy(nx, xyz, G * 3 * nV * sizeof(double), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) {
         cm_model_dev t = m;
-        t.n_geom = n_geom; t.xyz = nx; t.Kg = nK; t.R3 = nR; t.elen = nL;
+        t.n_geom = n_geom; t.xyz = nx; t.Kg = nK; t.Kt = nT; t.R3 = nR; t.elen = nL;
         ce = cudaEventRecord(h->ev[0], h->stream);
         if (ce == cudaSuccess) ce = cm_launch_element_tables(t, h->stream);
         h->launches++;
@@ -487,12 +489,12 @@ int cm_set_geometries(cm_handle *h, int32_t n_geom, const double *xyz) {
         if (ce == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->k1_ms = ms; }
     }
     if (ce != cudaSuccess) {
-        cudaFree(nx); cudaFree(nK); cudaFree(nR); cudaFree(nL);
+        cudaFree(nx); cudaFree(nK); cudaFree(nT); cudaFree(nR); cudaFree(nL);
         return fail(ce == cudaErrorMemoryAllocation ? CM_ERR_NOMEM : CM_ERR_CUDA, std::string("cm_set_geometries: ") + cudaGetErrorString(ce));
     }
-    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_R3); cudaFree(h->d_elen);
-    h->d_xyz = nx; h->d_Kg = nK; h->d_R3 = nR; h->d_elen = nL;
-    m.n_geom = n_geom; m.xyz = nx; m.Kg = nK; m.R3 = nR; m.elen = nL;
+    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_Kt); cudaFree(h->d_R3); cudaFree(h->d_elen);
+    h->d_xyz = nx; h->d_Kg = nK; h->d_Kt = nT; h->d_R3 = nR; h->d_elen = nL;
+    m.n_geom = n_geom; m.xyz = nx; m.Kg = nK; m.Kt = nT; m.R3 = nR; m.elen = nL;
     // the lumped element loads depend on the geometry: the load cases have to be set again
     if (h->d_q) { cudaFree(h->d_q); h->d_q = nullptr; }
     m.q = nullptr;

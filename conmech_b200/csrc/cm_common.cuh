@@ -62,6 +62,9 @@ struct cm_model_dev {
     const double *props;   // [nE*7] A,Jx,Iy,Iz,E,mu,rho
     const double *cr;      // [nE*6]
     double *Kg;            // [n_geom x nE*144] row major global element stiffness
+    double *Kt;            // [n_geom x nE*144] the same with entries |k| <= 1e-14 set to zero: what the assembly sums (the
+                           //   reference drops those entries per element, numpy_stiffness_assembly.py:384); written by K1 so
+                           //   that the gather of K2 and the reactions of K4 do not test every entry of every subset again
     double *R3;            // [n_geom x nE*9]
     double *elen;          // [n_geom x nE]
     const int *ne_ptr;     // [nV+1] node -> incident elements (ascending ids)

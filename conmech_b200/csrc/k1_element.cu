@@ -134,7 +134,7 @@ constexpr int K1_THREADS = 128;
 constexpr int K1_SSTR = K1_THREADS + 1;
 
 __device__ void element_tables(const double *pu, const double *pv, const double *pr, const double *cr,
-                               bool valid, double *Kg_block, int n_in_block, double *R3out, double *len_out,
+                               bool valid, double *Kg_block, double *Kt_block, int n_in_block, double *R3out, double *len_out,
                                double *s_stage) {
     const int tid = threadIdx.x;
     double R[3][3], L = 0.0;
@@ -191,7 +191,9 @@ __device__ void element_tables(const double *pu, const double *pv, const double 
         __syncthreads();
         for (int idx = tid; idx < n_in_block * 36; idx += K1_THREADS) {
             const int el = idx / 36, jj = idx - 36 * el;
-            Kg_block[(size_t)el * 144 + p * 36 + jj] = s_stage[jj * K1_SSTR + el];
+            const double kv = s_stage[jj * K1_SSTR + el];
+            Kg_block[(size_t)el * 144 + p * 36 + jj] = kv;
+            if (Kt_block) Kt_block[(size_t)el * 144 + p * 36 + jj] = (fabs(kv) > CM_EPS) ? kv : 0.0;
         }
         __syncthreads();
     }
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_element_tables(cm_model_dev m) 
     const int u = m.conn[2 * ec], v = m.conn[2 * ec + 1];
     const double *xyz = m.xyz + g * 3 * m.nV;
     element_tables(xyz + 3 * u, xyz + 3 * v, m.props + 7 * ec, m.cr + 6 * ec, valid, m.Kg + 144 * (g * m.nE + e0),
-                   min(K1_THREADS, m.nE - e0), m.R3 + 9 * (g * m.nE + ec), m.elen + g * m.nE + ec, s_stage);
+                   m.Kt + 144 * (g * m.nE + e0), min(K1_THREADS, m.nE - e0), m.R3 + 9 * (g * m.nE + ec), m.elen + g * m.nE + ec, s_stage);
 }
 
 __global__ void __launch_bounds__(K1_THREADS) k1_element_generic(const double *xyz_u, const double *xyz_v,
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_element_generic(const double *x
     const long long e = e0 + threadIdx.x;
     const bool valid = e < n;
     const long long ec = valid ? e : 0;
-    element_tables(xyz_u + 3 * ec, xyz_v + 3 * ec, props + 7 * ec, cr + 6 * ec, valid, Kg + 144 * e0,
+    element_tables(xyz_u + 3 * ec, xyz_v + 3 * ec, props + 7 * ec, cr + 6 * ec, valid, Kg + 144 * e0, nullptr,
                    (int)((n - e0) < K1_THREADS ? (n - e0) : K1_THREADS), R3 + 9 * ec, nullptr, s_stage);
 }
 

@@ -15,7 +15,6 @@ namespace {
 
 constexpr int K2_THREADS = 256;
 
-__device__ __forceinline__ double thr(double k) { return (fabs(k) > CM_EPS) ? k : 0.0; }
 
 // exclusive scan of n ints in shared memory, in place; returns the total (all threads).
 // scratch: K2_THREADS+1 ints.
@@ -53,13 +52,21 @@ __device__ __forceinline__ int node_row(const int *node_sup, const unsigned char
     return r;
 }
 
+// next tile row of the CTA for the calling warp
+__device__ __forceinline__ int next_row(int *counter, int lane) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, r, 0);
+}
+
 #ifndef K2_BULK_FILL
 #define K2_BULK_FILL 1
 #endif
 #ifndef K2_MIN_CTAS
-#define K2_MIN_CTAS 5          // 48 registers: five CTAs per SM (measured best: 4 CTAs at 60 registers 3.35 ms, 5 at 48 3.0 ms, 6 at 40 with spills 3.36 ms)
+#define K2_MIN_CTAS 4          // 64 registers, no spills: 4 CTAs 2.32 ms, 5 CTAs (48 registers, spills) 2.59, 6 CTAs 2.73 per 4096 subsets
+                               // (round 1, with the scatter's value array still in local memory, 5 CTAs won: 3.0 against 3.35)
 #endif
-template <bool TS>      // TS: the index tables are staged in shared memory
+template <bool TS, bool DS>      // TS: the index tables are staged in shared memory; DS: so is the Jacobi scale (n_pad doubles)
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, const int *geom, long long first,
                    cm_out_dev out, int ktilde_rm) {
@@ -75,6 +82,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     unsigned char *s_exist = s_free + m.nV;                        // [nV]
     unsigned char *s_aflag = s_exist + m.nV;                       // [n_tile_rows_max*band_tiles] tile holds K_mm entries
     char *s_blob = reinterpret_cast<char *>((reinterpret_cast<size_t>(s_aflag + m.n_tile_rows_max * m.band_tiles) + 15) & ~(size_t)15);   // [k2_blob_bytes] if TS
+    // the Jacobi scale of every solver row: read back per matrix entry by the scatter (row and six columns) and by the
+    // right-hand sides - from global memory that was an L2 round trip on the latency chain of every block row
+    double *s_dinv = reinterpret_cast<double *>(s_blob + (TS ? ((m.k2_blob_bytes + 15) & ~15) : 0));              // [n_pad] if DS
     __shared__ int s_red[8];
 #if K2_BULK_FILL
     __shared__ __align__(128) double s_zero[512];      // source of the bulk zero fill
@@ -82,7 +92,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // (ordered before the first bulk copy by the barriers below)
 #endif
     __shared__ unsigned long long s_work, s_ent;
-    __shared__ int s_ntile;
+    __shared__ int s_ntile, s_next;
     __shared__ double s_dred[K2_THREADS / 32];
 
     const int t = threadIdx.x, T = blockDim.x;
@@ -102,7 +112,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     const int nV = m.nV;
     // geometry variant of this subset: its slice of the stacked stiffness / load tables
     const size_t gv = geom ? (size_t)min(max(geom[gs], 0), m.n_geom - 1) : 0;
-    const double *Kg = m.Kg + gv * m.nE * 144;
+    const double *Kg = m.Kt + gv * m.nE * 144;        // entries |k| <= 1e-14 already dropped (K1)
     const double *qtab = m.q + gv * m.n_lc * m.nE * 12;
 
     // index tables: shared-memory copies when they fit (one coalesced pass), the global blob otherwise
@@ -127,7 +137,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 
     for (int w = t; w < m.mask_words; w += T) s_mask[w] = gmask[w];
     if (t < 8) s_red[t] = 0;
-    if (t == 0) { s_work = 0ull; s_ent = 0ull; s_ntile = 0; }
+    if (t == 0) { s_work = 0ull; s_ent = 0ull; s_ntile = 0; s_next = 0; }
     __syncthreads();
 
     // ---- node existence, support status (numpy_stiffness.py:156-184)
@@ -291,10 +301,10 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         for (int p = ne_ptr[v]; p < ne_ptr[v + 1]; ++p) {
             const int e = ne_elem[p];
             const int l = 6 * ne_end[p] + i;
-            const double kv = thr(Kg[(size_t)e * 144 + l * 12 + l]);
+            const double kv = Kg[(size_t)e * 144 + l * 12 + l];
             kii += elem_on(s_mask, e) ? kv : 0.0;
         }
-        dinv[r] = kii;
+        (DS ? s_dinv : dinv)[r] = kii;
         if (!(fabs(kii) > CM_EPS)) ok = 0;
     }
     if (!ok) atomicOr(&s_red[3], 1);
@@ -302,8 +312,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     const int jacobi = s_red[3] ? 0 : 1;
     for (int r = t; r < NT * CM_TILE; r += T) {
         double d = 1.0;
-        if (r < ns && jacobi) d = 1.0 / sqrt(dinv[r]);
+        if (r < ns && jacobi) d = 1.0 / sqrt((DS ? s_dinv : dinv)[r]);
         dinv[r] = d;
+        if (DS) s_dinv[r] = d;
     }
     if (t == 0) info[CM_INFO_JACOBI] = jacobi;
     __syncthreads();
@@ -322,8 +333,14 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     // s_tmp[p] = first solver row of the node at position p of the static order (exclusive scan above).
     {
         const int bt = m.band_tiles;
-        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
-        for (int IR = warp; IR < NT; IR += nw) {
+        const int lane = t & 31;
+        // tile rows are handed out dynamically (shared counter): rows differ in work (nodes, neighbours, tiles to fill),
+        // with a static round robin a quarter of the warps sat at the barrier below for 5 % of the kernel
+#if defined(K2_STATIC_ROWS) && K2_STATIC_ROWS
+        for (int IR = t >> 5; IR < NT; IR += T >> 5) {
+#else
+        for (int IR = next_row(&s_next, lane); IR < NT; IR = next_row(&s_next, lane)) {
+#endif
 #if K2_BULK_FILL
             // zero fill by the copy engine: lane 0 streams a zeroed 4 KB shared-memory block over every
             // tile of the row that receives entries (cp.async.bulk, two per tile) and waits for the
@@ -391,8 +408,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                         const double2 v0 = kp[0], v1 = kp[1], v2 = kp[2];
 #endif
                         if (elem_on(s_mask, e)) {
-                            s6[0] += thr(v0.x); s6[1] += thr(v0.y); s6[2] += thr(v1.x);
-                            s6[3] += thr(v1.y); s6[4] += thr(v2.x); s6[5] += thr(v2.y);
+                            s6[0] += v0.x; s6[1] += v0.y; s6[2] += v1.x;
+                            s6[3] += v1.y; s6[4] += v2.x; s6[5] += v2.y;
                         }
                     }
                 } else {
@@ -412,8 +429,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                         const double2 v0 = kp[0], v1 = kp[1], v2 = kp[2];
 #endif
                         if (elem_on(s_mask, e)) {
-                            s6[0] += thr(v0.x); s6[1] += thr(v0.y); s6[2] += thr(v1.x);
-                            s6[3] += thr(v1.y); s6[4] += thr(v2.x); s6[5] += thr(v2.y);
+                            s6[0] += v0.x; s6[1] += v0.y; s6[2] += v1.x;
+                            s6[3] += v1.y; s6[4] += v2.x; s6[5] += v2.y;
                             any = true;
                         }
                     }
@@ -422,7 +439,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                 // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only).
                 // Every index into the value array is a compile-time constant (a run-time index puts the array
                 // into local memory: that was 1.3 GB of L1-missing local loads per 4096 subsets).
-                const double dr = dinv[r];
+                const double *dv = DS ? s_dinv : dinv;
+                const double dr = dv[r];
                 const int sc = node_sup[c];
                 const int jmax = blk == 0 ? i : 5;
                 const int I = r >> 5;
@@ -431,7 +449,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                     // node c is not a support: its six DOFs are the columns base_c .. base_c + 5
                     double v[6];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) v[j] = (dr * s6[j]) * dinv[base_c + j];
+                    for (int j = 0; j < 6; ++j) v[j] = (dr * s6[j]) * dv[base_c + j];
                     const int K0 = base_c >> 5;
                     if (ktilde_rm && K0 == ((base_c + jmax) >> 5)) {
                         // row-major K~ tile: the row's entries are contiguous - 16-byte stores where aligned
@@ -464,7 +482,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
                         if (sup_cond[6 * sc + j]) continue;        // fixed DOF: no solver column
-                        if (j <= jmax) tile_of(cc >> 5)[ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31)] = (dr * s6[j]) * dinv[cc];
+                        if (j <= jmax) tile_of(cc >> 5)[ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31)] = (dr * s6[j]) * dv[cc];
                         ++cc;
                     }
                 }
@@ -501,7 +519,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             sq += pv * pv;
             if (s_exist[v]) {
                 int r = node_row(node_sup, sup_cond, v, i, s_base[v]);
-                if (r >= 0) Xl[r] = dinv[r] * pv;
+                if (r >= 0) Xl[r] = (DS ? s_dinv : dinv)[r] * pv;
             }
         }
         // deterministic block reduction of the squared norm
@@ -560,14 +578,26 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
                                       const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st) {
     const size_t base = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
                         (size_t)m.n_tile_rows_max * m.band_tiles + 16;
-    // tables in shared memory while five CTAs still fit an SM (the 1k-element frame needs 35 KB per CTA)
-    const bool ts = base + 16 + (size_t)m.k2_blob_bytes <= 44 * 1024;
-    const size_t smem = ts ? base + 16 + (size_t)m.k2_blob_bytes : base;
-    static cm_smem_cache cache[2];
-    cudaError_t e = ts ? cm_ensure_smem(k2_dofmap_assemble<true>, smem, cache[1], m.device)
-                       : cm_ensure_smem(k2_dofmap_assemble<false>, smem, cache[0], m.device);
-    if (e != cudaSuccess) return e;
-    if (ts) k2_dofmap_assemble<true><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, first, out, ktilde_rowmajor);
-    else k2_dofmap_assemble<false><<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, first, out, ktilde_rowmajor);
-    return cudaGetLastError();
+    // index tables and the Jacobi scale in shared memory while K2_MIN_CTAS CTAs still fit an SM (the 1k-element frame needs
+    // 35 KB + 16.6 KB per CTA)
+    const size_t budget = (size_t)(227 * 1024) / K2_MIN_CTAS - 1024 - 4500;      // per CTA: 1 KB reserved, 4.4 KB static
+    const size_t blob = ((size_t)m.k2_blob_bytes + 15) & ~(size_t)15;
+    const size_t dsz = (size_t)L.n_pad * sizeof(double);
+    // the index tables first (2.32 against 2.57 ms per 4096 subsets), the Jacobi scale if it still fits (2.52 alone)
+    bool ts = base + 16 + blob <= budget;
+    bool ds = base + 16 + (ts ? blob : 0) + dsz <= budget;
+    static const int force = getenv("CM_K2_SMEM") ? atoi(getenv("CM_K2_SMEM")) : -1;      // timing experiments: bit 0 tables, bit 1 scale
+    if (force >= 0) { ts = force & 1; ds = (force & 2) != 0; }
+    const size_t smem = base + 16 + (ts ? blob : 0) + (ds ? dsz : 0);
+    static cm_smem_cache cache[4];
+    auto go = [&](auto kernel, cm_smem_cache &c) -> cudaError_t {
+        cudaError_t e = cm_ensure_smem(kernel, smem, c, m.device);
+        if (e != cudaSuccess) return e;
+        kernel<<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, first, out, ktilde_rowmajor);
+        return cudaGetLastError();
+    };
+    if (ts && ds) return go(k2_dofmap_assemble<true, true>, cache[3]);
+    if (ts) return go(k2_dofmap_assemble<true, false>, cache[2]);
+    if (ds) return go(k2_dofmap_assemble<false, true>, cache[1]);
+    return go(k2_dofmap_assemble<false, false>, cache[0]);
 }

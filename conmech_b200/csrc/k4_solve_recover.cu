@@ -12,7 +12,6 @@ namespace {
 constexpr int K4_THREADS = 256;
 constexpr int K4_WARPS = K4_THREADS / 32;
 
-__device__ __forceinline__ double thr(double k) { return (fabs(k) > CM_EPS) ? k : 0.0; }
 __device__ __forceinline__ bool elem_on(const uint32_t *mask, int e) { return (mask[e >> 5] >> (e & 31)) & 1u; }
 
 // NB right-hand sides at once.  cs[j][ks] (valid on lanes 0..3, column 4*ks + lane) =
@@ -128,6 +127,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
     const uint32_t *mask = masks + (size_t)gs * m.mask_words;
     const size_t gv = geom ? (size_t)min(max(geom[gs], 0), m.n_geom - 1) : 0;      // geometry variant of this subset
     const double *Kg = m.Kg + gv * m.nE * 144;
+    const double *Kt = m.Kt + gv * m.nE * 144;        // the entries the assembly summed (|k| <= 1e-14 dropped)
     const double *R3g = m.R3 + gv * m.nE * 9;
     const int bt = m.band_tiles, nV = m.nV, nE = m.nE, n_lc = m.n_lc;
     const int zero_bits = info[CM_INFO_ZERO_LOAD];
@@ -295,12 +295,12 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     int e = m.ne_elem[p];
                     if (!elem_on(mask, e)) continue;
                     ex = true;
-                    const double *krow = Kg + (size_t)e * 144 + (6 * m.ne_end[p] + i) * 12;
+                    const double *krow = Kt + (size_t)e * 144 + (6 * m.ne_end[p] + i) * 12;
                     int n0 = m.conn[2 * e], n1 = m.conn[2 * e + 1];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) acc += thr(krow[j]) * u_at(6 * n0 + j);
+                    for (int j = 0; j < 6; ++j) acc += krow[j] * u_at(6 * n0 + j);
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) acc += thr(krow[6 + j]) * u_at(6 * n1 + j);
+                    for (int j = 0; j < 6; ++j) acc += krow[6 + j] * u_at(6 * n1 + j);
                 }
                 if (ex) Ro[6 * v + i] = acc - (zero_load ? 0.0 : Pl[6 * v + i]);   // P_f stays 0 when the solve is skipped (:260-270)
             }
