@@ -295,7 +295,10 @@ def other_configs_gpu(torch, np, dev, cpu_rates):
     sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)
     eng = sc._sc_ins
     t0 = time.perf_counter()
-    eng.set_geometries(shapes)
+    eng.set_geometries(shapes)                                  # first call: allocates the stacked tables (8.8 GB)
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.set_geometries(shapes)                                  # steady state of an optimisation loop: tables reused
     t_set = time.perf_counter() - t0
     k1_ms = eng.last_element_kernel_ms()
     sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
@@ -306,10 +309,12 @@ def other_configs_gpu(torch, np, dev, cpu_rates):
     def run_shapes():
         r['o'] = eng.solve_many_device(masks, want=FULL, out=r.get('o'), geometry=gidx)
     ms = timed(run_shapes, 3)
-    k1_bytes = G * nE * (152 + 153 * 8 + 8)                    # 152 B in, (144 + 9) doubles out (+ the member length)
+    # 152 B in, (144 + 9) doubles out; here + the member length and the second stiffness table
+    # (entries |k| <= 1e-14 dropped, what the assembly reads)
+    k1_bytes = G * nE * (152 + (2 * 144 + 9 + 1) * 8)
     hbm_peak, _ = measured_peaks()
     with_cpu('many_shapes_one_topology', {
-        'value': G / (ms * 1e-3 + t_set), 'unit': 'shapes/s', 'shapes': G, 'solve_ms': ms, 'set_geometries_ms': 1e3 * t_set,
+        'value': G / (ms * 1e-3 + t_set), 'unit': 'shapes/s', 'shapes': G, 'solve_ms': ms, 'set_geometries_ms': 1e3 * t_set, 'first_set_geometries_ms': 1e3 * t_first,
         'k1_ms': k1_ms, 'k1_elements': G * nE, 'k1_gbs': k1_bytes / (k1_ms * 1e-3) / 1e9, 'k1_frac_of_hbm': k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak,
         'status_ok': int((r['o']['status'] == 0).sum().item()),
         'what': '4096 geometry variants (node coordinates jittered) of the 7x7x8 frame: cm_set_geometries (host upload + ONE element-kernel '

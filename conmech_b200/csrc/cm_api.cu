@@ -36,6 +36,7 @@ struct cm_handle {
     std::vector<int32_t> conn;           // host copy of the connectivity (length checks of new geometries)
     int *d_geom = nullptr;               // staging of the per-subset geometry indices of the host entry point
     size_t geom_cap = 0;
+    size_t geom_tables_cap = 1;          // geometry variants the stacked tables have room for
     double k1_ms = 0.0;                  // device time of the most recent element-table launch
     // load tables
     double *d_q = nullptr, *d_pnodal = nullptr;
@@ -470,14 +471,22 @@ int cm_set_geometries(cm_handle *h, int32_t n_geom, const double *xyz) {
                 return fail(CM_ERR_INVALID, "geometry " + std::to_string(g) + ": E#" + std::to_string(e) + " - Bar length too small!");
         }
     CU(cudaSetDevice(h->device));
-    // new tables beside the old ones, swapped in on success
-    double *nx = nullptr, *nK = nullptr, *nT = nullptr, *nR = nullptr, *nL = nullptr;
-    cudaError_t ce = cudaMalloc((void **)&nx, G * 3 * nV * sizeof(double));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nK, G * 144 * nE * sizeof(double));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nT, G * 144 * nE * sizeof(double));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nR, G * 9 * nE * sizeof(double));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&nL, G * nE * sizeof(double));
-    if (ce == cudaSuccess) ce = cudaMemcpy(nx, xyz, G * 3 * nV * sizeof(double), cudaMemcpyHostToDevice);
+    // The tables are reused when they are large enough (an optimisation loop calls this once per iterate with the same
+    // number of variants: multi-GB allocations cost more than the kernel); otherwise new tables are allocated beside
+    // the old ones and swapped in on success.  A failure leaves the previous geometries in place unless the buffers
+    // were being reused - then the handle has no valid geometry until the next successful call.
+    const bool reuse = (size_t)n_geom <= h->geom_tables_cap;
+    double *nx = h->d_xyz, *nK = h->d_Kg, *nT = h->d_Kt, *nR = h->d_R3, *nL = h->d_elen;
+    cudaError_t ce = cudaSuccess;
+    if (!reuse) {
+        nx = nK = nT = nR = nL = nullptr;
+        ce = cudaMalloc((void **)&nx, G * 3 * nV * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&nK, G * 144 * nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&nT, G * 144 * nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&nR, G * 9 * nE * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&nL, G * nE * sizeof(double));
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(nx, xyz, G * 3 * nV * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (ce == cudaSuccess) {
         cm_model_dev t = m;
         t.n_geom = n_geom; t.xyz = nx; t.Kg = nK; t.Kt = nT; t.R3 = nR; t.elen = nL;
@@ -489,11 +498,15 @@ int cm_set_geometries(cm_handle *h, int32_t n_geom, const double *xyz) {
         if (ce == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->k1_ms = ms; }
     }
     if (ce != cudaSuccess) {
-        cudaFree(nx); cudaFree(nK); cudaFree(nT); cudaFree(nR); cudaFree(nL);
+        if (!reuse) { cudaFree(nx); cudaFree(nK); cudaFree(nT); cudaFree(nR); cudaFree(nL); }
+        else { m.n_lc = 0; h->info.n_loadcases = 0; }
         return fail(ce == cudaErrorMemoryAllocation ? CM_ERR_NOMEM : CM_ERR_CUDA, std::string("cm_set_geometries: ") + cudaGetErrorString(ce));
     }
-    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_Kt); cudaFree(h->d_R3); cudaFree(h->d_elen);
-    h->d_xyz = nx; h->d_Kg = nK; h->d_Kt = nT; h->d_R3 = nR; h->d_elen = nL;
+    if (!reuse) {
+        cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_Kt); cudaFree(h->d_R3); cudaFree(h->d_elen);
+        h->d_xyz = nx; h->d_Kg = nK; h->d_Kt = nT; h->d_R3 = nR; h->d_elen = nL;
+        h->geom_tables_cap = (size_t)n_geom;
+    }
     m.n_geom = n_geom; m.xyz = nx; m.Kg = nK; m.Kt = nT; m.R3 = nR; m.elen = nL;
     // the lumped element loads depend on the geometry: the load cases have to be set again
     if (h->d_q) { cudaFree(h->d_q); h->d_q = nullptr; }
