@@ -235,6 +235,47 @@ def other_configs_gpu(torch, np, dev, cpu_rates):
                                              'what': 'solve_sequence(order): all 24 prefixes of the BFS construction sequence in one call'})
     del sc
 
+    # config 2 on the largest bundled model: every prefix of the BFS sequence of cantilever_beam_truss (2197 elements)
+    from conmech_b200 import LoadCase as LC
+    mdir = os.path.join(REPO, 'tests', 'golden', 'models')
+    model = Model.from_json(os.path.join(mdir, 'cantilever_beam_truss.json'))
+    sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)
+    sc.set_loads(LC.from_json(os.path.join(mdir, 'cantilever_beam_truss_loadcase.json')))
+    sc.set_nodal_displacement_tol(trans_tol=1e-3)
+    order = syn.bfs_sequence(model)
+    for _ in range(2):
+        flags = sc.solve_sequence(order)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        flags = sc.solve_sequence(order)
+    dt = (time.perf_counter() - t0) / 5
+    for _ in range(2):
+        flags_ind = sc.solve_sequence(order, reuse=False)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        flags_ind = sc.solve_sequence(order, reuse=False)
+    dt_ind = (time.perf_counter() - t0) / 5
+    eng = sc._sc_ins
+    o = np.asarray(order)
+    words = np.zeros((len(o), eng.info['mask_words']), dtype=np.uint32)
+    words[np.arange(len(o)), o >> 5] = np.uint32(1) << (o & 31).astype(np.uint32)
+    dmask = torch.from_numpy(np.bitwise_or.accumulate(words, axis=0).view(np.int32)).to(dev)
+    eng.enable_timing(True)
+    for _ in range(2):
+        rr = eng.solve_many_device(dmask, want=SCALARS + ('profile_flops',))
+        torch.cuda.synchronize(dev)
+    st = eng.last_stage_ms()
+    eng.enable_timing(False)
+    with_cpu('config2_cantilever_bfs_prefixes', {
+        'value': len(order) / dt, 'unit': UNIT, 'ms_per_sequence': 1e3 * dt, 'prefixes': len(order), 'flags_true': int(sum(flags)),
+        'ms_per_sequence_independent_prefixes': 1e3 * dt_ind, 'flags_equal': flags == flags_ind,
+        'stage_ms_independent_prefixes': [float(x) for x in st], 'k3_tflops_algorithmic': float(rr['profile_flops'].sum().item()) / st[1] / 1e9,
+        'what': 'StiffnessChecker.solve_sequence(order): all 2197 prefixes of the BFS construction sequence of cantilever_beam_truss '
+                '(817 nodes, 4284 free DOFs, band of 14 tiles, 68 point loads) in one call, host wall clock, flags to the host; '
+                'the factorisation is reused along the sequence (groups of 32 prefixes share the factor rows in front of the rows '
+                'their added elements touch); *_independent_prefixes = the same prefixes as 2197 independent subsets'})
+    del sc, eng, rr, dmask
+
     # config 4: joints on horizontals, four load cases per subset, height-field subsets
     model = syn.grid_frame(7, 7, 8, joints=True)
     sc = StiffnessChecker(model, checker_engine='cuda', device=dev.index)

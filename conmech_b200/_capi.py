@@ -19,7 +19,7 @@ c_uint32_p = C.POINTER(C.c_uint32)
 class ModelDesc(C.Structure):
     _fields_ = [('n_nodes', C.c_int32), ('n_elems', C.c_int32), ('n_supports', C.c_int32),
                 ('device', C.c_int32), ('xyz', c_double_p), ('conn', c_int32_p), ('props', c_double_p),
-                ('cr', c_double_p), ('sup_node', c_int32_p), ('sup_cond', c_uint8_p)]
+                ('cr', c_double_p), ('sup_node', c_int32_p), ('sup_cond', c_uint8_p), ('node_order', c_int32_p)]
 
 
 class ModelInfo(C.Structure):
@@ -45,7 +45,7 @@ class SolveOutHost(C.Structure):
 # every symbol include/conmech_b200.h declares
 SYMBOLS = ('cm_pack_elements', 'cm_create', 'cm_destroy', 'cm_get_info', 'cm_get_element_tables', 'cm_get_node_order',
            'cm_set_geometries', 'cm_geometry_count', 'cm_get_geometry_tables', 'cm_last_element_kernel_ms',
-           'cm_solve_many_g', 'cm_solve_many_host_g',
+           'cm_solve_many_g', 'cm_solve_many_host_g', 'cm_solve_many_host_seq',
            'cm_set_loadcases', 'cm_get_element_loads', 'cm_set_tol', 'cm_set_variant', 'cm_debug_k3_phase_cycles',
            'cm_workspace_bytes', 'cm_solve_many', 'cm_solve_many_host', 'cm_solve_many_host_chunks', 'cm_solve_many_host_multi', 'cm_kernel_launches',
            'cm_reset_counters', 'cm_enable_timing', 'cm_last_stage_ms', 'cm_last_wave_count', 'cm_element_kernel_dev',
@@ -78,6 +78,7 @@ def load():
     lib.cm_last_element_kernel_ms.argtypes = [H, C.c_void_p]
     lib.cm_solve_many_g.argtypes = [H, C.c_uint64, C.c_uint64, C.c_int64, C.POINTER(SolveOut), C.c_uint64, C.c_size_t, C.c_uint64]
     lib.cm_solve_many_host_g.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SolveOutHost)]
+    lib.cm_solve_many_host_seq.argtypes = [H, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(SolveOutHost)]
     lib.cm_set_loadcases.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cm_get_element_loads.argtypes = [H, C.c_int32, C.c_void_p]
     lib.cm_set_tol.argtypes = [H, C.c_double, C.c_double]

@@ -55,6 +55,8 @@ struct cm_handle {
     char *wsbuf = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second stream of a prefix-sharing wave (assembly of the tails beside the trunks' factorisation)
+    cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
     // internal lanes: consecutive waves of one call rotate over them (each with its own share
     // of the workspace), so that the drain of one wave's factorisation overlaps the next wave
     cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -244,9 +246,21 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     long long fl0, fl1;
     envelope_stats(nV, nE, d->conn, nfree, nat, &nf0, &bw0, &fl0);
     envelope_stats(nV, nE, d->conn, nfree, rcm, &nf1, &bw1, &fl1);
-    const bool use_rcm = fl1 < fl0;
+    bool use_rcm = fl1 < fl0;
     h->order = use_rcm ? rcm : nat;
-    const int n_free_full = nf0, halfbw = use_rcm ? bw1 : bw0;
+    int n_free_full = nf0, halfbw = use_rcm ? bw1 : bw0;
+    if (d->node_order) {                 // the caller's ordering (construction sequences: order of first appearance)
+        std::vector<int> ord(d->node_order, d->node_order + nV);
+        std::vector<char> seen(nV, 0);
+        for (int p = 0; p < nV; ++p) {
+            if (ord[p] < 0 || ord[p] >= nV || seen[ord[p]]) { delete h; return fail(CM_ERR_INVALID, "cm_create: node_order is not a permutation of the node ids"); }
+            seen[ord[p]] = 1;
+        }
+        envelope_stats(nV, nE, d->conn, nfree, ord, &nf1, &bw1, &fl1);
+        h->order = ord;
+        use_rcm = true;                  // (fl1 / bw1 now describe the caller's ordering)
+        n_free_full = nf1; halfbw = bw1;
+    }
     std::vector<int> pos(nV);
     for (int p = 0; p < nV; ++p) pos[h->order[p]] = p;
 
@@ -360,6 +374,8 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
     for (int i = 0; i < CM_STAGE_SLOTS && ce == cudaSuccess; ++i) {
         ce = cudaEventCreateWithFlags(&h->slot_done[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot_free[i], cudaEventDisableTiming);
@@ -401,6 +417,8 @@ int cm_destroy(cm_handle *h) {
     }
     if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    for (int i = 0; i < 3; ++i) if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
     delete h;
     return CM_OK;
 }
@@ -692,8 +710,8 @@ static cm_out_dev out_dev_of(const cm_solve_out *o) {
 // The waves of one call.  `before(w, first, count, lane_stream, &od)` runs before a wave's kernels are
 // enqueued and may redirect the wave's outputs; `after(...)` runs right after its last kernel.
 template <typename Before, typename After>
-static int run_waves(cm_handle *h, const uint32_t *masks, const int *geom, int64_t B, const cm_out_dev &od0, char *ws,
-                     const WavePlan &P, cudaStream_t st, Before before, After after) {
+static int run_waves(cm_handle *h, const uint32_t *masks, const int *geom, const int *trows, int group, int64_t B,
+                     const cm_out_dev &od0, char *ws, const WavePlan &P, cudaStream_t st, Before before, After after) {
     const size_t per = h->L.per_subset;
     double acc_ms[3] = {0, 0, 0};
     if (P.lanes) {
@@ -707,18 +725,40 @@ static int run_waves(cm_handle *h, const uint32_t *masks, const int *geom, int64
         char *lws = P.lanes ? ws + (size_t)(w % P.NL) * (size_t)P.cap * per : ws;
         cm_out_dev od = od0;
         { int rc = before(w, first, count, ls, od); if (rc != CM_OK) return rc; }
+        const int vcfg = h->variant >= 10 ? h->variant :
+                         h->variant == 1 ? 0 : (h->variant >= 7 ? h->variant - 3 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2)));   // 7/8/9: 2/3/1 warps; 10-12: operand ring
+        const int prof = (h->variant == 4 || h->variant == 5) ? 1 : 0;
+        const int ktrm = h->variant != 0 ? 1 : 0;
         if (h->timing) CU(cudaEventRecord(h->ev[0], ls));
-        CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, geom, first, count, od, h->variant != 0 ? 1 : 0, ls));
-        if (h->variant != 0) { CU(cm_launch_schedule(h->L, lws, count, ls)); h->launches += 1; }
-        if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
-        if (h->variant == 0)
-            CU(cm_launch_factor(h->m, h->L, lws, count, 0, ls));
-        else
-        {
-            // variant -> CTA configuration of the dataflow kernel (0 automatic, 1: 8 warps, 2: 4 warps, 3: 16 warps)
-            const int cfg = h->variant >= 10 ? h->variant :
-                            h->variant == 1 ? 0 : (h->variant >= 7 ? h->variant - 3 : (h->variant == 6 ? 3 : ((h->variant & 1) ? 1 : 2)));   // 7/8/9: 2/3/1 warps; 10-12: operand ring
-            CU(cm_launch_factor_flow(h->m, h->L, lws, count, cfg, (h->variant == 4 || h->variant == 5) ? 1 : 0, ls));
+        if (trows && group > 1 && h->variant != 0) {
+            // Prefix-sharing groups.  The trunks (first subset of every group) are assembled and factored first - few
+            // CTAs that fill a fraction of the GPU - while a second stream assembles all the other subsets; then the
+            // wave is ranked and the others are factored, reading the trunks' rows.
+            const int n_trunks = (count + group - 1) / group;
+            const bool two = !h->timing && h->aux_stream;
+            cudaStream_t bs = two ? h->aux_stream : ls;
+            if (two) { CU(cudaEventRecord(h->aux_ev[0], ls)); CU(cudaStreamWaitEvent(bs, h->aux_ev[0], 0)); }
+            CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, geom, trows, group, 1, first, count, od, ktrm, ls));
+            if (two) CU(cudaEventRecord(h->aux_ev[1], ls));
+            if (!h->timing) CU(cm_launch_factor_flow(h->m, h->L, lws, 0, n_trunks, group, vcfg, prof, ls));
+            CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, geom, trows, group, 2, first, count, od, ktrm, bs));
+            if (two) CU(cudaStreamWaitEvent(bs, h->aux_ev[1], 0));              // the ranking reads the trunks' cost keys as well
+            CU(cm_launch_schedule(h->L, lws, count, bs));
+            if (two) { CU(cudaEventRecord(h->aux_ev[2], bs)); CU(cudaStreamWaitEvent(ls, h->aux_ev[2], 0)); }
+            if (h->timing) {
+                CU(cudaEventRecord(h->ev[1], ls));
+                CU(cm_launch_factor_flow(h->m, h->L, lws, 0, n_trunks, group, vcfg, prof, ls));
+            }
+            if (count > n_trunks) CU(cm_launch_factor_flow(h->m, h->L, lws, n_trunks, count - n_trunks, 0, vcfg, prof, ls));
+            h->launches += 3;
+        } else {
+            CU(cm_launch_dofmap_assemble(h->m, h->L, lws, masks, geom, nullptr, 0, 0, first, count, od, ktrm, ls));
+            if (h->variant != 0) { CU(cm_launch_schedule(h->L, lws, count, ls)); h->launches += 1; }
+            if (h->timing) CU(cudaEventRecord(h->ev[1], ls));
+            if (h->variant == 0)
+                CU(cm_launch_factor(h->m, h->L, lws, count, 0, ls));
+            else
+                CU(cm_launch_factor_flow(h->m, h->L, lws, 0, count, 0, vcfg, prof, ls));
         }
         if (h->timing) CU(cudaEventRecord(h->ev[2], ls));
         CU(cm_launch_solve_recover(h->m, h->L, lws, masks, geom, first, count, od, ls));
@@ -760,7 +800,7 @@ int cm_solve_many_g(cm_handle *h, uint64_t masks_dev, uint64_t geom_dev, int64_t
     WavePlan P;
     { int rc = plan_waves(h, B, ws_bytes, &P); if (rc != CM_OK) return rc; }
     CU(cudaSetDevice(h->device));
-    return run_waves(h, reinterpret_cast<const uint32_t *>(masks_dev), reinterpret_cast<const int *>(geom_dev), B, out_dev_of(o),
+    return run_waves(h, reinterpret_cast<const uint32_t *>(masks_dev), reinterpret_cast<const int *>(geom_dev), nullptr, 0, B, out_dev_of(o),
                      reinterpret_cast<char *>(ws_dev), P,
                      reinterpret_cast<cudaStream_t>(stream),
                      [](long long, long long, int, cudaStream_t, cm_out_dev &) { return CM_OK; },
@@ -798,6 +838,9 @@ void out_advance(const cm_handle *h, cm_solve_out_host *o, int64_t b0) {
 
 extern "C" {
 
+static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, const int32_t *trows_host, int group,
+                      int64_t B, const cm_solve_out_host *o);
+
 // Host buffers.  Masks go up in one copy.  Outputs are staged per WAVE in a ring of device slots: right
 // after a wave's last kernel its slot is drained to the caller's arrays by a copy stream (one
 // cudaMemcpyAsync per requested output, written at the subset's final position), while the lanes
@@ -811,6 +854,30 @@ int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B, cons
 
 int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, int64_t B,
                          const cm_solve_out_host *o) {
+    return solve_host(h, masks_host, geom_host, nullptr, 0, B, o);
+}
+
+// Prefix-sharing groups (the construction-sequence path).  Consecutive subsets of one group
+// are prefixes of ONE construction sequence in a node ordering where nodes are numbered by first appearance (the
+// handle was created with that ordering: cm_model_desc.node_order): the matrix of a later prefix differs from the
+// first subset of its group (the "trunk") only in solver rows >= the first row touched by the elements added since.
+// The trunk is factored completely; a "tail" subset b factors only the tile rows >= t_rows[b] and reads the rows above
+// from the trunk's slab (tiles of L, M_J, pivots, forward solutions) - in the factorisation AND in the back
+// substitution.  Waves hold whole groups; trunks are factored by one launch, tails by the next.
+int cm_solve_many_host_seq(cm_handle *h, const uint32_t *masks_host, int64_t B, int32_t group, const int32_t *t_rows_host,
+                           const cm_solve_out_host *o) {
+    if (!t_rows_host || group < 1) return fail(CM_ERR_INVALID, "cm_solve_many_host_seq: group >= 1 and t_rows required");
+    if (h && h->variant == 0) return fail(CM_ERR_STATE, "cm_solve_many_host_seq: not available with the scalar validation kernel");
+    for (int64_t b = 0; b < B; ++b)
+        if (t_rows_host[b] < 0 || (b % group == 0 && t_rows_host[b] != 0))
+            return fail(CM_ERR_INVALID, "cm_solve_many_host_seq: t_rows must be >= 0, and 0 for the first subset of every group");
+    return solve_host(h, masks_host, nullptr, t_rows_host, group, B, o);
+}
+
+}  // extern "C"
+
+static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, const int32_t *trows_host, int group,
+                      int64_t B, const cm_solve_out_host *o) {
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host: null argument");
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many_host: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
@@ -820,19 +887,24 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
                 return fail(CM_ERR_INVALID, "cm_solve_many_host: geometry index " + std::to_string(geom_host[b]) + " of subset " +
                                             std::to_string(b) + " not in [0, " + std::to_string(h->m.n_geom) + ")");
     CU(cudaSetDevice(h->device));
-    if (geom_host && (size_t)B > h->geom_cap) {
+    const int32_t *aux_host = geom_host ? geom_host : trows_host;       // one per-subset int array at a time
+    if (aux_host && (size_t)B > h->geom_cap) {
         cudaFree(h->d_geom);
         h->d_geom = nullptr; h->geom_cap = 0;
         CU(cudaMalloc((void **)&h->d_geom, (size_t)B * sizeof(int)));
         h->geom_cap = (size_t)B;
     }
+    if (trows_host && 2 * (size_t)h->L.n_pad * sizeof(double) > 100 * 1024)
+        return fail(CM_ERR_INVALID, "cm_solve_many_host_seq: model too large for shared rows (solution vectors must fit shared memory)");
     const cm_model_dev &m = h->m;
     const size_t Bn = (size_t)B;
     // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
     // (the driver is only asked about free memory when the workspace has to grow)
     const size_t per = h->L.per_subset;
     static const size_t ws_subsets = getenv("CM_WS_SUBSETS") ? (size_t)std::max(1, atoi(getenv("CM_WS_SUBSETS"))) : 8192;      // 4096: 266 k, 8192: 273 k, 12500: 272 k solves/s on config 3 (profiles/r01c_experiments.txt)
-    size_t want = std::min<size_t>(Bn, ws_subsets) * per;
+    size_t want_subsets = std::min<size_t>(Bn, ws_subsets);
+    if (trows_host && group > 1) want_subsets = (want_subsets + group - 1) / group * group;     // whole groups
+    size_t want = want_subsets * per;
     if (want > h->ws_bytes) {
         size_t freeb = 0, totalb = 0;
         CU(cudaMemGetInfo(&freeb, &totalb));
@@ -858,6 +930,18 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
     const long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
     WavePlan P;
     { int rc = plan_waves(h, B, h->ws_bytes, &P, max_wave); if (rc != CM_OK) return rc; }
+    if (trows_host && group > 1) {
+        // waves hold whole groups and run one after the other on the caller-facing stream: the overlap inside a wave
+        // (trunk factorisation beside the assembly of the tails) takes the place of the lanes
+        const long long cap_groups = (long long)(h->ws_bytes / h->L.per_subset) / group;
+        if (cap_groups < 1) return fail(CM_ERR_NOMEM, "cm_solve_many_host_seq: workspace smaller than one group");
+        const long long n_groups = (B + group - 1) / group;
+        const long long n_w = (n_groups + cap_groups - 1) / cap_groups;
+        P.lanes = false;
+        P.n_waves = n_w;
+        P.wsize = (n_groups + n_w - 1) / n_w * group;
+        P.cap = P.wsize;
+    }
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t mask_bytes = al(Bn * m.mask_words * 4);
     size_t slot_bytes = 0;
@@ -873,7 +957,7 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
     }
     cudaStream_t st = h->stream;
     CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
-    if (geom_host) CU(cudaMemcpyAsync(h->d_geom, geom_host, Bn * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (aux_host) CU(cudaMemcpyAsync(h->d_geom, aux_host, Bn * sizeof(int), cudaMemcpyHostToDevice, st));
     char *slots = h->stage + mask_bytes;
     auto before = [&](long long w, long long first, int, cudaStream_t ls, cm_out_dev &od) -> int {
         const int s = (int)(w % n_slots);
@@ -901,13 +985,16 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
         return CM_OK;
     };
     cm_out_dev od0{};
-    int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), geom_host ? h->d_geom : nullptr, B, od0, h->wsbuf, P, st, before, after);
+    int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), geom_host ? h->d_geom : nullptr,
+                       trows_host ? h->d_geom : nullptr, trows_host ? group : 0, B, od0, h->wsbuf, P, st, before, after);
     if (rc != CM_OK) { cudaDeviceSynchronize(); return rc; }
     CU(cudaEventRecord(h->copy_ev, h->copy_stream));
     CU(cudaStreamWaitEvent(st, h->copy_ev, 0));
     CU(cudaStreamSynchronize(st));
     return CM_OK;
 }
+
+extern "C" {
 
 int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t B, const cm_solve_out_host *o,
                               int64_t chunk, const volatile int32_t *ready) {

@@ -26,6 +26,11 @@ enum { CM_K2T_ORDER = 0, CM_K2T_NE_PTR, CM_K2T_NE_ELEM, CM_K2T_LP_PTR, CM_K2T_LP
 #define CM_INFO_JACOBI 5           // 1: Jacobi scaling applied, 0: identity (a |k_ii| <= eps)
 #define CM_INFO_COST 6             // factorisation cost of the subset (float bits of its envelope flops; 0: nothing to factor)
 #define CM_INFO_SCHED 7            // scheduling: record r holds the slab index of the subset with the r-th largest cost
+// Prefix-sharing groups (cm_solve_many_host_seq): a "tail" subset shares the first TROWS tile rows of its factor with
+// the "trunk" subset of its group (slab index TRUNK within the wave) instead of computing them again.
+#define CM_INFO_TROWS 8            // shared tile rows (0: the subset stands alone / is a trunk)
+#define CM_INFO_TRUNK 9            // slab index of the trunk
+#define CM_INFO_FAILROW 10         // 0, or 1 + the first tile row whose diagonal factorisation hit a bad pivot
 
 // Element (r,k) of a 32x32 tile, "fragment-major" order: [k/4][(r%8)*4 + k%4][r/8].
 // For the FP64 MMA m8n8k4 (lane = 4*g + t) the four A (or B) fragments of k-step ks that a lane
@@ -153,13 +158,20 @@ cudaError_t cm_launch_element_generic(const double *xyz_u, const double *xyz_v, 
 // (2 sectors instead of 6 partial-sector writes).  The tensor-core factorisation reads it that way
 // (acc_load_rm); the scalar validation kernel wants fragment-major.
 // geom: per-subset geometry index (device, indexed like masks) or nullptr = geometry 0
+// trows / group: prefix-sharing groups - subset gs shares trows[gs] tile rows with subset (gs / group) * group, which is
+// in the same wave (first and count are multiples of group); nullptr / 0 = no sharing
+// part: 0 = all `count` subsets; 1 = only the first subset of every group (the trunks: count / group CTAs);
+// 2 = all but those
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
-                                      const uint32_t *masks, const int *geom, long long first, int count,
-                                      const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st);
+                                      const uint32_t *masks, const int *geom, const int *trows, int group, int part,
+                                      long long first, int count, const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st);
+// ranks the subsets of a wave by factorisation cost, largest first; subsets without shared rows (trunks) before the tails
 cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaStream_t st);
 cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
                              int variant, cudaStream_t st);
-cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+// factors the subsets of ranks rank0 .. rank0 + count - 1 of the wave's schedule; stride > 0: no schedule, CTA b
+// factors the subset in slab b * stride (the trunks of prefix-sharing groups, before the wave has been ranked)
+cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int rank0, int count, int stride,
                                   int config, int prof, cudaStream_t st);
 cudaError_t cm_factor_flow_read_prof(unsigned long long *out16);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,

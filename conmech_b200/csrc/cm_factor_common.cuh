@@ -26,6 +26,10 @@ struct K3Ctx {
     const int *kcol; const unsigned long long *arow; int *prog; int *yprog;
     double *s_part; double *s_rhs; double *s_scr; double *s_minpiv; int *s_fail; double2 *s_dacc;
     long long *pc; long long *tpub;
+    // prefix-sharing group: tile rows < trows of the factor (tiles, M_J, pivots, forward solutions) are read from the
+    // trunk subset's slab, which an earlier launch has completed; trows == 0: none
+    const double *ttiles; const double *tminv; const double *tdpiv; const double *tX;
+    int trows;
     unsigned ring0, ringbar0;      // operand ring (OPS builds): shared-window address of warp 0's stages / barriers
     unsigned *ring_it;             // [NW] pairs each warp has consumed so far (stage index and barrier phase follow from it)
     int bt, n_pad, n_lc, zero_bits;
@@ -157,7 +161,10 @@ __device__ __noinline__ void diag_factor_blk(int I, bool in_smem, int lane) {
     }
     CTX(dpiv)[I * CM_TILE + lane] = dmine;
     s_rinv[lane] = rmine;
-    if (lane == 0) { *s_minpiv_w = minpiv; if (fail) *CTX(s_fail) = 1; }
+    if (lane == 0) {
+        *s_minpiv_w = minpiv;
+        if (fail && *CTX(s_fail) == 0) *CTX(s_fail) = I + 1;      // (diagonal tiles are factored one at a time, in row order)
+    }
     // ---- X = L^-1.  Diagonal blocks: lane 8*bb + j owns column j of X_bb (substitution on e_j)
     {
         const int bb = lane >> 3, j = lane & 7;

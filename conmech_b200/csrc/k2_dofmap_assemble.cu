@@ -68,8 +68,8 @@ __device__ __forceinline__ int next_row(int *counter, int lane) {
 #endif
 template <bool TS, bool DS>      // TS: the index tables are staged in shared memory; DS: so is the Jacobi scale (n_pad doubles)
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
-k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, const int *geom, long long first,
-                   cm_out_dev out, int ktilde_rm) {
+k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, const int *geom, const int *trows_of,
+                   int group, int part, long long first, cm_out_dev out, int ktilde_rm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout
     int *s_base = reinterpret_cast<int *>(smem_raw);             // [nV] first solver row of node
@@ -96,7 +96,9 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     __shared__ double s_dred[K2_THREADS / 32];
 
     const int t = threadIdx.x, T = blockDim.x;
-    const int sb = blockIdx.x;
+    // part 1: CTA b assembles the first subset of group b (the trunks); part 2: every subset but those
+    const int sb = part == 1 ? blockIdx.x * group : blockIdx.x;
+    if (part == 2 && sb % group == 0) return;
     const long long gs = first + sb;
     char *slab = ws + (size_t)sb * L.per_subset;
     double *tiles = reinterpret_cast<double *>(slab + L.off_tiles);
@@ -137,7 +139,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 
     for (int w = t; w < m.mask_words; w += T) s_mask[w] = gmask[w];
     if (t < 8) s_red[t] = 0;
-    if (t == 0) { s_work = 0ull; s_ent = 0ull; s_ntile = 0; s_next = 0; }
+    if (t == 0) { s_work = 0ull; s_ent = 0ull; s_ntile = 0; }
     __syncthreads();
 
     // ---- node existence, support status (numpy_stiffness.py:156-184)
@@ -179,6 +181,13 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         info[CM_INFO_ZERO_LOAD] = 0;
         info[CM_INFO_JACOBI] = 1;
         info[CM_INFO_COST] = 0;
+        info[CM_INFO_FAILROW] = 0;
+        // prefix-sharing group: the first trows tile rows of this subset's factor are those of the group's first subset
+        // (recorded for K3 / K4; the assembly below is complete all the same, so that the factorisation can fall back to
+        // factoring the subset on its own when the trunk turns out not to be usable)
+        info[CM_INFO_TROWS] = (trows_of && status == CM_ST_OK) ? min(trows_of[gs], n_free / CM_TILE) : 0;
+        info[CM_INFO_TRUNK] = group > 0 ? (int)((gs / group) * group - first) : 0;
+        s_next = 0;
     }
     if (status != CM_ST_OK) return;      // uniform for the block
 
@@ -275,7 +284,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     }
     __syncthreads();
     if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
-    if (t == 0) info[CM_INFO_COST] = __float_as_int((float)s_work + 1.0f);      // > 0, monotone in the work
+    // cost key of the schedule: > 0, monotone in the work.  (For a tail the shared rows still count: an upper bound.)
+    if (t == 0) info[CM_INFO_COST] = __float_as_int((float)s_work + 1.0f);
     for (int I = t; I < NT; I += T) {
         kfirst_g[I] = s_kfirst[I]; kcol_g[I] = s_kcol[I] & ~1;
         if (out.envelope_tiles) atomicAdd(&s_ntile, I - s_kfirst[I] + 1);
@@ -548,19 +558,25 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 // `rank`.  count^2 integer comparisons - microseconds for the wave sizes in use.
 namespace {
 __global__ void __launch_bounds__(256) k2_schedule(cm_ws_layout L, char *ws, int count) {
-    __shared__ int s_key[256];
+    __shared__ long long s_key[256];
     const int i = blockIdx.x * 256 + threadIdx.x;
     auto info_of = [&](int s) { return reinterpret_cast<int *>(ws + (size_t)s * L.per_subset + L.off_info); };
-    const int mine = i < count ? info_of(i)[CM_INFO_COST] : -1;
+    // key: cost, with the first subset of every prefix-sharing group (the trunk) ahead of all others - the trunks are
+    // factored by an earlier launch, the others may read their rows.  (Without groups only slab 0 is "a trunk": harmless.)
+    auto key_of = [&](int s) -> long long {
+        const int *inf = info_of(s);
+        return (long long)inf[CM_INFO_COST] + (inf[CM_INFO_TRUNK] == s ? (1ll << 32) : 0ll);      // first subset of its group
+    };
+    const long long mine = i < count ? key_of(i) : -1;
     int rank = 0;
     for (int j0 = 0; j0 < count; j0 += 256) {
         const int j = j0 + threadIdx.x;
         __syncthreads();
-        s_key[threadIdx.x] = j < count ? info_of(j)[CM_INFO_COST] : -1;
+        s_key[threadIdx.x] = j < count ? key_of(j) : -1;
         __syncthreads();
         const int n = min(256, count - j0);
         for (int k = 0; k < n; ++k) {
-            const int key = s_key[k];
+            const long long key = s_key[k];
             rank += (key > mine || (key == mine && j0 + k < i)) ? 1 : 0;
         }
     }
@@ -574,7 +590,7 @@ cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaS
 }
 
 cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
-                                      const uint32_t *masks, const int *geom, long long first, int count,
+                                      const uint32_t *masks, const int *geom, const int *trows, int group, int part, long long first, int count,
                                       const cm_out_dev &out, int ktilde_rowmajor, cudaStream_t st) {
     const size_t base = (size_t)(2 * m.nV + 2 * m.n_tile_rows_max + K2_THREADS + 1 + m.mask_words) * 4 + 2 * (size_t)m.nV +
                         (size_t)m.n_tile_rows_max * m.band_tiles + 16;
@@ -593,7 +609,8 @@ cudaError_t cm_launch_dofmap_assemble(const cm_model_dev &m, const cm_ws_layout 
     auto go = [&](auto kernel, cm_smem_cache &c) -> cudaError_t {
         cudaError_t e = cm_ensure_smem(kernel, smem, c, m.device);
         if (e != cudaSuccess) return e;
-        kernel<<<count, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, first, out, ktilde_rowmajor);
+        const int ctas = part == 1 ? (count + group - 1) / group : count;
+        kernel<<<ctas, K2_THREADS, smem, st>>>(m, L, ws, masks, geom, trows, group, part, first, out, ktilde_rowmajor);
         return cudaGetLastError();
     };
     if (ts && ds) return go(k2_dofmap_assemble<true, true>, cache[3]);

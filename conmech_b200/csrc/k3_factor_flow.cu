@@ -25,6 +25,7 @@
 
 namespace {
 
+__device__ __forceinline__ bool t_is_zero() { return threadIdx.x == 0; }
 
 // instrumented build: cycles per activity, summed over all row warps (slots: 0 wait for an update
 // operand, 1 update streams, 2 wait for M_J, 3 solve product, 4 diagonal-tile updates, 5 wait for the
@@ -58,6 +59,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     int qs = max(kcI, CTX(kcol)[J]);
     int K = qs >> 3;
     FP_T0(pc);
+    const int trows = CTX(trows);                   // rows < trows live in the trunk's slab
     TileAcc acc;
     if (K >= J && !has_a && J != I - 1) {         // no entries and no fill-in: the tile of L is zero (the chain tile still hands the diagonal over)
 #pragma unroll 1
@@ -66,20 +68,22 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     }
     if (has_a) acc_load_rm(acc, T, lane); else acc_zero(acc);      // assembled K~ tiles are row-major (K2)
     while (K < J) {
-        const int Kend = min(wait_prog_gt(CTX(prog), J, K), J);
+        int Kend = min(wait_prog_gt(CTX(prog), J, K), J);
+        if (K < trows && Kend > trows) Kend = trows;           // the pivots of the shared columns come from the trunk
         FP_ADD(pc, 0);
         const double *tiles = CTX(tiles);
         const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
-        const double *Bm = tiles + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
+        const double *Bm = (J < trows ? CTX(ttiles) : tiles) + ((size_t)J * bt + (bt - 1 - J)) * CM_TILE_ELEMS + (size_t)qs * 128;
+        const double *dq = (K < trows ? CTX(tdpiv) : CTX(dpiv)) + qs * 4;
         if (OPS) {
             const int w = threadIdx.x >> 5;
             unsigned *itp = CTX(ring_it) + w;
             OpRing R{CTX(ring0) + w * (OPS * CM_RING_STAGE_BYTES), CTX(ringbar0) + w * (OPS * 8), *itp};
-            acc_update_stream_ring<OPS ? OPS : 1>(acc, A, Bm, CTX(dpiv) + qs * 4, Kend * 8 - qs, lane, R);
+            acc_update_stream_ring<OPS ? OPS : 1>(acc, A, Bm, dq, Kend * 8 - qs, lane, R);
             if (lane == 0) *itp = R.it;
             __syncwarp();
         } else
-            acc_update_stream<false>(acc, A, Bm, CTX(dpiv) + qs * 4, Kend * 8 - qs, lane);
+            acc_update_stream<false>(acc, A, Bm, dq, Kend * 8 - qs, lane);
         K = Kend;
         qs = K * 8;
         FP_ADD(pc, 1);
@@ -87,7 +91,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     wait_prog_gt(CTX(prog), J, J);                // M_J published
     FP_ADD(pc, 2);
     if (PROF && pc && J == I - 1 && (threadIdx.x & 31) == 0) pc[12] += clock64() - *CTX(tpub);     // reaction gap on the chain
-    acc_solve_inplace(acc, CTX(minv) + (size_t)J * CM_TILE_ELEMS, max(kcI - 8 * J, 0) >> 1, lane);
+    acc_solve_inplace(acc, (J < trows ? CTX(tminv) : CTX(minv)) + (size_t)J * CM_TILE_ELEMS, max(kcI - 8 * J, 0) >> 1, lane);
     acc_store(acc, cm_tile_ptr(CTX(tiles), bt, I, J), lane);
     if (PROF && pc && J == I - 1) FP_ADD(pc, 10); else FP_ADD(pc, 3);
     // share of this tile in the forward substitution of row I:  s_I += L(I,J) y_J
@@ -99,7 +103,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     FP_ADD(pc, 7);
     double2 dk[4];                                // pivots of block J for the diagonal term below: in flight with the y loads
     {
-        const double *dJ = CTX(dpiv) + J * CM_TILE + 2 * (lane & 3);
+        const double *dJ = (J < trows ? CTX(tdpiv) : CTX(dpiv)) + J * CM_TILE + 2 * (lane & 3);
 #pragma unroll
         for (int cs = 0; cs < 4; ++cs) dk[cs] = ldg2(dJ + cs * 8);
     }
@@ -109,7 +113,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
         for (int lc = 0; lc < n_lc; ++lc) {
             if ((zero_bits >> lc) & 1) continue;
             double part[4];
-            acc_matvec(acc, CTX(X) + (size_t)lc * CTX(n_pad) + J * CM_TILE, part, lane);
+            acc_matvec(acc, (J < trows ? CTX(tX) : CTX(X)) + (size_t)lc * CTX(n_pad) + J * CM_TILE, part, lane);
             if ((lane & 3) == 0) {
 #pragma unroll
                 for (int ri = 0; ri < 4; ++ri) s_part[lc * 32 + ri * 8 + (lane >> 2)] += part[ri];
@@ -132,7 +136,7 @@ template <int NW, bool PROF, int OPS>
 #define CM_K3_CTAS4 4          // resident 4-warp CTAs per SM the register allocation aims at (timing experiments: 5)
 #endif
 __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 4 ? (OPS ? 3 : CM_K3_CTAS4) : (NW <= 16 ? 16 / NW : 1)))
-k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
+k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
     double *s_rhs = s_scr + DSCR;                                    // [NW][32] forward substitution scratch
@@ -155,11 +159,28 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // CTA r factors the subset with the r-th largest cost of the wave (k2_schedule): big ones first
-    const int sb = reinterpret_cast<const int *>(ws + (size_t)blockIdx.x * L.per_subset + L.off_info)[CM_INFO_SCHED];
+    const int sb = stride > 0 ? (int)blockIdx.x * stride
+                              : reinterpret_cast<const int *>(ws + (size_t)(rank0 + blockIdx.x) * L.per_subset + L.off_info)[CM_INFO_SCHED];
     char *slab = ws + (size_t)sb * L.per_subset;
     int *info = reinterpret_cast<int *>(slab + L.off_info);
     if (info[CM_INFO_STATUS] != CM_ST_OK) return;
     const int NT = info[CM_INFO_NT];
+    // prefix-sharing group: the first trows tile rows are the trunk's (factored by the previous launch) - if the trunk
+    // is usable: solved, or failed behind the shared rows; same Jacobi-scaling decision (a zero diagonal anywhere switches
+    // the scaling off for the whole matrix, numpy_stiffness.py:283-290); at least trows complete tile rows.  Otherwise the
+    // subset is factored on its own, exactly as without sharing (K2 has assembled all of it).
+    int trows = info[CM_INFO_TROWS];
+    const char *tslab = ws + (size_t)info[CM_INFO_TRUNK] * L.per_subset;
+    if (trows > 0) {
+        const int *tinfo = reinterpret_cast<const int *>(tslab + L.off_info);
+        const int tst = tinfo[CM_INFO_STATUS], tfail = tinfo[CM_INFO_FAILROW];
+        const bool usable = (tst == CM_ST_OK || (tst == CM_ST_SINGULAR && tfail - 1 >= trows)) &&
+                            tinfo[CM_INFO_JACOBI] == info[CM_INFO_JACOBI] && tinfo[CM_INFO_NS] / CM_TILE >= trows;
+        if (!usable) {
+            trows = 0;
+            if (t_is_zero()) info[CM_INFO_TROWS] = 0;          // (K4 reads it)
+        }
+    }
     double *tiles = reinterpret_cast<double *>(slab + L.off_tiles);
     const int *kfirst = reinterpret_cast<const int *>(slab + L.off_kfirst);
     const int *kcol = reinterpret_cast<const int *>(slab + L.off_kcol);
@@ -179,6 +200,11 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         s_ctx.s_part = s_part; s_ctx.s_rhs = s_rhs; s_ctx.s_scr = s_scr; s_ctx.s_minpiv = s_minpiv; s_ctx.s_fail = s_fail; s_ctx.s_dacc = s_dacc;
         s_ctx.pc = PROF ? &s_pc[0][0] : nullptr; s_ctx.tpub = &s_tpub;
         s_ctx.bt = bt; s_ctx.n_pad = L.n_pad; s_ctx.n_lc = n_lc; s_ctx.zero_bits = zero_bits;
+        s_ctx.trows = trows;
+        s_ctx.ttiles = reinterpret_cast<const double *>(tslab + L.off_tiles);
+        s_ctx.tminv = reinterpret_cast<const double *>(tslab + L.off_minv);
+        s_ctx.tdpiv = reinterpret_cast<const double *>(tslab + L.off_dpiv);
+        s_ctx.tX = reinterpret_cast<const double *>(tslab + L.off_x);
         if (OPS) {
             s_ctx.ring0 = (unsigned)__cvta_generic_to_shared(s_ring);
             s_ctx.ringbar0 = (unsigned)__cvta_generic_to_shared(s_ringbar);
@@ -189,7 +215,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
         }
     }
     for (int I = t; I < NT; I += NW * 32) {
-        s_prog[I] = kfirst[I];
+        s_prog[I] = I < trows ? I + 1 : kfirst[I];        // shared rows are complete
         s_kcol[I] = kcol[I];
         for (int w = 0; w < aw; ++w) {
             unsigned long long bits = 0;
@@ -198,7 +224,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
             s_arow[I * aw + w] = bits;
         }
     }
-    if (t == 0) { *s_yprog = 0; *s_fail = 0; }
+    if (t == 0) { *s_yprog = trows; *s_fail = 0; }
     if (t < NW) s_minpiv[t] = __longlong_as_double(0x7ff0000000000000LL);
     __syncthreads();
 
@@ -207,7 +233,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     const long long tstart = PROF ? clock64() : 0;
     double *s_part_w = s_part + warp * n_lc * 32;
     double2 *s_dacc_w = s_dacc + warp * 320;
-    for (int I = warp; I < NT; I += NW) {
+    for (int I = warp + (trows + NW - 1 - warp) / NW * NW; I < NT; I += NW) {      // this warp's first row >= trows
         const int kcI = s_kcol[I];               // first nonzero column of the row in k-steps (even)
         const int kfI = kcI >> 3;                // = kfirst[I], the first tile column of the row
         for (int lc = 0; lc < n_lc; ++lc) s_part_w[lc * 32 + lane] = 0.0;
@@ -263,7 +289,8 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws) {
     if (t == 0) {
         double mp = s_minpiv[0];
         for (int w = 1; w < NW; ++w) mp = fmin(mp, s_minpiv[w]);
-        if (*s_fail) info[CM_INFO_STATUS] = CM_ST_SINGULAR;
+        if (*s_fail) { info[CM_INFO_STATUS] = CM_ST_SINGULAR; info[CM_INFO_FAILROW] = *s_fail; }
+        if (trows > 0) mp = fmin(mp, reinterpret_cast<const double *>(tslab + L.off_dpiv)[L.n_pad]);
         dpiv[L.n_pad] = mp;            // slot after the pivots
     }
 }
@@ -277,12 +304,12 @@ size_t flow_smem(const cm_model_dev &m, int nw, int ops) {
 }  // namespace
 
 template <int NW, bool PROF, int OPS>
-static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
+static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int rank0, int count, int stride, cudaStream_t st) {
     static cm_smem_cache cache;
     const size_t smem = flow_smem(m, NW, OPS);
     cudaError_t e = cm_ensure_smem(k3_factor_flow<NW, PROF, OPS>, smem, cache, m.device);
     if (e != cudaSuccess) return e;
-    k3_factor_flow<NW, PROF, OPS><<<count, NW * 32, smem, st>>>(m, L, ws);
+    k3_factor_flow<NW, PROF, OPS><<<count, NW * 32, smem, st>>>(m, L, ws, rank0, stride);
     return cudaGetLastError();
 }
 
@@ -290,7 +317,7 @@ static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, cha
 // Automatic: four small CTAs per SM hide the serial chain of a subset behind other subsets and are
 // best whenever the launch fills the GPU; a launch with few subsets of a wide band (the 10k-element
 // frames) instead needs its parallelism INSIDE the subset - more tile rows in flight per CTA.
-cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int count,
+cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int rank0, int count, int stride,
                                   int config, int prof, cudaStream_t st) {
     if (config == 0) {
         const int n_sm = m.n_sm > 0 ? m.n_sm : 148;
@@ -300,16 +327,16 @@ cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, 
     }
     // operand ring (cm_set_variant 10 / 11: 4-warp CTAs with one / two stages per warp; 12: 16-warp CTAs, two stages): CM_K3_RING=1 makes the 16-warp
     // configuration use it by default (one CTA per SM: the shared memory is there)
-    if (config == 10) return launch_flow<4, false, 1>(m, L, ws, count, st);     // 59 KB per CTA: three CTAs per SM
-    if (config == 11) return launch_flow<4, false, 2>(m, L, ws, count, st);     // 76 KB: three CTAs per SM just fit
-    if (config == 12) return launch_flow<8, false, 2>(m, L, ws, count, st);      // 8-warp CTAs (wide bands)
+    if (config == 10) return launch_flow<4, false, 1>(m, L, ws, rank0, count, stride, st);     // 59 KB per CTA: three CTAs per SM
+    if (config == 11) return launch_flow<4, false, 2>(m, L, ws, rank0, count, stride, st);     // 76 KB: three CTAs per SM just fit
+    if (config == 12) return launch_flow<8, false, 2>(m, L, ws, rank0, count, stride, st);      // 8-warp CTAs (wide bands)
     static const int ring16 = getenv("CM_K3_RING") ? atoi(getenv("CM_K3_RING")) : 0;
-    if (config == 1) return prof ? launch_flow<8, true, 0>(m, L, ws, count, st) : launch_flow<8, false, 0>(m, L, ws, count, st);
-    if (config == 3) return ring16 ? launch_flow<8, false, 2>(m, L, ws, count, st) : launch_flow<16, false, 0>(m, L, ws, count, st);
-    if (config == 4) return launch_flow<2, false, 0>(m, L, ws, count, st);
-    if (config == 5) return launch_flow<3, false, 0>(m, L, ws, count, st);
-    if (config == 6) return launch_flow<1, false, 0>(m, L, ws, count, st);
-    return prof ? launch_flow<4, true, 0>(m, L, ws, count, st) : launch_flow<4, false, 0>(m, L, ws, count, st);
+    if (config == 1) return prof ? launch_flow<8, true, 0>(m, L, ws, rank0, count, stride, st) : launch_flow<8, false, 0>(m, L, ws, rank0, count, stride, st);
+    if (config == 3) return ring16 ? launch_flow<8, false, 2>(m, L, ws, rank0, count, stride, st) : launch_flow<16, false, 0>(m, L, ws, rank0, count, stride, st);
+    if (config == 4) return launch_flow<2, false, 0>(m, L, ws, rank0, count, stride, st);
+    if (config == 5) return launch_flow<3, false, 0>(m, L, ws, rank0, count, stride, st);
+    if (config == 6) return launch_flow<1, false, 0>(m, L, ws, rank0, count, stride, st);
+    return prof ? launch_flow<4, true, 0>(m, L, ws, rank0, count, stride, st) : launch_flow<4, false, 0>(m, L, ws, rank0, count, stride, st);
 }
 
 // read (and clear) the activity counters of the instrumented build

@@ -132,6 +132,13 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
     const int bt = m.band_tiles, nV = m.nV, nE = m.nE, n_lc = m.n_lc;
     const int zero_bits = info[CM_INFO_ZERO_LOAD];
     const int n_pad = L.n_pad;
+    // prefix-sharing group: tile rows < trows of L, M, the pivots and the forward solutions are the trunk subset's
+    const int trows = info[CM_INFO_TROWS];
+    const char *tslab = ws + (size_t)info[CM_INFO_TRUNK] * L.per_subset;
+    const double *ttiles = reinterpret_cast<const double *>(tslab + L.off_tiles);
+    const double *tminv = reinterpret_cast<const double *>(tslab + L.off_minv);
+    const double *tdpiv = reinterpret_cast<const double *>(tslab + L.off_dpiv);
+    const double *tX = reinterpret_cast<const double *>(tslab + L.off_x);
 
     if (out.min_pivot && t == 0)
         out.min_pivot[gs] = (status == CM_ST_OK || status == CM_ST_SINGULAR) ? dpiv[n_pad] : nan("");
@@ -148,11 +155,13 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
               const bool live = lc < n_lc && !((zero_bits >> lc) & 1);
               any |= live;
               double *Xg = X + (size_t)(lc < n_lc ? lc : 0) * n_pad;
+              const double *Xt = tX + (size_t)(lc < n_lc ? lc : 0) * n_pad;
               double *Xl = XS ? s_x + j * n_pad : Xg;
               for (int r = t; r < NT * CM_TILE; r += K4_THREADS) {
-                  const double d = dpiv[r];
+                  const bool shared_row = XS && r < trows * CM_TILE;       // (sharing needs the shared-memory vectors: host checks)
+                  const double d = shared_row ? tdpiv[r] : dpiv[r];
                   if (XS && j == 0) s_x[NB * n_pad + r] = d;
-                  Xl[r] = live ? Xg[r] / d : 0.0;
+                  Xl[r] = live ? (shared_row ? Xt[r] : Xg[r]) / d : 0.0;
               }
           }
           __syncthreads();
@@ -169,7 +178,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                 for (int j = 0; j < NB; ++j)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) w4[j][i] = dpl[J * CM_TILE + i * 8 + g] * Xb[j * n_pad + J * CM_TILE + i * 8 + g];
-                mtile_tmatvec<NB>(minv + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
+                mtile_tmatvec<NB>((J < trows ? tminv : minv) + (size_t)J * CM_TILE_ELEMS, w4, cs, lane);
                 __syncwarp();
                 if (lane < 4)
 #pragma unroll
@@ -181,7 +190,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             for (int I = NT - 1; I > 0; --I) {
                 // M_{I-1} is needed at the end of this row's chain: start its DRAM read now
                 if (warp == 0) {
-                    const double *Mn = minv + (size_t)(I - 1) * CM_TILE_ELEMS;
+                    const double *Mn = (I - 1 < trows ? tminv : minv) + (size_t)(I - 1) * CM_TILE_ELEMS;
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + lane * 16));
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(Mn + 512 + lane * 16));
                 }
@@ -189,7 +198,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                 if (I >= 2) {
                     const int kfn = kfirst[I - 1];
                     for (int J = I - 2 - warp; J >= kfn; J -= K4_WARPS) {
-                        const double *Tn = cm_tile_ptr(tiles, bt, I - 1, J) + lane * 16;
+                        const double *Tn = cm_tile_ptr(I - 1 < trows ? ttiles : tiles, bt, I - 1, J) + lane * 16;
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn));
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(Tn + 512));
                     }
@@ -203,7 +212,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                     for (int i = 0; i < 4; ++i) x4[j][i] = Xb[j * n_pad + I * CM_TILE + i * 8 + g];
                 for (int J = I - 1 - warp; J >= kf; J -= K4_WARPS) {
                     double cs[NB][8];
-                    tile_tmatvec<NB>(cm_tile_ptr(tiles, bt, I, J), x4, cs, lane);
+                    tile_tmatvec<NB>(cm_tile_ptr(I < trows ? ttiles : tiles, bt, I, J), x4, cs, lane);
                     if (lane < 4)
 #pragma unroll
                         for (int j = 0; j < NB; ++j)
@@ -400,7 +409,7 @@ cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L
     const size_t vec = (size_t)L.n_pad * sizeof(double);
     static const int nb_env = getenv("CM_K4_NB") ? atoi(getenv("CM_K4_NB")) : 0;
     int nb = 0;
-    if (2 * vec <= 64 * 1024) {
+    if (2 * vec <= 100 * 1024) {          // (two CTAs per SM at the upper end; beyond that the vectors stay in global memory)
         nb = 1;
         if (m.n_lc >= 2 && 3 * vec <= 64 * 1024) nb = 2;
         if (m.n_lc >= 3 && 5 * vec <= 64 * 1024) nb = 4;

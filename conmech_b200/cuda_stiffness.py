@@ -40,9 +40,12 @@ def _ptr(a):
 
 
 class CudaStiffness(StiffnessBase):
-    def __init__(self, model, verbose=False, output_json=False, device=None, devices=None):
+    def __init__(self, model, verbose=False, output_json=False, device=None, devices=None, node_order=None):
         super(CudaStiffness, self).__init__(model, verbose, output_json)
         self._lib = _capi.load()
+        self._model = model
+        self._node_order = None if node_order is None else np.ascontiguousarray(node_order, dtype=np.int32)
+        self._static_pos = None                # solve_sequence: node -> position in the handle's static ordering
         if devices is not None:
             devices = [int(d) for d in devices]
             if len(devices) == 0 or len(set(devices)) != len(devices):
@@ -168,7 +171,8 @@ class CudaStiffness(StiffnessBase):
             desc = _capi.ModelDesc(nV, nE, len(sup_node), dev,
                                    xyz.ctypes.data_as(_capi.c_double_p), conn.ctypes.data_as(_capi.c_int32_p),
                                    props.ctypes.data_as(_capi.c_double_p), cr.ctypes.data_as(_capi.c_double_p),
-                                   sup_node.ctypes.data_as(_capi.c_int32_p), sup_cond.ctypes.data_as(_capi.c_uint8_p))
+                                   sup_node.ctypes.data_as(_capi.c_int32_p), sup_cond.ctypes.data_as(_capi.c_uint8_p),
+                                   self._node_order.ctypes.data_as(_capi.c_int32_p) if self._node_order is not None else None)
             h = C.c_void_p()
             _capi.check(self._lib.cm_create(C.byref(desc), C.byref(h)))
             self._handles.append(h)
@@ -423,6 +427,79 @@ class CudaStiffness(StiffnessBase):
             if rc != _capi.CM_OK:
                 raise _capi.CmError('conmech_b200 error {}: {}'.format(rc, msg))
         return res
+
+    # ------------------------------------------------------------------ construction sequences
+    SEQUENCE_GROUP = 32            # consecutive prefixes that share the factor rows of the group's first prefix
+                                   # (cantilever_beam_truss, 2197 prefixes: 8 -> 20.7 ms, 16 -> 16.8, 32 -> 15.5, 64 -> 16.4; independent 21.9)
+
+    def solve_sequence(self, order, want=('flag', 'status', 'max_trans', 'compliance'), group=None):
+        """Every prefix ``order[:k+1]`` of a construction sequence, with the factorisation REUSED along the sequence:
+        result row k is what ``solve_many`` returns for the subset ``order[:k+1]`` (same arithmetic in the same order
+        for every row of the factor, whether computed or shared).
+
+        The solver numbers the existing nodes in the handle's static ordering; a prefix differs from an earlier one by
+        the nodes and elements added since.  Every solver row in front of the first row that an added element touches -
+        or that a new node is inserted before - is identical in both.  Prefixes are therefore solved in groups of
+        ``group``: the first of a group completely (the trunk), the others share the trunk's factor rows (tiles of L,
+        inverted diagonal factors, pivots, forward solutions) in front of that row and factor only the rows behind it
+        (``cm_solve_many_host_seq``).  Replaces the loop ``for k: sc.solve(order[:k])`` of the sequencing planners
+        around the reference (README.rst:39-42, examples/notebook_demo/demo.ipynb), which re-assembles and re-factors
+        everything N times."""
+        self._push_loads()
+        order = [int(e) for e in order]
+        N, nE, nV = len(order), self.nE, self.nV
+        if N == 0:
+            return {name: np.zeros((0,) + self._out_shapes(0)[name][1:], dtype=_OUT_DTYPE[name]) for name in want}
+        oa = np.asarray(order, dtype=np.int64)
+        if oa.min() < 0 or oa.max() >= nE:
+            raise IndexError('element id not within range!')
+        if len(set(order)) != N:
+            raise ValueError('duplicate element id in the sequence')
+        group = int(group or self.SEQUENCE_GROUP)
+        t_rows = self._sequence_shared_rows(oa, group)
+        # prefix masks by a cumulative OR
+        W = self._info.mask_words
+        words = np.zeros((N, W), dtype=np.uint32)
+        words[np.arange(N), oa >> 5] = np.uint32(1) << (oa & 31).astype(np.uint32)
+        masks = np.bitwise_or.accumulate(words, axis=0)
+        shapes = self._out_shapes(N)
+        res = {name: np.empty(shapes[name], dtype=_OUT_DTYPE[name]) for name in OUT_FIELDS if name in want}
+        oh = _capi.SolveOutHost()
+        for name in OUT_FIELDS:
+            setattr(oh, name, res[name].ctypes.data if name in res else None)
+        _capi.check(self._lib.cm_solve_many_host_seq(self._handle, _ptr(masks), N, group, _ptr(t_rows), C.byref(oh)))
+        return res
+
+    def _sequence_shared_rows(self, oa, group):
+        """t_rows[k]: 32-row tile rows of prefix k's factor that equal those of the first prefix of its group.
+        In the trunk's compacted numbering a node at static position p - present or not - sits in front of solver row
+        cum[p] = (free DOFs of the trunk's nodes at positions < p); an added element touches the rows of its end nodes,
+        a new node is inserted in front of row cum[p]: everything in front of the smallest such row is untouched."""
+        N, nV = len(oa), self.nV
+        if getattr(self, '_static_pos', None) is None:
+            no = np.zeros(nV, dtype=np.int32)
+            _capi.check(self._lib.cm_get_node_order(self._handle, _ptr(no)))
+            pos = np.empty(nV, dtype=np.int64)
+            pos[no] = np.arange(nV)
+            self._static_pos, self._static_order = pos, no.astype(np.int64)
+        pos, no = self._static_pos, self._static_order
+        nfree = np.full(nV, 6, dtype=np.int64)
+        nfree[self._sup_node] = 6 - self._sup_cond.sum(axis=1)
+        ends = self._conn[oa].astype(np.int64)                                   # (N, 2)
+        appeared = np.full(nV, N, dtype=np.int64)                                # step at which a node first exists
+        np.minimum.at(appeared, ends.ravel(), np.repeat(np.arange(N), 2))
+        free_end = nfree[ends] > 0
+        t_rows = np.zeros(N, dtype=np.int32)
+        big = np.iinfo(np.int64).max
+        for g0 in range(0, N, group):
+            g1 = min(N, g0 + group)
+            if g1 - g0 < 2:
+                continue
+            trunk_rows = np.where(appeared[no] <= g0, nfree[no], 0)              # by static position
+            cum = np.concatenate([[0], np.cumsum(trunk_rows)])[:-1]
+            r = np.where(free_end[g0 + 1:g1], cum[pos[ends[g0 + 1:g1]]], big).min(axis=1)
+            t_rows[g0 + 1:g1] = np.minimum(np.minimum.accumulate(r) // 32, 2 ** 30).astype(np.int32)
+        return t_rows
 
     def solve_many_csr(self, flat_ids, offsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None):
         """``solve_many`` for subsets kept as two arrays: subset b = ``flat_ids[offsets[b]:offsets[b+1]]``

@@ -120,15 +120,22 @@ class StiffnessChecker(object):
             return flags, {k: r[k][:, 0].copy() for k in ('status', 'max_trans', 'compliance')}
         return flags
 
-    def solve_sequence(self, order, return_details=False):
-        """Stiffness check of EVERY prefix of a construction sequence in one batched pass: flag k
-        is ``solve(order[:k+1])``.  This is the loop the sequencing planners around the reference
-        run one solve at a time (README.rst:39-42, examples/notebook_demo/demo.ipynb); here the
-        prefix masks are built vectorised (cumulative OR) and solved together."""
+    def solve_sequence(self, order, return_details=False, reuse=True):
+        """Stiffness check of EVERY prefix of a construction sequence in one call: flag k is
+        ``solve(order[:k+1])``.  This is the loop the sequencing planners around the reference run one solve at a
+        time (README.rst:39-42, examples/notebook_demo/demo.ipynb).  ``reuse=True`` (default) reuses the
+        factorisation along the sequence (``CudaStiffness.solve_sequence``: prefixes share the factor rows in front of
+        the rows their added elements touch); ``reuse=False`` solves the N prefix masks as N independent subsets."""
         order = np.asarray(list(order), dtype=np.int64)
         nE = len(self.model.elements)
         if order.size and (order.min() < 0 or order.max() >= nE):
             raise IndexError('element id not within range!')
+        if reuse and order.size:
+            r = self._sc_ins.solve_sequence(order.tolist())
+            flags = [bool(f) for f in r['flag'][:, 0]]
+            if return_details:
+                return flags, {k: r[k][:, 0].copy() for k in ('status', 'max_trans', 'compliance')}
+            return flags
         W = (nE + 31) // 32
         words = np.zeros((len(order), W), dtype=np.uint32)
         words[np.arange(len(order)), order >> 5] = np.uint32(1) << (order & 31).astype(np.uint32)

@@ -43,6 +43,9 @@ def build_workload(spec):
         model = Model.from_json(os.path.join(REPO, 'tests', 'golden', 'models', m[1]))
     if spec['loads'] == 'config4':
         lcs = syn.config4_loadcases(model)
+    elif spec['loads'].startswith('json:'):
+        from conmech_b200 import LoadCase as LC
+        lcs = [LC.from_json(os.path.join(REPO, 'tests', 'golden', 'models', spec['loads'][5:]))]
     else:
         lcs = [LoadCase(gravity_load=GravityLoad([0, 0, -1]))]
     kind = spec['subsets']
@@ -55,6 +58,10 @@ def build_workload(spec):
     elif kind == 'bfs_prefixes':
         order = syn.bfs_sequence(model)
         sub = lambda s: order[:(s % len(order)) + 1]
+    elif kind.startswith('bfs_prefixes_spread:'):          # n prefixes evenly spread over the sequence
+        order = syn.bfs_sequence(model)
+        n = int(kind.split(':')[1])
+        sub = lambda s: order[:max(1, ((s % n) + 1) * len(order) // n)]
     else:
         sub = lambda s: []
     return model, lcs, sub
@@ -185,6 +192,8 @@ OTHER_CONFIGS = {
     'config2_tower_bfs_prefixes': {'model': ('json', 'tower_3D.json'), 'loads': 'gravity', 'subsets': 'bfs_prefixes', 'trans_tol': 1e-3},
     'config4_joints_4_loadcases': {'model': ('grid', 7, 7, 8, True), 'loads': 'config4', 'subsets': 'heightfield', 'trans_tol': 1e-3},
     'config5_10k_frame': {'model': ('grid', 15, 15, 16, False), 'loads': 'gravity', 'subsets': 'connected', 'trans_tol': 1e-3},
+    'config2_cantilever_bfs_prefixes': {'model': ('json', 'cantilever_beam_truss.json'), 'loads': 'json:cantilever_beam_truss_loadcase.json',
+                                        'subsets': 'bfs_prefixes_spread:64', 'trans_tol': 1e-3},
 }
 
 
@@ -247,6 +256,8 @@ def other_configs_record():
     out['config2_tower_bfs_prefixes'] = _rate_record(OTHER_CONFIGS['config2_tower_bfs_prefixes'], 24, 1, kind)
     out['config4_joints_4_loadcases'] = _rate_record(OTHER_CONFIGS['config4_joints_4_loadcases'], 6 * n_procs, n_procs, kind)
     out['config5_10k_frame'] = _rate_record(OTHER_CONFIGS['config5_10k_frame'], n_procs, n_procs, kind)
+    out['config2_cantilever_bfs_prefixes'] = _rate_record(OTHER_CONFIGS['config2_cantilever_bfs_prefixes'], 64, n_procs, kind)
+    out['config2_cantilever_bfs_prefixes']['sample'] += ' (64 prefixes evenly spread over the 2197-step sequence: the mean prefix)'
     out['many_shapes_one_topology'] = shapes_record()
     return out
 

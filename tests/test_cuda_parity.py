@@ -435,6 +435,71 @@ def test_cantilever_bfs_prefixes():
     assert [flags[k - 1] for k in ks] == [bool(f) for f in r['flag'][:, 0]]
 
 
+def _compare_results(a, b, tag):
+    """Two result sets of the same subsets from different solver orderings: integers / flags equal, values 1e-9."""
+    for k in ('flag', 'n_free', 'n_fixed', 'node_exists'):
+        assert_array_equal(a[k], b[k], err_msg='{} {}'.format(tag, k))
+    st_a, st_b = a['status'][:, 0], b['status'][:, 0]
+    assert_array_equal(st_a, st_b, err_msg=tag)
+    has_map = ~np.isin(st_a, (ST_NO_SUPPORT, 2))           # no DOF map without supports (the reference raises there)
+    assert_array_equal(a['dof_map'][has_map], b['dof_map'][has_map], err_msg=tag + ' dof_map')
+    for i in np.flatnonzero((st_a == ST_OK) | (st_a == ST_ZERO_LOAD)):
+        for k in ('U', 'Rf', 'eR'):
+            assert split_err(a[k][i, 0].ravel(), b[k][i, 0].ravel()) <= REL_TOL, (tag, k, i)
+        for k in ('max_trans', 'compliance'):
+            assert abs(a[k][i, 0] - b[k][i, 0]) <= REL_TOL * max(abs(b[k][i, 0]), 1e-300), (tag, k, i)
+
+
+def test_sequence_factor_reuse():
+    """solve_sequence reuses the factorisation along a construction sequence (node ordering by first
+    appearance, groups of prefixes sharing the factor rows of the group's first prefix).  Every prefix must come out as
+    from the independent batched path (flags / status / integer outputs equal, values 1e-9) and as the oracle says - for
+    BFS sequences, for a shuffled sequence (early prefixes without support: no sharing possible, fall-back paths), for
+    several group sizes (1 = no sharing at all) and with joint releases (singular prefixes)."""
+    import os
+    from conmech_b200 import synthetic as syn, Model, LoadCase, GravityLoad, StiffnessChecker
+    cases = []
+    tower = Model.from_json(os.path.join(MODELS, 'tower_3D.json'))
+    cases.append(('tower', tower, LoadCase(gravity_load=GravityLoad([0, 0, -1])), syn.bfs_sequence(tower)))
+    shuffled = list(range(len(tower.elements)))
+    random.Random(5).shuffle(shuffled)
+    cases.append(('tower-shuffled', tower, LoadCase(gravity_load=GravityLoad([0, 0, -1])), shuffled))
+    topo = Model.from_json(os.path.join(MODELS, 'topopt-100.json'))
+    cases.append(('topopt', topo, Golden('topopt-100__self_weight+point_load').loadcase(topo), syn.bfs_sequence(topo)))
+    grid = syn.grid_frame(4, 4, 4, joints=True, diagonals=True)
+    cases.append(('grid-joints', grid, LoadCase(gravity_load=GravityLoad([0, 0, -1])), syn.bfs_sequence(grid)))
+    for name, model, lc, order in cases:
+        sc, orc = make_pair(model, lc, 1e-3)
+        eng = sc._sc_ins
+        prefixes = [order[:k] for k in range(1, len(order) + 1)]
+        r_ind = eng.solve_many(prefixes, want=ALL)
+        for group in (1, 5, 16):
+            r_seq = eng.solve_sequence(order, want=ALL, group=group)
+            _compare_results(r_seq, r_ind, '{}-g{}'.format(name, group))
+        step = max(1, len(prefixes) // 24)
+        pick = list(range(0, len(prefixes), step))
+        check_against_oracle(eng, orc, [prefixes[i] for i in pick], {k: v[pick] for k, v in r_seq.items()}, tag='seq-' + name)
+        assert sc.solve_sequence(order) == [bool(f) for f in r_ind['flag'][:, 0]]
+        assert sc.solve_sequence(order, reuse=False) == sc.solve_sequence(order)
+    # the largest bundled model: all 2197 prefixes, reuse against the independent path
+    model = Model.from_json(os.path.join(MODELS, 'cantilever_beam_truss.json'))
+    lc = LoadCase.from_json(os.path.join(MODELS, 'cantilever_beam_truss_loadcase.json'))
+    sc, orc = make_pair(model, lc, 1e-3)
+    eng = sc._sc_ins
+    order = syn.bfs_sequence(model)
+    want = ('flag', 'status', 'n_free', 'n_fixed', 'max_trans', 'compliance')
+    r_seq = eng.solve_sequence(order, want=want)
+    r_ind = eng.solve_many([order[:k] for k in range(1, len(order) + 1)], want=want)
+    for k in ('flag', 'status', 'n_free', 'n_fixed'):
+        assert_array_equal(r_seq[k], r_ind[k], err_msg=k)
+    ok = (r_ind['status'][:, 0] == ST_OK) & (r_ind['max_trans'][:, 0] > 0)
+    assert ok.sum() > 400            # (point loads only: the early prefixes carry no load on their own nodes, U = 0)
+    assert np.max(np.abs(r_seq['max_trans'][ok] - r_ind['max_trans'][ok]) / r_ind['max_trans'][ok]) <= REL_TOL
+    ks = [10, 500, 1234, 2197]
+    check_against_oracle(eng, orc, [order[:k] for k in ks],
+                         {k: v[[x - 1 for x in ks]] for k, v in eng.solve_sequence(order, want=ALL).items()}, tag='seq-cantilever')
+
+
 def test_k2_shared_memory_window():
     """a model whose K2 dynamic shared memory falls between 44.9 and 48 KB (static + dynamic
     above the 48 KB no-opt-in limit) must launch.  Grids around 2.5k nodes sit in that window."""

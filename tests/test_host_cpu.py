@@ -27,7 +27,7 @@ def test_capi_loads_and_exports_header_symbols():
     # struct layouts the header promises
     import ctypes as C
     assert C.sizeof(_capi.SolveOut) == 18 * 8 and C.sizeof(_capi.SolveOutHost) == 18 * 8
-    assert C.sizeof(_capi.ModelDesc) == 16 + 6 * 8
+    assert C.sizeof(_capi.ModelDesc) == 16 + 7 * 8
 
 
 def test_engine_fails_loudly_without_gpu():
