@@ -177,6 +177,32 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this rank's host threads - and so place its pinned result buffers (first touch) - on
+    the CPUs of the NUMA node the GPU hangs off, so that eight ranks' device->host result copies do not all land in
+    one socket's memory.  Best effort; returns a note for the bench line."""
+    try:
+        out = subprocess.run(['nvidia-smi', '-i', str(index), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                             capture_output=True, text=True).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out            # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open('/sys/bus/pci/devices/{}/local_cpulist'.format(bus)) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return 'rank bound to {} CPUs local to GPU {} ({})'.format(len(cpus), index, spec)
+    except Exception as ex:
+        return 'numa binding skipped: {!r}'.format(ex)
+    return 'numa binding skipped: no local cpu list'
+
+
 def measured_peaks():
     try:
         with open(os.path.join(REPO, 'MEASURED_PEAKS.json')) as f:
@@ -398,6 +424,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -650,7 +677,7 @@ def main():
                                                  'half_bandwidth_full': info['half_bandwidth'],
                                                  'flags_true_last_step_rank0': flags_true,
                                                  'status_ok_last_step_rank0': status_ok}),
-                'value_flags_only': value_flags,
+                'value_flags_only': value_flags, 'host_placement': numa_note,
                 'clocks': clocks,
                 'e2e': {'value': e2e_full, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_full,
                         'outputs': 'U, Rf, eR, flag, status, max_trans, compliance per subset (pinned host arrays)',

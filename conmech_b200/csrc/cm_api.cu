@@ -858,12 +858,12 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
 }
 
 // Prefix-sharing groups (the construction-sequence path).  Consecutive subsets of one group
-// are prefixes of ONE construction sequence in a node ordering where nodes are numbered by first appearance (the
-// handle was created with that ordering: cm_model_desc.node_order): the matrix of a later prefix differs from the
-// first subset of its group (the "trunk") only in solver rows >= the first row touched by the elements added since.
-// The trunk is factored completely; a "tail" subset b factors only the tile rows >= t_rows[b] and reads the rows above
-// from the trunk's slab (tiles of L, M_J, pivots, forward solutions) - in the factorisation AND in the back
-// substitution.  Waves hold whole groups; trunks are factored by one launch, tails by the next.
+// are prefixes of ONE construction sequence: in the handle's static node ordering the matrix of a later prefix differs
+// from the first subset of its group (the "trunk") only at and behind the first solver row that an added element
+// touches or a new node is inserted in front of.  The trunk is factored completely; a "tail" subset b factors only the
+// tile rows >= t_rows[b] and reads the rows above from the trunk's slab (tiles of L, M_J, pivots, forward solutions) -
+// in the factorisation AND in the back substitution.  Waves hold whole groups; the trunks are assembled and factored
+// first, beside the assembly of the tails on a second stream.
 int cm_solve_many_host_seq(cm_handle *h, const uint32_t *masks_host, int64_t B, int32_t group, const int32_t *t_rows_host,
                            const cm_solve_out_host *o) {
     if (!t_rows_host || group < 1) return fail(CM_ERR_INVALID, "cm_solve_many_host_seq: group >= 1 and t_rows required");

@@ -103,7 +103,7 @@ __device__ double block_nanmax(double v, double *s_red) {
 // dependent global round trips.  NB load cases share one pass over L (every tile is read once for
 // the NB right-hand sides); the recovery below then runs per load case.
 template <bool XS, int NB>
-__global__ void __launch_bounds__(K4_THREADS)
+__global__ void __launch_bounds__(K4_THREADS, NB == 1 ? 4 : (NB == 2 ? 2 : 1))      // 64 / 128 / 255 registers
 k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks, const int *geom, long long first,
                  cm_out_dev out) {
     static_assert(XS || NB == 1, "several right-hand sides per pass need the shared-memory vectors");

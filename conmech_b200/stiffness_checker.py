@@ -120,6 +120,8 @@ class StiffnessChecker(object):
             return flags, {k: r[k][:, 0].copy() for k in ('status', 'max_trans', 'compliance')}
         return flags
 
+    SEQUENCE_REUSE_MIN = 256       # shorter sequences are one small batch: the independent path has less launch overhead
+
     def solve_sequence(self, order, return_details=False, reuse=True):
         """Stiffness check of EVERY prefix of a construction sequence in one call: flag k is
         ``solve(order[:k+1])``.  This is the loop the sequencing planners around the reference run one solve at a
@@ -130,7 +132,7 @@ class StiffnessChecker(object):
         nE = len(self.model.elements)
         if order.size and (order.min() < 0 or order.max() >= nE):
             raise IndexError('element id not within range!')
-        if reuse and order.size:
+        if reuse and order.size >= self.SEQUENCE_REUSE_MIN:
             r = self._sc_ins.solve_sequence(order.tolist())
             flags = [bool(f) for f in r['flag'][:, 0]]
             if return_details:

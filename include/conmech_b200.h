@@ -69,8 +69,7 @@ typedef struct cm_model_desc {
                              /*   rotational pin rule (numpy_stiffness.py:179-181)               */
     const int32_t *node_order; /* [n_nodes] solver ordering, position -> node id (a permutation), or  */
                              /*   NULL: the library picks the better of natural and reverse        */
-                             /*   Cuthill-McKee.  The sequence path passes "order of first          */
-                             /*   appearance in the construction sequence" (cm_solve_many_host_seq). */
+                             /*   Cuthill-McKee (by envelope work of the full structure).            */
 } cm_model_desc;
 
 /* Static facts about a created model (sizes a caller needs to allocate outputs). */
@@ -238,16 +237,18 @@ int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t
 /* Construction sequences (callers: the sequencing loops sketched at reference
  * README.rst:39-42 and examples/notebook_demo/demo.ipynb, which call solve(order[:k]) for k = 1..N and
  * re-assemble and re-factor everything N times).  The B subsets are consecutive PREFIXES of one
- * construction sequence, on a handle whose node_order numbers the nodes by first appearance in that
- * sequence - so that every prefix's free DOFs are a leading block of the next prefix's.  The batch is cut
- * into groups of `group` consecutive prefixes.  The first prefix of a group (the "trunk") is factored
- * completely; a later prefix b of the group differs from the trunk only in solver rows at or behind the
- * first row touched by the elements added since, so it shares the first t_rows[b] 32-row tile rows of the
- * factor (L, the inverted diagonal factors, pivots, forward solutions) with the trunk: those rows are
- * neither assembled nor factored again, and the back substitution reads them from the trunk.  t_rows[b]
- * = floor(first modified solver row / 32), 0 for the first prefix of every group (host array [B]; the
- * Python engine computes it).  Results are those of cm_solve_many_host on the same handle (same
- * arithmetic in the same order), at a fraction of the assembly and factorisation work. */
+ * construction sequence; the batch is cut into groups of `group` consecutive prefixes.  The solver numbers
+ * the existing nodes of a subset in the handle's static ordering, so a later prefix differs from the first
+ * prefix of its group (the "trunk") only at and behind the first solver row that an added element touches or
+ * in front of which a new node is inserted.  The trunk is factored completely; prefix b shares the first
+ * t_rows[b] 32-row tile rows of the factor (L, the inverted diagonal factors, pivots, forward solutions)
+ * with it: those rows are not factored again, and the back substitution reads them from the trunk.
+ * t_rows[b] = floor(first differing solver row / 32) in the trunk's numbering, 0 for the first prefix of
+ * every group (host array [B]; CudaStiffness.solve_sequence computes it from the node ordering of
+ * cm_get_node_order).  A prefix whose trunk cannot be used (not solvable, different Jacobi-scaling
+ * decision, bad pivot inside the shared rows) is factored on its own.  Results are those of
+ * cm_solve_many_host on the same masks: every row of the factor is the same arithmetic in the same
+ * order, whether computed or shared. */
 int cm_solve_many_host_seq(cm_handle *h, const uint32_t *masks_host, int64_t B, int32_t group,
                            const int32_t *t_rows_host, const cm_solve_out_host *out);
 

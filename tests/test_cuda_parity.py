@@ -479,6 +479,7 @@ def test_sequence_factor_reuse():
         step = max(1, len(prefixes) // 24)
         pick = list(range(0, len(prefixes), step))
         check_against_oracle(eng, orc, [prefixes[i] for i in pick], {k: v[pick] for k, v in r_seq.items()}, tag='seq-' + name)
+        sc.SEQUENCE_REUSE_MIN = 1                   # (the facade only reuses for long sequences; force it here)
         assert sc.solve_sequence(order) == [bool(f) for f in r_ind['flag'][:, 0]]
         assert sc.solve_sequence(order, reuse=False) == sc.solve_sequence(order)
     # the largest bundled model: all 2197 prefixes, reuse against the independent path
