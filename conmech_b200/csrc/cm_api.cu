@@ -66,6 +66,10 @@ struct cm_handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t slot_done[CM_STAGE_SLOTS] = {}, slot_free[CM_STAGE_SLOTS] = {};
     cudaEvent_t copy_ev = nullptr;
+    // one copy stream per lane: the results of a wave leave when ITS kernels are done, not behind the copies of waves
+    // that were enqueued earlier but finish later on another lane
+    cudaStream_t copy_lane[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int overlap = 1;
     int n_lanes = 3;                     // CM_LANES=1..4: 2 lanes 250 k, 3 lanes 255 k, 4 lanes 255 k solves/s on config 3
 };
@@ -381,6 +385,10 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot_free[i], cudaEventDisableTiming);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming);
+    for (int i = 0; i < 4 && ce == cudaSuccess; ++i) {
+        ce = cudaStreamCreateWithFlags(&h->copy_lane[i], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->copy_lane_ev[i], cudaEventDisableTiming);
+    }
     if (const char *e = getenv("CM_LANES")) { int n = atoi(e); if (n >= 1 && n <= 4) h->n_lanes = n; }
     if (const char *e = getenv("CM_NO_OVERLAP")) h->overlap = (e[0] == '1') ? 0 : 1;
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev[0], h->stream);
@@ -417,6 +425,10 @@ int cm_destroy(cm_handle *h) {
     }
     if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 4; ++i) {
+        if (h->copy_lane_ev[i]) cudaEventDestroy(h->copy_lane_ev[i]);
+        if (h->copy_lane[i]) cudaStreamDestroy(h->copy_lane[i]);
+    }
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     for (int i = 0; i < 3; ++i) if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
     delete h;
@@ -665,7 +677,7 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
 // the caller's stream: a factorisation launch drains over roughly one CTA lifetime, and the other
 // lanes' kernels fill the SMs it frees.  Every wave is independent (own subsets, own outputs, own
 // share of the workspace).
-struct WavePlan { bool lanes; int NL; long long cap, n_waves, wsize; };
+struct WavePlan { bool lanes; int NL; long long cap, n_waves, wsize; std::vector<int> sizes; };      // sizes: empty = equal waves of wsize
 // max_wave > 0: upper bound for the subsets of one wave (the host entry point with large outputs wants waves whose
 // device->host copy is short, see cm_solve_many_host_g)
 static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *p, long long max_wave = 0) {
@@ -681,6 +693,35 @@ static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *
     p->n_waves = (B + p->cap - 1) / p->cap;
     if (p->lanes && getenv("CM_WAVE_ROUND") && atoi(getenv("CM_WAVE_ROUND")) && p->n_waves % p->NL) p->n_waves += p->NL - p->n_waves % p->NL;   // experiment: same number of waves per lane
     p->wsize = (B + p->n_waves - 1) / p->n_waves;
+    p->sizes.clear();
+    // Large outputs (max_wave > 0): the results of a wave exist when its last kernel has finished, so whatever the last
+    // waves of the lanes produce is copied to the host AFTER the kernels have ended - an unhidden tail of about three
+    // waves' results with equal waves (5 ms of a 49 ms call on the 1k-element frame).  The waves therefore shrink
+    // geometrically towards the end of the batch (by 0.8 per wave down to 4/3 CTAs per SM; 70 % / two per SM measured
+    // 46.6, 80 % / 1.35 per SM 46.3 ms per 12 500 full-result subsets, equal waves 48.6): what is still to be copied when
+    // the last kernel ends is small, and the waves in front of them stay large.
+    static const int taper_pct = getenv("CM_TAPER") ? atoi(getenv("CM_TAPER")) : 80;
+    static const int taper_min = getenv("CM_TAPER_MIN") ? atoi(getenv("CM_TAPER_MIN")) : 0;
+    static const int stagger = getenv("CM_STAGGER") ? atoi(getenv("CM_STAGGER")) : 0;     // first waves of the lanes 1/NL, 2/NL, ... of a wave
+    if (max_wave > 0 && p->lanes && p->n_waves > 2 * p->NL && ((taper_pct > 0 && taper_pct < 100) || stagger)) {
+        const long long wmin = taper_min > 0 ? taper_min : std::max(32, 4 * h->m.n_sm / 3);
+        std::vector<int> head, tail;             // tail: from the end of the batch backwards
+        long long t_sum = 0;
+        if (stagger)
+            for (int i = 1; i < p->NL; ++i) { head.push_back((int)std::max<long long>(wmin, p->wsize * i / p->NL)); t_sum += head.back(); }
+        if (taper_pct > 0 && taper_pct < 100)
+            for (double v = (double)wmin; v < (double)p->wsize && t_sum + (long long)v < B / 2; v = v * 100.0 / taper_pct) {
+                tail.push_back((int)v);
+                t_sum += (long long)v;
+            }
+        const long long rest = B - t_sum;
+        const long long n_full = (rest + p->wsize - 1) / p->wsize;
+        const long long full = (rest + n_full - 1) / n_full;
+        p->sizes = head;
+        for (long long r = rest; r > 0; r -= full) p->sizes.push_back((int)std::min<long long>(full, r));
+        for (size_t i = tail.size(); i-- > 0;) p->sizes.push_back(tail[i]);
+        p->n_waves = (long long)p->sizes.size();
+    }
     return CM_OK;
 }
 
@@ -719,8 +760,9 @@ static int run_waves(cm_handle *h, const uint32_t *masks, const int *geom, const
         for (int i = 0; i < P.NL; ++i) CU(cudaStreamWaitEvent(h->lane_stream[i], h->lane_ev[0], 0));
     }
     long long w = 0;
-    for (long long first = 0; first < B; first += P.wsize, ++w) {
-        const int count = (int)std::min<long long>(P.wsize, B - first);
+    for (long long first = 0, step = 0; first < B; first += step, ++w) {
+        step = P.sizes.empty() ? P.wsize : P.sizes[(size_t)w];
+        const int count = (int)std::min<long long>(step, B - first);
         cudaStream_t ls = P.lanes ? h->lane_stream[w % P.NL] : st;
         char *lws = P.lanes ? ws + (size_t)(w % P.NL) * (size_t)P.cap * per : ws;
         cm_out_dev od = od0;
@@ -938,6 +980,7 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         const long long n_groups = (B + group - 1) / group;
         const long long n_w = (n_groups + cap_groups - 1) / cap_groups;
         P.lanes = false;
+        P.sizes.clear();
         P.n_waves = n_w;
         P.wsize = (n_groups + n_w - 1) / n_w * group;
         P.cap = P.wsize;
@@ -956,12 +999,22 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         h->stage_bytes = need;
     }
     cudaStream_t st = h->stream;
+    // CM_WAVE_TRACE=1 (debug aid): device timeline of the call on stderr - per wave, when its first kernel started, when
+    // its last kernel ended and when its results were on the host, in ms from the start of the call
+    static const bool trace = getenv("CM_WAVE_TRACE") && atoi(getenv("CM_WAVE_TRACE"));
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(1 + 3 * (size_t)P.n_waves);
+        for (auto &e : tev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(tev[0], st));
+    }
     CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
     if (aux_host) CU(cudaMemcpyAsync(h->d_geom, aux_host, Bn * sizeof(int), cudaMemcpyHostToDevice, st));
     char *slots = h->stage + mask_bytes;
     auto before = [&](long long w, long long first, int, cudaStream_t ls, cm_out_dev &od) -> int {
         const int s = (int)(w % n_slots);
         if (w >= n_slots) CU(cudaStreamWaitEvent(ls, h->slot_free[s], 0));      // the slot's previous copies are done
+        if (trace) CU(cudaEventRecord(tev[1 + 3 * (size_t)w], ls));
         // the kernels index their outputs by the subset's position in the batch: bias the slot pointers
         char *base = slots + (size_t)s * slot_bytes;
         auto bp = [&](int i) -> char * { return it[i].host ? base + it[i].off - (size_t)first * it[i].stride : nullptr; };
@@ -972,25 +1025,52 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         od.max_abs_sigma = (double *)bp(15); od.profile_entries = (double *)bp(16); od.envelope_tiles = (double *)bp(17);
         return CM_OK;
     };
+    // The waves of one lane finish in order, the waves of different lanes do not (wave 1 may be done 3 ms before wave 0):
+    // with ONE copy stream the copies would leave in enqueue order, each behind the kernels of every earlier wave.
+    static const bool copy_lanes = !(getenv("CM_COPY_LANES") && atoi(getenv("CM_COPY_LANES")) == 0);
+    auto copy_stream_of = [&](long long w) { return (P.lanes && copy_lanes) ? h->copy_lane[w % P.NL] : h->copy_stream; };
     auto after = [&](long long w, long long first, int count, cudaStream_t ls) -> int {
         const int s = (int)(w % n_slots);
         char *base = slots + (size_t)s * slot_bytes;
+        cudaStream_t cs = copy_stream_of(w);
         CU(cudaEventRecord(h->slot_done[s], ls));
-        CU(cudaStreamWaitEvent(h->copy_stream, h->slot_done[s], 0));
+        if (trace) CU(cudaEventRecord(tev[2 + 3 * (size_t)w], ls));
+        CU(cudaStreamWaitEvent(cs, h->slot_done[s], 0));
         for (int i = 0; i < N_OUT; ++i)
             if (it[i].host)
                 CU(cudaMemcpyAsync(static_cast<char *>(it[i].host) + (size_t)first * it[i].stride, base + it[i].off,
-                                   (size_t)count * it[i].stride, cudaMemcpyDeviceToHost, h->copy_stream));
-        CU(cudaEventRecord(h->slot_free[s], h->copy_stream));
+                                   (size_t)count * it[i].stride, cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(h->slot_free[s], cs));
+        if (trace) CU(cudaEventRecord(tev[3 + 3 * (size_t)w], cs));
         return CM_OK;
     };
     cm_out_dev od0{};
     int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), geom_host ? h->d_geom : nullptr,
                        trows_host ? h->d_geom : nullptr, trows_host ? group : 0, B, od0, h->wsbuf, P, st, before, after);
     if (rc != CM_OK) { cudaDeviceSynchronize(); return rc; }
-    CU(cudaEventRecord(h->copy_ev, h->copy_stream));
-    CU(cudaStreamWaitEvent(st, h->copy_ev, 0));
+    if (P.lanes && copy_lanes) {
+        for (int i = 0; i < P.NL; ++i) {
+            CU(cudaEventRecord(h->copy_lane_ev[i], h->copy_lane[i]));
+            CU(cudaStreamWaitEvent(st, h->copy_lane_ev[i], 0));
+        }
+    } else {
+        CU(cudaEventRecord(h->copy_ev, h->copy_stream));
+        CU(cudaStreamWaitEvent(st, h->copy_ev, 0));
+    }
     CU(cudaStreamSynchronize(st));
+    if (trace) {
+        long long first = 0;
+        for (long long w = 0; w < P.n_waves; ++w) {
+            const long long cnt = std::min<long long>(P.sizes.empty() ? P.wsize : P.sizes[(size_t)w], B - first);
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * (size_t)w]);
+            cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * (size_t)w]);
+            cudaEventElapsedTime(&c, tev[0], tev[3 + 3 * (size_t)w]);
+            fprintf(stderr, "[cm wave %2lld lane %lld] %5lld subsets  start %7.2f  kernels done %7.2f  on host %7.2f ms\n", w, w % P.NL, cnt, a, b, c);
+            first += cnt;
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     return CM_OK;
 }
 

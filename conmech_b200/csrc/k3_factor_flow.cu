@@ -125,7 +125,12 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
     // memory); the chain tile completes the diagonal tile and hands it to the factorisation
     const bool chain = J == I - 1;
     diag_term(acc, chain, dk, CTX(s_scr),
-              CTX(s_dacc) + (threadIdx.x >> 5) * 320, max(kcI - 8 * J, 0) >> 1, lane);
+#if defined(CM_EXP_DACC1)
+              CTX(s_dacc),
+#else
+              CTX(s_dacc) + (threadIdx.x >> 5) * 320,
+#endif
+              max(kcI - 8 * J, 0) >> 1, lane);
     if (chain) FP_ADD(pc, 11); else FP_ADD(pc, 4);
     return chain;
 }
@@ -135,7 +140,10 @@ template <int NW, bool PROF, int OPS>
 #ifndef CM_K3_CTAS4
 #define CM_K3_CTAS4 4          // resident 4-warp CTAs per SM the register allocation aims at (timing experiments: 5)
 #endif
-__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 4 ? (OPS ? 3 : CM_K3_CTAS4) : (NW <= 16 ? 16 / NW : 1)))
+#ifndef CM_K3_RING_CTAS
+#define CM_K3_RING_CTAS 3       // the same for the operand-ring builds
+#endif
+__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 4 ? (OPS ? CM_K3_RING_CTAS : CM_K3_CTAS4) : (NW <= 16 ? 16 / NW : 1)))
 k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) {
     extern __shared__ __align__(16) double smem[];
     double *s_scr = smem;                                            // [DSCR] diagonal scratch (shared by the CTA)
@@ -143,7 +151,11 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
     double *s_part = s_rhs + NW * 32;                                // [NW][n_lc][32] pending forward sums of the rows in progress
     double *s_minpiv = s_part + NW * m.n_lc * 32;                    // [NW]
     double2 *s_dacc = reinterpret_cast<double2 *>(s_minpiv + NW + (NW & 1));   // [NW][10][32] pending diagonal-tile sums (16-byte aligned)
+#if defined(CM_EXP_DACC1)       // timing experiment (wrong results): one pending-sum region for all warps
+    int *s_prog = reinterpret_cast<int *>(s_dacc + 320);
+#else
     int *s_prog = reinterpret_cast<int *>(s_dacc + NW * 320);        // [n_tile_rows_max] factor progress
+#endif
     int *s_yprog = s_prog + m.n_tile_rows_max;                       // rows forward-substituted
     int *s_fail = s_yprog + 1;
     int *s_kcol = s_yprog + 4;                                       // [n_tile_rows_max] envelope: first nonzero k-step of each row
@@ -232,7 +244,11 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
     if (PROF && lane == 0) for (int i = 0; i < 16; ++i) pc[i] = 0;
     const long long tstart = PROF ? clock64() : 0;
     double *s_part_w = s_part + warp * n_lc * 32;
+#if defined(CM_EXP_DACC1)
+    double2 *s_dacc_w = s_dacc;
+#else
     double2 *s_dacc_w = s_dacc + warp * 320;
+#endif
     for (int I = warp + (trows + NW - 1 - warp) / NW * NW; I < NT; I += NW) {      // this warp's first row >= trows
         const int kcI = s_kcol[I];               // first nonzero column of the row in k-steps (even)
         const int kfI = kcI >> 3;                // = kfirst[I], the first tile column of the row
@@ -296,7 +312,12 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
 }
 
 size_t flow_smem(const cm_model_dev &m, int nw, int ops) {
-    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw + (nw & 1) + nw * 640) * sizeof(double) +
+#if defined(CM_EXP_DACC1)
+    const int ndacc = 1;
+#else
+    const int ndacc = nw;
+#endif
+    return (size_t)(DSCR + nw * 32 + nw * std::max(1, m.n_lc) * 32 + nw + (nw & 1) + ndacc * 640) * sizeof(double) +
            (size_t)(2 * m.n_tile_rows_max + 8) * sizeof(int) + (size_t)m.n_tile_rows_max * ((m.band_tiles + 63) >> 6) * sizeof(unsigned long long) +
            (ops ? 128 + (size_t)nw * ops * (CM_RING_STAGE_BYTES + 8) + (size_t)nw * 4 : 0);
 }
