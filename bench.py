@@ -535,8 +535,28 @@ def main():
     pcie_d2h_gbs = (1 << 30) / (e0.elapsed_time(e1) * 1e-3) / 1e9
     del probe_d, probe_h
     torch.cuda.empty_cache()
-    e2e_full = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=FULL, out=out_host))
-    d2h_full = int(sum(out_host[n].nbytes for n in FULL))
+    e2e_dense = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=FULL, out=out_host))
+    d2h_dense = int(sum(out_host[n].nbytes for n in FULL))
+    # the same results without zero padding - what the reference's get_solved_results() returns: displacements, the
+    # reactions of the support nodes, the end forces of the EXISTING elements (rows in ascending element id)
+    COMPACT = ('flag', 'status', 'max_trans', 'compliance', 'U', 'Rf_sup', 'eR_rows')
+    outs_c = []
+    for hm in host_np:
+        oc = {n: out_host[n] for n in ('flag', 'status', 'max_trans', 'compliance', 'U')}
+        oc['Rf_sup'] = pin((B, 1, len(model.supports), 6), torch.float64)
+        oc['eR_rows'] = pin((int(eng.element_row_offsets(hm)[-1]), 12), torch.float64)
+        outs_c.append(oc)
+    e2e_full = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=COMPACT, out=outs_c[k % n_batches]))
+    d2h_full = int(sum(sum(oc[n].nbytes for n in COMPACT) for oc in outs_c) // len(outs_c))
+    # compact rows == dense rows of the existing elements (same bits), support reactions == dense reactions there
+    rc = eng.solve_many(host_np[0], want=COMPACT, out=outs_c[0])
+    eng.solve_many(host_np[0], want=FULL, out=out_host)
+    off = rc['eR_row_offsets']
+    sup_ids = np.array(list(model.supports.keys()))
+    assert np.array_equal(rc['Rf_sup'], out_host['Rf'].reshape(B, 1, -1, 6)[:, :, sup_ids])
+    for b in range(0, B, 97):
+        ids = cm_masks.mask_to_ids(host_np[0][b], nE)
+        assert np.array_equal(rc['eR_rows'][off[b]:off[b + 1]], out_host['eR'][b, 0][ids]), b
     # the host path and the device path deliver the same bits
     eng.solve_many(host_np[0], want=FULL, out=out_host)
     step_device(0, FULL)
@@ -680,12 +700,16 @@ def main():
                 'value_flags_only': value_flags, 'host_placement': numa_note,
                 'clocks': clocks,
                 'e2e': {'value': e2e_full, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_full,
-                        'outputs': 'U, Rf, eR, flag, status, max_trans, compliance per subset (pinned host arrays)',
+                        'outputs': 'per subset, to pinned host arrays: flag, status, max_trans, compliance, U (6 nV), the reactions of the '
+                                   'support nodes (nS x 6) and the end forces of the EXISTING elements (12 per element) - the content of '
+                                   'the reference\'s get_solved_results(), no zero padding; checked against the dense arrays in this run',
                         'd2h_gbs': d2h_full * e2e_full / (world * B) / 1e9,
                         'pcie_d2h_gbs_measured': pcie_d2h_gbs,
                         'fraction_of_device_resident': e2e_full / value,
-                        'note': 'every wave\'s results are copied to the host by a copy stream while later waves compute; what is left '
-                                'is the copy of the last waves, which finish together',
+                        'dense_value': e2e_dense, 'dense_d2h_bytes_per_step': d2h_dense,
+                        'dense_what': 'the same with zero-padded arrays: Rf over all 6 nV DOFs, eR rows for all nE elements (127 KB per solve)',
+                        'note': 'every wave\'s results are copied to the host by the copy stream of its lane while later waves compute; the '
+                                'waves shrink towards the end of the batch so that little is left to copy when the last kernel ends',
                         'flags_only_value': e2e_flags, 'flags_only_d2h_bytes_per_step': d2h_flags,
                         'id_lists_value': e2e_lists,
                         'id_lists_what': 'StiffnessChecker.solve_many(list of Python id lists) -> list of bools, packing included'},

@@ -31,7 +31,7 @@ class ModelInfo(C.Structure):
 
 OUT_FIELDS = ('flag', 'status', 'n_free', 'n_fixed', 'dof_map', 'node_exists', 'U', 'Rf', 'eR',
               'compliance', 'max_trans', 'max_rot', 'min_pivot', 'profile_flops', 'sigma_max', 'max_abs_sigma',
-              'profile_entries', 'envelope_tiles')
+              'profile_entries', 'envelope_tiles', 'Rf_sup', 'eR_rows', 'eR_row_offsets')
 
 
 class SolveOut(C.Structure):
@@ -46,7 +46,7 @@ class SolveOutHost(C.Structure):
 SYMBOLS = ('cm_pack_elements', 'cm_create', 'cm_destroy', 'cm_get_info', 'cm_get_element_tables', 'cm_get_node_order',
            'cm_set_geometries', 'cm_geometry_count', 'cm_get_geometry_tables', 'cm_last_element_kernel_ms',
            'cm_solve_many_g', 'cm_solve_many_host_g', 'cm_solve_many_host_seq',
-           'cm_set_loadcases', 'cm_get_element_loads', 'cm_set_tol', 'cm_set_variant', 'cm_debug_k3_phase_cycles',
+           'cm_set_loadcases', 'cm_get_element_loads', 'cm_set_tol', 'cm_set_variant', 'cm_debug_k3_phase_cycles', 'cm_debug_k2_phase_cycles',
            'cm_workspace_bytes', 'cm_solve_many', 'cm_solve_many_host', 'cm_solve_many_host_chunks', 'cm_solve_many_host_multi', 'cm_kernel_launches',
            'cm_reset_counters', 'cm_enable_timing', 'cm_last_stage_ms', 'cm_last_wave_count', 'cm_element_kernel_dev',
            'cm_last_error', 'cm_version')
@@ -84,6 +84,7 @@ def load():
     lib.cm_set_tol.argtypes = [H, C.c_double, C.c_double]
     lib.cm_set_variant.argtypes = [H, C.c_int32]
     lib.cm_debug_k3_phase_cycles.argtypes = [H, C.c_void_p]
+    lib.cm_debug_k2_phase_cycles.argtypes = [H, C.c_void_p]
     lib.cm_workspace_bytes.argtypes = [H, C.c_int64]
     lib.cm_workspace_bytes.restype = C.c_size_t
     lib.cm_solve_many.argtypes = [H, C.c_uint64, C.c_int64, C.POINTER(SolveOut), C.c_uint64, C.c_size_t, C.c_uint64]

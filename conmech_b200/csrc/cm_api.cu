@@ -36,6 +36,8 @@ struct cm_handle {
     std::vector<int32_t> conn;           // host copy of the connectivity (length checks of new geometries)
     int *d_geom = nullptr;               // staging of the per-subset geometry indices of the host entry point
     size_t geom_cap = 0;
+    long long *d_rowoff = nullptr;       // device copy of the caller's eR_row_offsets (compact element rows)
+    size_t rowoff_cap = 0;
     size_t geom_tables_cap = 1;          // geometry variants the stacked tables have room for
     double k1_ms = 0.0;                  // device time of the most recent element-table launch
     // load tables
@@ -412,7 +414,7 @@ int cm_destroy(cm_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->d_q) cudaFree(h->d_q);
     if (h->d_pnodal) cudaFree(h->d_pnodal);
-    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_Kt); cudaFree(h->d_R3); cudaFree(h->d_elen); cudaFree(h->d_geom);
+    cudaFree(h->d_xyz); cudaFree(h->d_Kg); cudaFree(h->d_Kt); cudaFree(h->d_R3); cudaFree(h->d_elen); cudaFree(h->d_geom); cudaFree(h->d_rowoff);
     if (h->stage) cudaFree(h->stage);
     if (h->wsbuf) cudaFree(h->wsbuf);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -669,6 +671,14 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
     return CM_OK;
 }
 
+int cm_debug_k2_phase_cycles(cm_handle *h, uint64_t *out8) {   // 16 slots    // phase counters of a -DK2_PROF=1 build of the assembly kernel (zeros otherwise)
+    if (!h || !out8) return fail(CM_ERR_INVALID, "cm_debug_k2_phase_cycles: null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    CU(cm_k2_read_prof(reinterpret_cast<unsigned long long *>(out8)));
+    return CM_OK;
+}
+
 }  // extern "C"
 
 // ---- wave plan.  The batch is cut into equal waves (a short last wave would leave most SMs idle).
@@ -680,7 +690,7 @@ int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16) {   // variant 4 (in
 struct WavePlan { bool lanes; int NL; long long cap, n_waves, wsize; std::vector<int> sizes; };      // sizes: empty = equal waves of wsize
 // max_wave > 0: upper bound for the subsets of one wave (the host entry point with large outputs wants waves whose
 // device->host copy is short, see cm_solve_many_host_g)
-static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *p, long long max_wave = 0) {
+static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *p, long long max_wave = 0, size_t out_per_subset = 0) {
     const size_t per = h->L.per_subset;
     long long wave = (long long)(ws_bytes / per);
     if (wave < 1) return fail(CM_ERR_NOMEM, "cm_solve_many: workspace smaller than one subset (" + std::to_string(per) + " bytes)");
@@ -704,7 +714,9 @@ static int plan_waves(const cm_handle *h, int64_t B, size_t ws_bytes, WavePlan *
     static const int taper_min = getenv("CM_TAPER_MIN") ? atoi(getenv("CM_TAPER_MIN")) : 0;
     static const int stagger = getenv("CM_STAGGER") ? atoi(getenv("CM_STAGGER")) : 0;     // first waves of the lanes 1/NL, 2/NL, ... of a wave
     if (max_wave > 0 && p->lanes && p->n_waves > 2 * p->NL && ((taper_pct > 0 && taper_pct < 100) || stagger)) {
-        const long long wmin = taper_min > 0 ? taper_min : std::max(32, 4 * h->m.n_sm / 3);
+        // smallest wave: about half a millisecond of device->host copy (26 MB), not below 4/3 CTAs per SM
+        const long long wmin = taper_min > 0 ? taper_min
+                                             : std::max<long long>(4 * h->m.n_sm / 3, out_per_subset ? (26ll << 20) / (long long)out_per_subset : 0);
         std::vector<int> head, tail;             // tail: from the end of the batch backwards
         long long t_sum = 0;
         if (stagger)
@@ -745,6 +757,10 @@ static cm_out_dev out_dev_of(const cm_solve_out *o) {
     od.max_abs_sigma = reinterpret_cast<double *>(o->max_abs_sigma);
     od.profile_entries = reinterpret_cast<double *>(o->profile_entries);
     od.envelope_tiles = reinterpret_cast<double *>(o->envelope_tiles);
+    od.Rf_sup = reinterpret_cast<double *>(o->Rf_sup);
+    od.eR_rows = reinterpret_cast<double *>(o->eR_rows);
+    od.eR_row_offsets = reinterpret_cast<const long long *>(o->eR_row_offsets);
+    od.row_bias = 0;             // (device entry points: off[0] == 0)
     return od;
 }
 
@@ -839,6 +855,7 @@ int cm_solve_many_g(cm_handle *h, uint64_t masks_dev, uint64_t geom_dev, int64_t
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
     if (!masks_dev || !ws_dev) return fail(CM_ERR_INVALID, "cm_solve_many: null device buffer");
+    if (o->eR_rows && !o->eR_row_offsets) return fail(CM_ERR_INVALID, "cm_solve_many: eR_rows needs eR_row_offsets");
     WavePlan P;
     { int rc = plan_waves(h, B, ws_bytes, &P); if (rc != CM_OK) return rc; }
     CU(cudaSetDevice(h->device));
@@ -854,7 +871,7 @@ int cm_solve_many_g(cm_handle *h, uint64_t masks_dev, uint64_t geom_dev, int64_t
 // per-subset bytes of every output of cm_solve_out_host, in the order of the struct
 namespace {
 struct OutItem { void *host; size_t stride; size_t off; };       // stride = bytes per subset; off = offset inside a staging slot
-constexpr int N_OUT = 18;
+constexpr int N_OUT = 19;      // fixed-stride outputs; eR_rows (rows of the existing elements only) is handled beside them
 void out_items(const cm_handle *h, const cm_solve_out_host *o, OutItem (&it)[N_OUT]) {
     const size_t nV = h->m.nV, nE = h->m.nE, Lc = h->m.n_lc;
     const OutItem t[N_OUT] = {
@@ -862,7 +879,7 @@ void out_items(const cm_handle *h, const cm_solve_out_host *o, OutItem (&it)[N_O
         {o->node_exists, nV, 0}, {o->U, Lc * 6 * nV * 8, 0}, {o->Rf, Lc * 6 * nV * 8, 0}, {o->eR, Lc * nE * 12 * 8, 0},
         {o->compliance, Lc * 8, 0}, {o->max_trans, Lc * 8, 0}, {o->max_rot, Lc * 8, 0}, {o->min_pivot, 8, 0},
         {o->profile_flops, 8, 0}, {o->sigma_max, Lc * nE * 8, 0}, {o->max_abs_sigma, Lc * 8, 0},
-        {o->profile_entries, 8, 0}, {o->envelope_tiles, 8, 0}};
+        {o->profile_entries, 8, 0}, {o->envelope_tiles, 8, 0}, {o->Rf_sup, Lc * (size_t)h->m.nS * 6 * 8, 0}};
     for (int i = 0; i < N_OUT; ++i) it[i] = t[i];
 }
 void out_advance(const cm_handle *h, cm_solve_out_host *o, int64_t b0) {
@@ -872,9 +889,13 @@ void out_advance(const cm_handle *h, cm_solve_out_host *o, int64_t b0) {
                        (void **)&o->node_exists, (void **)&o->U, (void **)&o->Rf, (void **)&o->eR, (void **)&o->compliance,
                        (void **)&o->max_trans, (void **)&o->max_rot, (void **)&o->min_pivot, (void **)&o->profile_flops,
                        (void **)&o->sigma_max, (void **)&o->max_abs_sigma, (void **)&o->profile_entries,
-                       (void **)&o->envelope_tiles};
+                       (void **)&o->envelope_tiles, (void **)&o->Rf_sup};
     for (int i = 0; i < N_OUT; ++i)
         if (it[i].host) *f[i] = static_cast<char *>(it[i].host) + (size_t)b0 * it[i].stride;
+    if (o->eR_row_offsets) {          // subset b0's rows start (off[b0] - off[0]) rows into eR_rows
+        if (o->eR_rows) o->eR_rows += (size_t)(o->eR_row_offsets[b0] - o->eR_row_offsets[0]) * h->m.n_lc * 12;
+        o->eR_row_offsets += b0;
+    }
 }
 }  // namespace
 
@@ -928,7 +949,30 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
             if (geom_host[b] < 0 || geom_host[b] >= h->m.n_geom)
                 return fail(CM_ERR_INVALID, "cm_solve_many_host: geometry index " + std::to_string(geom_host[b]) + " of subset " +
                                             std::to_string(b) + " not in [0, " + std::to_string(h->m.n_geom) + ")");
+    const int64_t *roff = o->eR_rows ? o->eR_row_offsets : nullptr;
+    if (o->eR_rows) {
+        // the caller sized eR_rows from its offsets: they must be the exclusive prefix sum of the masks' popcounts, or the
+        // kernel would write rows where the caller did not reserve any
+        if (!roff) return fail(CM_ERR_INVALID, "cm_solve_many_host: eR_rows needs eR_row_offsets (i64 [B+1])");
+        const int W = h->m.mask_words;
+        for (int64_t b = 0; b < B; ++b) {
+            int64_t cnt = 0;
+            const uint32_t *mw = masks_host + (size_t)b * W;
+            int w = 0;
+            for (; w + 1 < W; w += 2) cnt += __builtin_popcountll((unsigned long long)mw[w] | ((unsigned long long)mw[w + 1] << 32));
+            if (w < W) cnt += __builtin_popcount(mw[w]);
+            if (roff[b + 1] - roff[b] != cnt)
+                return fail(CM_ERR_INVALID, "cm_solve_many_host: eR_row_offsets[" + std::to_string(b + 1) + "] - [" + std::to_string(b) +
+                                            "] is not the number of elements of subset " + std::to_string(b));
+        }
+    }
     CU(cudaSetDevice(h->device));
+    if (roff && (size_t)B + 1 > h->rowoff_cap) {
+        cudaFree(h->d_rowoff);
+        h->d_rowoff = nullptr; h->rowoff_cap = 0;
+        CU(cudaMalloc((void **)&h->d_rowoff, ((size_t)B + 1) * sizeof(long long)));
+        h->rowoff_cap = (size_t)B + 1;
+    }
     const int32_t *aux_host = geom_host ? geom_host : trows_host;       // one per-subset int array at a time
     if (aux_host && (size_t)B > h->geom_cap) {
         cudaFree(h->d_geom);
@@ -968,10 +1012,11 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     // outputs therefore run in waves of about 64 MB of results (never below what fills the GPU twice).
     size_t out_per_subset = 0;
     for (int i = 0; i < N_OUT; ++i) if (it[i].host) out_per_subset += it[i].stride;
+    if (roff) out_per_subset += (size_t)((roff[B] - roff[0]) / B) * m.n_lc * 96;
     static const long long wave_mb = getenv("CM_HOST_WAVE_MB") ? atoll(getenv("CM_HOST_WAVE_MB")) : 64;
     const long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
     WavePlan P;
-    { int rc = plan_waves(h, B, h->ws_bytes, &P, max_wave); if (rc != CM_OK) return rc; }
+    { int rc = plan_waves(h, B, h->ws_bytes, &P, max_wave, out_per_subset); if (rc != CM_OK) return rc; }
     if (trows_host && group > 1) {
         // waves hold whole groups and run one after the other on the caller-facing stream: the overlap inside a wave
         // (trunk factorisation beside the assembly of the tails) takes the place of the lanes
@@ -990,6 +1035,17 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     size_t slot_bytes = 0;
     for (int i = 0; i < N_OUT; ++i)
         if (it[i].host) { it[i].off = slot_bytes; slot_bytes = al(slot_bytes + (size_t)P.wsize * it[i].stride); }
+    size_t rows_off = 0;                 // the compact element rows of a wave: sized by the wave with the most rows
+    if (roff) {
+        long long max_rows = 0, first = 0;
+        for (long long w = 0; first < B; ++w) {
+            const long long cnt = std::min<long long>(P.sizes.empty() ? P.wsize : P.sizes[(size_t)w], B - first);
+            max_rows = std::max<long long>(max_rows, roff[first + cnt] - roff[first]);
+            first += cnt;
+        }
+        rows_off = slot_bytes;
+        slot_bytes = al(slot_bytes + (size_t)max_rows * m.n_lc * 96);
+    }
     const int n_slots = (int)std::min<long long>(CM_STAGE_SLOTS, P.n_waves);
     const size_t need = mask_bytes + (size_t)n_slots * slot_bytes;
     if (need > h->stage_bytes) {
@@ -1010,6 +1066,7 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     }
     CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
     if (aux_host) CU(cudaMemcpyAsync(h->d_geom, aux_host, Bn * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (roff) CU(cudaMemcpyAsync(h->d_rowoff, roff, (Bn + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     char *slots = h->stage + mask_bytes;
     auto before = [&](long long w, long long first, int, cudaStream_t ls, cm_out_dev &od) -> int {
         const int s = (int)(w % n_slots);
@@ -1023,6 +1080,8 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         od.eR = (double *)bp(8); od.compliance = (double *)bp(9); od.max_trans = (double *)bp(10); od.max_rot = (double *)bp(11);
         od.min_pivot = (double *)bp(12); od.profile_flops = (double *)bp(13); od.sigma_max = (double *)bp(14);
         od.max_abs_sigma = (double *)bp(15); od.profile_entries = (double *)bp(16); od.envelope_tiles = (double *)bp(17);
+        od.Rf_sup = (double *)bp(18);
+        if (roff) { od.eR_rows = (double *)(base + rows_off); od.eR_row_offsets = h->d_rowoff; od.row_bias = roff[first]; }
         return CM_OK;
     };
     // The waves of one lane finish in order, the waves of different lanes do not (wave 1 may be done 3 ms before wave 0):
@@ -1040,6 +1099,9 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
             if (it[i].host)
                 CU(cudaMemcpyAsync(static_cast<char *>(it[i].host) + (size_t)first * it[i].stride, base + it[i].off,
                                    (size_t)count * it[i].stride, cudaMemcpyDeviceToHost, cs));
+        if (roff && roff[first + count] > roff[first])
+            CU(cudaMemcpyAsync(o->eR_rows + (size_t)(roff[first] - roff[0]) * m.n_lc * 12, base + rows_off,
+                               (size_t)(roff[first + count] - roff[first]) * m.n_lc * 96, cudaMemcpyDeviceToHost, cs));
         CU(cudaEventRecord(h->slot_free[s], cs));
         if (trace) CU(cudaEventRecord(tev[3 + 3 * (size_t)w], cs));
         return CM_OK;

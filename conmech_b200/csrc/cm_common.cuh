@@ -141,6 +141,10 @@ struct cm_out_dev {
     unsigned char *node_exists;
     double *U, *Rf, *eR, *compliance, *max_trans, *max_rot, *min_pivot, *profile_flops, *sigma_max, *max_abs_sigma;
     double *profile_entries, *envelope_tiles;
+    // compact results (include/conmech_b200.h): reactions of the support nodes, end forces of the existing elements
+    double *Rf_sup, *eR_rows;
+    const long long *eR_row_offsets;      // [B+1], indexed like the masks
+    long long row_bias;                   // rows of subset gs start at eR_rows + (off[gs] - row_bias) * n_lc * 12
 };
 
 // kernel launchers (one per stage); all enqueue on `st` and return the launch error
@@ -174,6 +178,7 @@ cudaError_t cm_launch_factor(const cm_model_dev &m, const cm_ws_layout &L, char 
 cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int rank0, int count, int stride,
                                   int config, int prof, cudaStream_t st);
 cudaError_t cm_factor_flow_read_prof(unsigned long long *out16);
+cudaError_t cm_k2_read_prof(unsigned long long *out8);
 cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L, char *ws,
                                     const uint32_t *masks, const int *geom, long long first, int count,
                                     const cm_out_dev &out, cudaStream_t st);

@@ -15,6 +15,24 @@ namespace {
 
 constexpr int K2_THREADS = 256;
 
+// instrumented build (-DK2_PROF=1, tools/build_variant.py): cycles of thread 0 between the block barriers that separate the
+// phases, summed over CTAs (slots: 0 table / mask staging, 1 node existence, 2 numbering + envelope, 3 diagonal gather,
+// 4 Jacobi scale, 5 fill + scatter, 6 load vectors, 7 total)
+__device__ unsigned long long g_k2_prof[16];     // 8..: inside fill + scatter, per warp (lane 0): 8 zero fill incl. wait, 9 row lookup, 10 diagonal step, 11 pair steps, 12 idle at the closing barrier
+#if defined(K2_PROF) && K2_PROF
+#define K2P_T0() long long _k2t = clock64(); const long long _k2start = _k2t
+#define K2P(slot) do { if (threadIdx.x == 0) { const long long _n = clock64(); atomicAdd(&g_k2_prof[slot], (unsigned long long)(_n - _k2t)); _k2t = _n; } } while (0)
+#define K2P_END() do { if (threadIdx.x == 0) atomicAdd(&g_k2_prof[7], (unsigned long long)(clock64() - _k2start)); } while (0)
+#define K2W_T0() long long _k2w = clock64()
+#define K2W(slot) do { const long long _n = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_k2_prof[slot], (unsigned long long)(_n - _k2w)); _k2w = _n; } while (0)
+#else
+#define K2W_T0()
+#define K2W(slot)
+#define K2P_T0()
+#define K2P(slot)
+#define K2P_END()
+#endif
+
 
 // exclusive scan of n ints in shared memory, in place; returns the total (all threads).
 // scratch: K2_THREADS+1 ints.
@@ -96,6 +114,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     __shared__ double s_dred[K2_THREADS / 32];
 
     const int t = threadIdx.x, T = blockDim.x;
+    K2P_T0();
     // part 1: CTA b assembles the first subset of group b (the trunks); part 2: every subset but those
     const int sb = part == 1 ? blockIdx.x * group : blockIdx.x;
     if (part == 2 && sb % group == 0) return;
@@ -141,6 +160,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     if (t < 8) s_red[t] = 0;
     if (t == 0) { s_work = 0ull; s_ent = 0ull; s_ntile = 0; }
     __syncthreads();
+    K2P(0);
 
     // ---- node existence, support status (numpy_stiffness.py:156-184)
     int my_fixed = 0, my_exist = 0, my_sup = 0;
@@ -162,6 +182,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     atomicAdd(&s_red[1], my_exist);
     atomicOr(&s_red[2], my_sup);
     __syncthreads();
+    K2P(1);
     const int n_fixed = s_red[0], n_exist = s_red[1];
     const int status = (s_red[2] == 0) ? CM_ST_NO_SUPPORT : (n_fixed == 0 ? CM_ST_NO_FIXED_DOF : CM_ST_OK);
     const int n_free = 6 * n_exist - n_fixed;
@@ -283,6 +304,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             atomicAdd(&s_ent, (unsigned long long)nf * (unsigned long long)(base - cmin + 1) + (unsigned long long)(nf * (nf - 1) / 2));
     }
     __syncthreads();
+    K2P(2);
     if (t == 0 && out.profile_flops) out.profile_flops[gs] = (double)s_work;
     // cost key of the schedule: > 0, monotone in the work.  (For a tail the shared rows still count: an upper bound.)
     if (t == 0) info[CM_INFO_COST] = __float_as_int((float)s_work + 1.0f);
@@ -319,6 +341,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     }
     if (!ok) atomicOr(&s_red[3], 1);
     __syncthreads();
+    K2P(3);
     const int jacobi = s_red[3] ? 0 : 1;
     for (int r = t; r < NT * CM_TILE; r += T) {
         double d = 1.0;
@@ -328,6 +351,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     }
     if (t == 0) info[CM_INFO_JACOBI] = jacobi;
     __syncthreads();
+    K2P(4);
 
     // ---- gather assembly.  Per node: the 6x6 diagonal block (lower triangle) and one 6x6 block per
     // lower pair (a,c) - 36 entries each, all entries of the node spread over the lanes of a warp.
@@ -344,6 +368,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
     {
         const int bt = m.band_tiles;
         const int lane = t & 31;
+        K2W_T0();
         // tile rows are handed out dynamically (shared counter): rows differ in work (nodes, neighbours, tiles to fill),
         // with a static round robin a quarter of the warps sat at the barrier below for 5 % of the kernel
 #if defined(K2_STATIC_ROWS) && K2_STATIC_ROWS
@@ -380,6 +405,7 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
             }
 #endif
             __syncwarp();
+            K2W(8);
             // first position whose node ends beyond the first row of the tile row (binary search on the scan)
             const int row0 = IR * CM_TILE, row1 = min(row0 + CM_TILE, ns);
             int lo = 0, hi = nV;
@@ -390,6 +416,119 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
 #if defined(K2_EXP) && K2_EXP == 2          // timing experiment (wrong results): no gather/scatter
             lo = nV;
 #endif
+#if !defined(K2_NODE_CENTRIC) || !K2_NODE_CENTRIC
+            // One lane per matrix ROW of the tile row.  Step s = -1 is the row's part of its node's 6x6 diagonal block (lower
+            // triangle), steps s = 0, 1, .. its 6x6 blocks towards the node's lower pairs: in every step all lanes run the
+            // same path, whereas one lane per (node, block, row) - one node at a time - left 6 of 32 lanes on the long
+            // diagonal path (14.7 active lanes per instruction over the kernel, profiles/r02_experiments.txt).  The 6
+            // entries of row i of a block are 48 contiguous bytes of the element's K_G (three 16-byte loads per element);
+            // an entry sums its elements in ascending element id as before.
+            const int r = row0 + lane;
+            int a = -1, i = 0, base_a = 0;
+            for (int pa = lo; pa < nV && s_tmp[pa] < row1; ++pa) {            // (uniform: at most 7 nodes touch a tile row)
+                const int v = order[pa], nf = s_free[v], b = s_tmp[pa];
+                if (r >= b && r < b + nf) {
+                    a = v; base_a = b; i = r - b;
+                    const int sv = node_sup[v];
+                    if (sv >= 0) {                                             // support node with free DOFs: i-th free one
+                        const unsigned char *cnd = sup_cond + 6 * sv;
+                        int k = i; i = 0;
+                        while (cnd[i] || k > 0) { k -= cnd[i] ? 0 : 1; ++i; }
+                    }
+                }
+            }
+            __syncwarp();
+            K2W(9);
+            if (a >= 0) {
+                const int p0 = ne_ptr[a], p1 = ne_ptr[a + 1];
+                const int q0 = lp_ptr[a], npairs = lp_ptr[a + 1] - q0;
+                const double *dv = DS ? s_dinv : dinv;
+                const double dr = dv[r];
+                const int I = IR;
+                auto tile_of = [&](int K) { return tiles + ((size_t)I * bt + (K - I + bt - 1)) * CM_TILE_ELEMS; };
+                for (int s = -1; s < npairs; ++s) {
+                    double s6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    int c = a, base_c = base_a;
+                    if (s < 0) {
+#pragma unroll 2
+                        for (int p = p0; p < p1; ++p) {
+                            const int e = ne_elem[p];
+                            const int o = 6 * ne_end[p];
+                            const double2 *kp = reinterpret_cast<const double2 *>(Kg + (size_t)e * 144 + (o + i) * 12 + o);
+                            const double2 v0 = kp[0], v1 = kp[1], v2 = kp[2];
+                            if (elem_on(s_mask, e)) {
+                                s6[0] += v0.x; s6[1] += v0.y; s6[2] += v1.x;
+                                s6[3] += v1.y; s6[4] += v2.x; s6[5] += v2.y;
+                            }
+                        }
+                    } else {
+                        const int q = q0 + s;
+                        c = lp_node[q];
+                        if (s_free[c] == 0) continue;
+                        base_c = s_base[c];
+                        bool any = false;
+                        const int pe1 = lp_eptr[q + 1];
+                        for (int pe = lp_eptr[q]; pe < pe1; ++pe) {
+                            const int e = lp_elem[pe];
+                            const int ea = lp_end[pe];
+                            const double2 *kp = reinterpret_cast<const double2 *>(Kg + (size_t)e * 144 + (6 * ea + i) * 12 + 6 * (1 - ea));
+                            const double2 v0 = kp[0], v1 = kp[1], v2 = kp[2];
+                            if (elem_on(s_mask, e)) {
+                                s6[0] += v0.x; s6[1] += v0.y; s6[2] += v1.x;
+                                s6[3] += v1.y; s6[4] += v2.x; s6[5] += v2.y;
+                                any = true;
+                            }
+                        }
+                        if (!any) continue;          // no existing element joins the pair: the tile may be unassembled
+                    }
+                    // scale and store; columns = free DOFs of node c in order (diagonal block: lower triangle only).
+                    // Every index into the value array is a compile-time constant (a run-time index puts the array
+                    // into local memory: that was 1.3 GB of L1-missing local loads per 4096 subsets).
+                    const int sc = node_sup[c];
+                    const int jmax = s < 0 ? i : 5;
+                    if (sc < 0) {
+                        // node c is not a support: its six DOFs are the columns base_c .. base_c + 5
+                        double v[6];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) v[j] = (dr * s6[j]) * dv[base_c + j];
+                        const int K0 = base_c >> 5;
+                        if (ktilde_rm && K0 == ((base_c + jmax) >> 5)) {
+                            // row-major K~ tile: the row's entries are contiguous - 16-byte stores where aligned
+                            double *dst = tile_of(K0) + (r & 31) * 32 + (base_c & 31);
+                            if (base_c & 1) {
+                                dst[0] = v[0];
+                                if (jmax >= 2) *reinterpret_cast<double2 *>(dst + 1) = make_double2(v[1], v[2]); else if (jmax == 1) dst[1] = v[1];
+                                if (jmax >= 4) *reinterpret_cast<double2 *>(dst + 3) = make_double2(v[3], v[4]); else if (jmax == 3) dst[3] = v[3];
+                                if (jmax == 5) dst[5] = v[5];
+                            } else {
+                                if (jmax >= 1) *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]); else dst[0] = v[0];
+                                if (jmax >= 3) *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]); else if (jmax == 2) dst[2] = v[2];
+                                if (jmax == 5) *reinterpret_cast<double2 *>(dst + 4) = make_double2(v[4], v[5]); else if (jmax == 4) dst[4] = v[4];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+                                if (j <= jmax) {
+                                    const int cc = base_c + j;
+                                    tile_of(cc >> 5)[ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31)] = v[j];
+                                }
+                        }
+                    } else {
+                        // support node with some free DOFs: compact the columns (rare; entry by entry)
+                        int cc = base_c;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            if (sup_cond[6 * sc + j]) continue;        // fixed DOF: no solver column
+                            if (j <= jmax) tile_of(cc >> 5)[ktilde_rm ? (r & 31) * 32 + (cc & 31) : cm_tile_off(r & 31, cc & 31)] = (dr * s6[j]) * dv[cc];
+                            ++cc;
+                        }
+                    }
+                    if (s < 0) K2W(10);
+                }
+            }
+            __syncwarp();
+            K2W(11);
+#else
             for (int pa = lo; pa < nV && s_tmp[pa] < row1; ++pa) {
             const int a = order[pa];
             if (s_free[a] == 0) continue;
@@ -498,8 +637,11 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
                 }
             }
             }
+#endif
         }
+        K2W(12);
         __syncthreads();
+        K2P(5);
         // unit diagonal on the padding rows of the last tile
         for (int r = ns + t; r < NT * CM_TILE; r += T) {
             int I = r >> 5;
@@ -545,6 +687,8 @@ k2_dofmap_assemble(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *mas
         __syncthreads();
     }
     if (t == 0) info[CM_INFO_ZERO_LOAD] = zero_bits;
+    K2P(6);
+    K2P_END();
 }
 
 }  // namespace
@@ -583,6 +727,14 @@ __global__ void __launch_bounds__(256) k2_schedule(cm_ws_layout L, char *ws, int
     if (i < count) info_of(rank)[CM_INFO_SCHED] = i;
 }
 }  // namespace
+
+// read (and clear) the phase counters of the instrumented build (zeros otherwise)
+cudaError_t cm_k2_read_prof(unsigned long long *out8) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8, g_k2_prof, 16 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(g_k2_prof, z, sizeof(z));
+}
 
 cudaError_t cm_launch_schedule(const cm_ws_layout &L, char *ws, int count, cudaStream_t st) {
     k2_schedule<<<(count + 255) / 256, 256, 0, st>>>(L, ws, count);

@@ -108,7 +108,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                  cm_out_dev out) {
     static_assert(XS || NB == 1, "several right-hand sides per pass need the shared-memory vectors");
     __shared__ double s_red[K4_WARPS];
-    extern __shared__ __align__(16) double s_x[];            // XS: [NB][n_pad] solutions, then [n_pad] pivots
+    extern __shared__ __align__(16) double s_x[];            // XS: [NB][n_pad] solutions, then [n_pad] pivots; then [mask_words] ints
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long gs = first + blockIdx.x;
@@ -142,6 +142,18 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
 
     if (out.min_pivot && t == 0)
         out.min_pivot[gs] = (status == CM_ST_OK || status == CM_ST_SINGULAR) ? dpiv[n_pad] : nan("");
+    // compact element rows: rank of an existing element among the subset's elements = popcount of the mask bits below it
+    int *s_wpre = reinterpret_cast<int *>(s_x + (XS ? (size_t)(NB + 1) * n_pad : 0));      // [mask_words] exclusive prefix of the word popcounts
+    long long crow0 = 0, ccnt = 0;
+    if (out.eR_rows) {
+        crow0 = out.eR_row_offsets[gs] - out.row_bias;
+        ccnt = out.eR_row_offsets[gs + 1] - out.eR_row_offsets[gs];
+        if (t == 0) {
+            int run = 0;
+            for (int w = 0; w < m.mask_words; ++w) { s_wpre[w] = run; run += __popc(mask[w]); }
+        }
+        __syncthreads();
+    }
 
     for (int lc0 = 0; lc0 < n_lc; lc0 += NB) {
       // ---- back substitution of the load cases lc0 .. lc0+NB-1 in one pass over L (status OK only;
@@ -234,6 +246,8 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
         double *Uo = out.U ? out.U + ol * 6 * nV : nullptr;
         double *Ro = out.Rf ? out.Rf + ol * 6 * nV : nullptr;
         double *Eo = out.eR ? out.eR + ol * (size_t)nE * 12 : nullptr;
+        double *Rs = out.Rf_sup ? out.Rf_sup + ol * (size_t)m.nS * 6 : nullptr;
+        double *Ec = out.eR_rows ? out.eR_rows + ((size_t)crow0 * n_lc + (size_t)lc * ccnt) * 12 : nullptr;
         const bool zero_load = (zero_bits >> lc) & 1;
         // a zero load vector skips the factorisation in the reference (numpy_stiffness.py:267), so a
         // singular matrix does not fail that load case
@@ -242,6 +256,8 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
             if (Uo) for (int i = t; i < 6 * nV; i += K4_THREADS) Uo[i] = 0.0;
             if (Ro) for (int i = t; i < 6 * nV; i += K4_THREADS) Ro[i] = 0.0;
             if (Eo) for (int i = t; i < 12 * nE; i += K4_THREADS) Eo[i] = 0.0;
+            if (Rs) for (int i = t; i < 6 * m.nS; i += K4_THREADS) Rs[i] = 0.0;
+            if (Ec) for (long long i = t; i < 12 * ccnt; i += K4_THREADS) Ec[i] = 0.0;
             if (out.sigma_max) for (int i = t; i < nE; i += K4_THREADS) out.sigma_max[ol * (size_t)nE + i] = 0.0;
             if (t == 0) {
                 if (out.max_abs_sigma) out.max_abs_sigma[ol] = nan("");
@@ -291,13 +307,15 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
         mr = block_nanmax(mr, s_red);
 
         // ---- fixity reactions at the fixed DOFs of existing support nodes
-        if (Ro) {
-            for (int d = t; d < 6 * nV; d += K4_THREADS) Ro[d] = 0.0;
-            __syncthreads();
+        if (Ro || Rs) {
+            if (Ro) {
+                for (int d = t; d < 6 * nV; d += K4_THREADS) Ro[d] = 0.0;
+                __syncthreads();
+            }
             for (int idx = t; idx < 6 * m.nS; idx += K4_THREADS) {
                 int s = idx / 6, i = idx - 6 * s;
                 int v = m.sup_node[s];
-                if (!m.sup_cond[6 * s + i]) continue;
+                if (!m.sup_cond[6 * s + i]) { if (Rs) Rs[idx] = 0.0; continue; }
                 bool ex = false;
                 double acc = 0.0;
                 for (int p = m.ne_ptr[v]; p < m.ne_ptr[v + 1]; ++p) {
@@ -311,7 +329,9 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
 #pragma unroll
                     for (int j = 0; j < 6; ++j) acc += krow[6 + j] * u_at(6 * n1 + j);
                 }
-                if (ex) Ro[6 * v + i] = acc - (zero_load ? 0.0 : Pl[6 * v + i]);   // P_f stays 0 when the solve is skipped (:260-270)
+                const double rv = ex ? acc - (zero_load ? 0.0 : Pl[6 * v + i]) : 0.0;   // P_f stays 0 when the solve is skipped (:260-270)
+                if (ex && Ro) Ro[6 * v + i] = rv;
+                if (Rs) Rs[idx] = rv;
             }
         }
 
@@ -321,7 +341,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
         // r = sqrt(A/pi), W = Iy/r for BOTH axes, My/Mz = larger end moment in magnitude
         double *So = out.sigma_max ? out.sigma_max + ol * (size_t)nE : nullptr;
         double smax = -1.0;
-        if (Eo || So || out.max_abs_sigma) {
+        if (Eo || Ec || So || out.max_abs_sigma) {
             for (int i0 = 0; i0 < 4 * nE; i0 += K4_THREADS) {       // uniform trip count: shuffles below
                 const int idx = i0 + t;
                 const bool valid = idx < 4 * nE;
@@ -349,6 +369,11 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
                 }
                 if (Eo && valid) {
                     double *dst = Eo + (size_t)e * 12 + 3 * pblk;
+                    dst[0] = d3[0]; dst[1] = d3[1]; dst[2] = d3[2];
+                }
+                if (Ec && on) {
+                    const int rank = s_wpre[e >> 5] + __popc(mask[e >> 5] & ((1u << (e & 31)) - 1u));
+                    double *dst = Ec + (size_t)rank * 12 + 3 * pblk;
                     dst[0] = d3[0]; dst[1] = d3[1]; dst[2] = d3[2];
                 }
                 if (So || out.max_abs_sigma) {
@@ -393,7 +418,7 @@ k4_solve_recover(cm_model_dev m, cm_ws_layout L, char *ws, const uint32_t *masks
 template <int NB>
 static cudaError_t launch_k4_xs(const cm_model_dev &m, const cm_ws_layout &L, char *ws, const uint32_t *masks, const int *geom,
                                 long long first, int count, const cm_out_dev &out, cudaStream_t st) {
-    const size_t xs_bytes = (size_t)(NB + 1) * L.n_pad * sizeof(double);      // NB solutions and the pivots
+    const size_t xs_bytes = (size_t)(NB + 1) * L.n_pad * sizeof(double) + (size_t)m.mask_words * sizeof(int);      // NB solutions and the pivots; word prefix of the mask
     static cm_smem_cache cache;
     cudaError_t e = cm_ensure_smem(k4_solve_recover<true, NB>, xs_bytes, cache, m.device);
     if (e != cudaSuccess) return e;
@@ -418,6 +443,6 @@ cudaError_t cm_launch_solve_recover(const cm_model_dev &m, const cm_ws_layout &L
     if (nb == 4) return launch_k4_xs<4>(m, L, ws, masks, geom, first, count, out, st);
     if (nb == 2) return launch_k4_xs<2>(m, L, ws, masks, geom, first, count, out, st);
     if (nb == 1) return launch_k4_xs<1>(m, L, ws, masks, geom, first, count, out, st);
-    k4_solve_recover<false, 1><<<count, K4_THREADS, 0, st>>>(m, L, ws, masks, geom, first, out);
+    k4_solve_recover<false, 1><<<count, K4_THREADS, (size_t)m.mask_words * sizeof(int), st>>>(m, L, ws, masks, geom, first, out);
     return cudaGetLastError();
 }

@@ -30,6 +30,7 @@ DEFAULT_GRAVITY_DIRECTION = np.array([0., 0., -1.])
 _OUT_DTYPE = {'flag': np.uint8, 'status': np.uint8, 'n_free': np.int32, 'n_fixed': np.int32,
               'dof_map': np.int32, 'node_exists': np.uint8, 'U': np.float64, 'Rf': np.float64,
               'eR': np.float64, 'compliance': np.float64, 'max_trans': np.float64,
+              'Rf_sup': np.float64, 'eR_rows': np.float64, 'eR_row_offsets': np.int64,
               'max_rot': np.float64, 'min_pivot': np.float64, 'profile_flops': np.float64,
               'sigma_max': np.float64, 'max_abs_sigma': np.float64, 'profile_entries': np.float64,
               'envelope_tiles': np.float64}
@@ -109,6 +110,10 @@ class CudaStiffness(StiffnessBase):
     @property
     def nV(self):
         return len(self._nodes)
+
+    @property
+    def nS(self):
+        return len(self._sup_node)
 
     @property
     def nE(self):
@@ -326,7 +331,15 @@ class CudaStiffness(StiffnessBase):
                 'node_exists': (B, nV), 'U': (B, L, 6 * nV), 'Rf': (B, L, 6 * nV), 'eR': (B, L, nE, 12),
                 'compliance': (B, L), 'max_trans': (B, L), 'max_rot': (B, L), 'min_pivot': (B,),
                 'profile_flops': (B,), 'sigma_max': (B, L, nE), 'max_abs_sigma': (B, L),
-                'profile_entries': (B,), 'envelope_tiles': (B,)}
+                'profile_entries': (B,), 'envelope_tiles': (B,), 'Rf_sup': (B, L, self.nS, 6)}
+
+    @staticmethod
+    def element_row_offsets(masks):
+        """Exclusive prefix sum of the subsets' element counts, int64 [B+1]: where each subset's rows start in the
+        compact ``eR_rows`` output (``cm_solve_out.eR_row_offsets``)."""
+        off = np.zeros(len(masks) + 1, dtype=np.int64)
+        np.cumsum(np.bitwise_count(masks).sum(axis=1, dtype=np.int64), out=off[1:])
+        return off
 
     def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None, geometry=None):
         """Solve B element subsets (list of id lists, [] = full structure, or a (B, words)
@@ -334,7 +347,13 @@ class CudaStiffness(StiffnessBase):
         the requested outputs are copied back.  Returns {name: ndarray}; see ``cm_solve_out``
         in include/conmech_b200.h for names and shapes.  ``out`` may hold preallocated
         (e.g. pinned) arrays to write into.  ``geometry``: one geometry-variant index per subset
-        (``set_geometries``), default variant 0."""
+        (``set_geometries``), default variant 0.
+
+        Compact results (what the reference's ``get_solved_results`` returns, without zero padding): ``'Rf_sup'`` =
+        reactions of the support nodes ``(B, L, nS, 6)`` in the order of the model's supports; ``'eR_rows'`` = end
+        forces of the EXISTING elements only, ``(rows * L, 12)``: subset b owns ``rows[off[b] * L:off[b + 1] * L]``
+        viewed as ``(L, off[b + 1] - off[b], 12)``, elements in ascending id; ``off`` is returned as
+        ``'eR_row_offsets'``."""
         self._push_loads()
         masks0 = as_mask_matrix(subsets, self._info.mask_words)
         prepacked = masks0 is not None
@@ -343,8 +362,14 @@ class CudaStiffness(StiffnessBase):
         B = len(masks0) if prepacked else len(subsets)
         shapes = self._out_shapes(B)
         res = {}
+        if 'eR_rows' in want:                  # the row offsets come from the masks: pack them all first
+            if not prepacked:
+                masks0, prepacked = pack_masks(subsets, self.nE), True
+            off = self.element_row_offsets(masks0)
+            shapes['eR_rows'] = (int(off[-1]) * self._n_lc, 12)
+            res['eR_row_offsets'] = off
         for name in OUT_FIELDS:
-            if name in want:
+            if name in want and name != 'eR_row_offsets':
                 a = out[name] if out is not None and name in out else np.empty(shapes[name], dtype=_OUT_DTYPE[name])
                 assert a.flags['C_CONTIGUOUS'] and a.dtype == _OUT_DTYPE[name] and a.size == int(np.prod(shapes[name]))
                 res[name] = a.reshape(shapes[name])
@@ -352,7 +377,13 @@ class CudaStiffness(StiffnessBase):
         def out_struct(b0=0):
             oh = _capi.SolveOutHost()
             for name in OUT_FIELDS:
-                setattr(oh, name, res[name][b0:].ctypes.data if name in res and b0 < B else None)
+                if name in ('eR_rows', 'eR_row_offsets'):
+                    assert b0 == 0 or name not in res
+                    setattr(oh, name, res[name].ctypes.data if name in res and res[name].size else None)
+                else:
+                    setattr(oh, name, res[name][b0:].ctypes.data if name in res and b0 < B else None)
+            if 'eR_rows' in res and not res['eR_rows'].size:
+                oh.eR_row_offsets = None
             return oh
 
         if B == 0:
@@ -521,11 +552,28 @@ class CudaStiffness(StiffnessBase):
         dev = masks.device
         B = masks.shape[0]
         shapes = self._out_shapes(B)
-        tdt = {np.uint8: torch.uint8, np.int32: torch.int32, np.float64: torch.float64}
+        tdt = {np.uint8: torch.uint8, np.int32: torch.int32, np.float64: torch.float64, np.int64: torch.int64}
         res = {}
         od = _capi.SolveOut()
+        if 'eR_rows' in want:
+            # compact element rows: offsets = exclusive prefix sum of the masks' popcounts (a caller that already has
+            # them passes out['eR_row_offsets'], int64 [B+1] on the device, first entry 0)
+            off = out.get('eR_row_offsets') if out is not None else None
+            if off is None:
+                x = masks.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+                x = x - ((x >> 1) & 0x55555555)
+                x = (x & 0x33333333) + ((x >> 2) & 0x33333333)
+                x = (((x + (x >> 4)) & 0x0F0F0F0F) * 0x01010101 >> 24) & 0xFF
+                off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(x.sum(dim=1), 0, out=off[1:])
+            assert off.is_cuda and off.dtype == torch.int64 and off.numel() == B + 1 and off.is_contiguous()
+            res['eR_row_offsets'] = off
+            n_rows = int(out['eR_rows'].numel() // (12 * self._n_lc)) if out is not None and 'eR_rows' in out else int(off[-1].item())
+            shapes['eR_rows'] = (n_rows * self._n_lc, 12)
         for name in OUT_FIELDS:
-            if name in want:
+            if name == 'eR_row_offsets':
+                setattr(od, name, res[name].data_ptr() if name in res else 0)
+            elif name in want:
                 tns = out[name] if out is not None and name in out else \
                     torch.empty(shapes[name], dtype=tdt[_OUT_DTYPE[name]], device=dev)
                 assert tns.is_contiguous()

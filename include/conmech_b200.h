@@ -165,6 +165,18 @@ typedef struct cm_solve_out {
     uint64_t profile_entries; /* f64 [B]    sum_j (h_j + 1): entries of the scalar profile (lower, with diagonal)  */
                           /*                of the subset's K_mm; 8x this = S_K of SURVEY.md section 8d (profile)  */
     uint64_t envelope_tiles; /* f64 [B]     32x32 tiles of the block-band envelope that is factorised (8 KB each)  */
+    /* Compact results - what the reference returns, without the zero padding of the dense arrays above:
+     * get_solved_results() gives fR rows for the support nodes and eR rows for the existing elements only
+     * (numpy_stiffness.py:375-391).  On the 1k-element frame a dense result is 127 KB per solve, the compact
+     * one (U dense + these two) about 70 KB: the host entry point is bound by the device->host link. */
+    uint64_t Rf_sup;      /* f64 [B*L*nS*6] fixity reactions of the support nodes in the order of cm_model_desc.sup_node */
+                          /*                (the reference's fR rows); 0 at free DOFs and for absent support nodes      */
+    uint64_t eR_rows;     /* f64 [rows*L*12] element end forces of the EXISTING elements only: subset b owns rows      */
+                          /*                off[b] .. off[b+1] (ascending element id), stored [L][off[b+1]-off[b]][12]  */
+                          /*                at eR_rows + (off[b] - off[0])*L*12                                          */
+    uint64_t eR_row_offsets; /* INPUT, i64 [B+1]: off[b] = number of existing elements of the subsets before b         */
+                          /*                (exclusive prefix sum of the popcounts of the masks); required with        */
+                          /*                eR_rows; the device entry points want off[0] == 0                           */
 } cm_solve_out;
 
 /* Factorisation kernel variant: 1 (default) = FP64 tensor-core block-band LDL^T, dataflow
@@ -183,6 +195,7 @@ int cm_set_variant(cm_handle *h, int32_t variant);
 /* Development aid: after a solve with variant 4 or 5, reads and clears the 16 activity counters
  * (clock64 cycles summed over all row warps; slot meanings in csrc/k3_factor_flow.cu). */
 int cm_debug_k3_phase_cycles(cm_handle *h, uint64_t *out16);
+int cm_debug_k2_phase_cycles(cm_handle *h, uint64_t *out16);  /* -DK2_PROF=1 builds of the assembly kernel: cycles per phase */
 
 /* Bytes of workspace needed to run `subsets_in_flight` subsets at once. cm_solve_many splits
  * B into waves that fit the workspace it is given. */
@@ -225,6 +238,9 @@ typedef struct cm_solve_out_host {
     double *max_abs_sigma;
     double *profile_entries;
     double *envelope_tiles;
+    double *Rf_sup;                 /* compact results, see cm_solve_out */
+    double *eR_rows;
+    const int64_t *eR_row_offsets;  /* INPUT, host i64 [B+1] */
 } cm_solve_out_host;
 
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,

@@ -294,6 +294,63 @@ def test_config3_grid_batch():
         assert_array_equal(r[k], r2[k])
 
 
+def test_compact_results_match_dense():
+    """Compact results (reactions of the support nodes, end forces of the existing elements only - the rows the
+    reference's get_solved_results returns, numpy_stiffness.py:375-391) are bit for bit the dense arrays without their
+    zero padding: host path over several waves, device path, several load cases, failing subsets, wrong offsets."""
+    import torch
+    from conmech_b200 import synthetic as syn, LoadCase, GravityLoad, PointLoad, _capi
+    for model, lcs, B in ((syn.grid_frame(7, 7, 8), [LoadCase(gravity_load=GravityLoad([0, 0, -1]))], 3000),
+                          (syn.grid_frame(4, 3, 4), [LoadCase(gravity_load=GravityLoad([0, 0, -1])),
+                                                     LoadCase(point_loads=[PointLoad([1, 0, 0], [0, 0, 0], 40)]),
+                                                     LoadCase(gravity_load=GravityLoad([0, 0, -1]), point_loads=[PointLoad([0, 2, 0], [0, 1, 0], 30)])], 200)):
+        from conmech_b200 import StiffnessChecker
+        sc = StiffnessChecker(model, checker_engine='cuda')
+        eng = sc._sc_ins
+        if len(lcs) == 1:
+            sc.set_loads(lcs[0])
+        else:
+            sc.set_load_cases(lcs)
+        nE, L = len(model.elements), len(lcs)
+        rng = random.Random(5)
+        subsets = [syn.connected_subset(model, s) for s in range(B - 3)]
+        floating = [e for e in range(nE) if not (set(model.elements[e].end_node_inds) & set(model.supports.keys()))]
+        subsets += [[], floating[:3], sorted(rng.sample(range(nE), nE // 2))]      # full structure, no support, arbitrary
+        masks = syn.pack_masks(subsets, nE)
+        dense = eng.solve_many(masks, want=('flag', 'status', 'U', 'Rf', 'eR'))
+        comp = eng.solve_many(masks, want=('flag', 'status', 'U', 'Rf_sup', 'eR_rows'))
+        off = comp['eR_row_offsets']
+        assert_array_equal(off, eng.element_row_offsets(masks))
+        assert comp['eR_rows'].shape == (off[-1] * L, 12)
+        assert_array_equal(comp['flag'], dense['flag'])
+        assert_array_equal(comp['U'], dense['U'])
+        assert (dense['status'] != ST_OK).any() and (dense['status'] == ST_OK).any()
+        sup = np.array(list(model.supports.keys()))
+        assert_array_equal(comp['Rf_sup'], dense['Rf'].reshape(B, L, -1, 6)[:, :, sup])
+        for b in range(B):
+            ids = sorted(subsets[b]) or list(range(nE))
+            rows = comp['eR_rows'][off[b] * L:off[b + 1] * L].reshape(L, len(ids), 12)
+            assert_array_equal(rows, dense['eR'][b][:, ids], err_msg=str(b))
+        # the device entry point delivers the same rows
+        dm = torch.from_numpy(masks.view(np.int32)).cuda()
+        rd = eng.solve_many_device(dm, want=('flag', 'Rf_sup', 'eR_rows'))
+        torch.cuda.synchronize()
+        assert_array_equal(rd['eR_row_offsets'].cpu().numpy(), off)
+        assert_array_equal(rd['eR_rows'].cpu().numpy(), comp['eR_rows'])
+        assert_array_equal(rd['Rf_sup'].cpu().numpy(), comp['Rf_sup'])
+        # offsets that do not match the masks are refused before anything is written
+        bad = off.copy()
+        bad[B // 2] += 1
+        oh = _capi.SolveOutHost()
+        rows = np.zeros_like(comp['eR_rows'])
+        oh.eR_rows, oh.eR_row_offsets = rows.ctypes.data, bad.ctypes.data
+        import ctypes as C
+        assert eng._lib.cm_solve_many_host(eng._handle, masks.ctypes.data, B, C.byref(oh)) != _capi.CM_OK
+        assert b'eR_row_offsets' in eng._lib.cm_last_error()
+        oh.eR_row_offsets = None
+        assert eng._lib.cm_solve_many_host(eng._handle, masks.ctypes.data, B, C.byref(oh)) != _capi.CM_OK
+
+
 def test_config3_full_size_properties():
     """Full-size batch (4096 subsets of the 1k frame): properties that need no oracle -
     vertical reactions balance the self weight of the existing elements, displacement at fixed

@@ -26,7 +26,7 @@ def test_capi_loads_and_exports_header_symbols():
     assert b'sm_100a' in lib.cm_version()
     # struct layouts the header promises
     import ctypes as C
-    assert C.sizeof(_capi.SolveOut) == 18 * 8 and C.sizeof(_capi.SolveOutHost) == 18 * 8
+    assert C.sizeof(_capi.SolveOut) == 21 * 8 and C.sizeof(_capi.SolveOutHost) == 21 * 8
     assert C.sizeof(_capi.ModelDesc) == 16 + 7 * 8
 
 

@@ -47,3 +47,14 @@ if variant in (4, 5):
     tot = float(out[9])
     for n, v in zip(names, out[:len(names)]):
         print('  {:18s} {:14d} cycles  {:6.2f}%'.format(n, int(v), 100.0 * float(v) / tot))
+if os.environ.get('CM_K2_PROF'):
+    import ctypes as C
+    out = np.zeros(16, dtype=np.uint64)
+    eng._lib.cm_debug_k2_phase_cycles(eng._handle, out.ctypes.data_as(C.c_void_p))
+    names = ['stage tables/mask', 'node existence', 'numbering+envelope', 'diagonal gather', 'jacobi scale', 'fill+scatter', 'load vectors', 'total',
+             'w: zero fill + wait', 'w: row lookup', 'w: diagonal step', 'w: pair steps', 'w: closing barrier']
+    tot = float(out[7]) or 1.0
+    for n, v in zip(names, out):
+        if n.startswith('w:'):
+            tot = float(out[8:13].sum()) or 1.0
+        print('  K2 {:20s} {:14d} cycles  {:6.2f}%'.format(n, int(v), 100.0 * float(v) / tot))
