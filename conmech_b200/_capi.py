@@ -49,7 +49,7 @@ SYMBOLS = ('cm_pack_elements', 'cm_create', 'cm_destroy', 'cm_get_info', 'cm_get
            'cm_set_loadcases', 'cm_get_element_loads', 'cm_set_tol', 'cm_set_variant', 'cm_debug_k3_phase_cycles', 'cm_debug_k2_phase_cycles',
            'cm_workspace_bytes', 'cm_solve_many', 'cm_solve_many_host', 'cm_solve_many_host_chunks', 'cm_solve_many_host_multi', 'cm_kernel_launches',
            'cm_reset_counters', 'cm_enable_timing', 'cm_last_stage_ms', 'cm_last_wave_count', 'cm_element_kernel_dev',
-           'cm_last_error', 'cm_version')
+           'cm_element_row_offsets', 'cm_last_error', 'cm_version')
 
 _lib = None
 
@@ -97,6 +97,7 @@ def load():
     lib.cm_enable_timing.argtypes = [H, C.c_int32]
     lib.cm_last_stage_ms.argtypes = [H, C.c_void_p]
     lib.cm_last_wave_count.argtypes = [H]
+    lib.cm_element_row_offsets.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.cm_element_kernel_dev.argtypes = [C.c_uint64] * 4 + [C.c_int64] + [C.c_uint64] * 3
     lib.cm_last_error.restype = C.c_char_p
     lib.cm_version.restype = C.c_char_p

@@ -870,6 +870,13 @@ int cm_solve_many_g(cm_handle *h, uint64_t masks_dev, uint64_t geom_dev, int64_t
 
 // per-subset bytes of every output of cm_solve_out_host, in the order of the struct
 namespace {
+inline int64_t popcount_words(const uint32_t *w, int n) {
+    int64_t cnt = 0;
+    int i = 0;
+    for (; i + 1 < n; i += 2) cnt += __builtin_popcountll((unsigned long long)w[i] | ((unsigned long long)w[i + 1] << 32));
+    if (i < n) cnt += __builtin_popcount(w[i]);
+    return cnt;
+}
 struct OutItem { void *host; size_t stride; size_t off; };       // stride = bytes per subset; off = offset inside a staging slot
 constexpr int N_OUT = 19;      // fixed-stride outputs; eR_rows (rows of the existing elements only) is handled beside them
 void out_items(const cm_handle *h, const cm_solve_out_host *o, OutItem (&it)[N_OUT]) {
@@ -944,6 +951,9 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host: null argument");
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many_host: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double host_mark[4] = {0, 0, 0, 0};
     if (geom_host)
         for (int64_t b = 0; b < B; ++b)
             if (geom_host[b] < 0 || geom_host[b] >= h->m.n_geom)
@@ -956,11 +966,7 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         if (!roff) return fail(CM_ERR_INVALID, "cm_solve_many_host: eR_rows needs eR_row_offsets (i64 [B+1])");
         const int W = h->m.mask_words;
         for (int64_t b = 0; b < B; ++b) {
-            int64_t cnt = 0;
-            const uint32_t *mw = masks_host + (size_t)b * W;
-            int w = 0;
-            for (; w + 1 < W; w += 2) cnt += __builtin_popcountll((unsigned long long)mw[w] | ((unsigned long long)mw[w + 1] << 32));
-            if (w < W) cnt += __builtin_popcount(mw[w]);
+            const int64_t cnt = popcount_words(masks_host + (size_t)b * W, W);
             if (roff[b + 1] - roff[b] != cnt)
                 return fail(CM_ERR_INVALID, "cm_solve_many_host: eR_row_offsets[" + std::to_string(b + 1) + "] - [" + std::to_string(b) +
                                             "] is not the number of elements of subset " + std::to_string(b));
@@ -1062,6 +1068,7 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     if (trace) {
         tev.resize(1 + 3 * (size_t)P.n_waves);
         for (auto &e : tev) CU(cudaEventCreate(&e));
+        host_mark[0] = host_ms();
         CU(cudaEventRecord(tev[0], st));
     }
     CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
@@ -1110,6 +1117,7 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     int rc = run_waves(h, reinterpret_cast<const uint32_t *>(h->stage), geom_host ? h->d_geom : nullptr,
                        trows_host ? h->d_geom : nullptr, trows_host ? group : 0, B, od0, h->wsbuf, P, st, before, after);
     if (rc != CM_OK) { cudaDeviceSynchronize(); return rc; }
+    host_mark[1] = host_ms();
     if (P.lanes && copy_lanes) {
         for (int i = 0; i < P.NL; ++i) {
             CU(cudaEventRecord(h->copy_lane_ev[i], h->copy_lane[i]));
@@ -1120,7 +1128,10 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         CU(cudaStreamWaitEvent(st, h->copy_ev, 0));
     }
     CU(cudaStreamSynchronize(st));
+    host_mark[2] = host_ms();
     if (trace) {
+        fprintf(stderr, "[cm host] validation + staging set-up until the first event %.3f ms, all waves enqueued at %.3f, synchronised at %.3f\n",
+                host_mark[0], host_mark[1], host_mark[2]);
         long long first = 0;
         for (long long w = 0; w < P.n_waves; ++w) {
             const long long cnt = std::min<long long>(P.sizes.empty() ? P.wsize : P.sizes[(size_t)w], B - first);
@@ -1215,6 +1226,17 @@ int cm_last_stage_ms(const cm_handle *h, double *ms) {
 }
 
 int cm_last_wave_count(const cm_handle *h) { return h ? h->last_waves : 0; }
+
+int cm_element_row_offsets(const uint32_t *masks_host, int64_t B, int32_t mask_words, int64_t *offsets) {
+    if (!masks_host || !offsets || B < 0 || mask_words < 1) return fail(CM_ERR_INVALID, "cm_element_row_offsets: bad argument");
+    int64_t run = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        offsets[b] = run;
+        run += popcount_words(masks_host + (size_t)b * mask_words, mask_words);
+    }
+    offsets[B] = run;
+    return CM_OK;
+}
 
 int cm_element_kernel_dev(uint64_t xyz_u, uint64_t xyz_v, uint64_t props, uint64_t cr, int64_t n, uint64_t Kg,
                           uint64_t R3, uint64_t stream) {

@@ -337,8 +337,10 @@ class CudaStiffness(StiffnessBase):
     def element_row_offsets(masks):
         """Exclusive prefix sum of the subsets' element counts, int64 [B+1]: where each subset's rows start in the
         compact ``eR_rows`` output (``cm_solve_out.eR_row_offsets``)."""
+        masks = np.ascontiguousarray(masks, dtype=np.uint32)
         off = np.zeros(len(masks) + 1, dtype=np.int64)
-        np.cumsum(np.bitwise_count(masks).sum(axis=1, dtype=np.int64), out=off[1:])
+        if len(masks):
+            _capi.check(_capi.load().cm_element_row_offsets(_ptr(masks), len(masks), masks.shape[1], _ptr(off)))
         return off
 
     def solve_many(self, subsets, want=('flag', 'status', 'max_trans', 'compliance'), out=None, geometry=None):

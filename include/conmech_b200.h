@@ -245,6 +245,9 @@ typedef struct cm_solve_out_host {
 
 int cm_solve_many_host(cm_handle *h, const uint32_t *masks_host, int64_t B,
                        const cm_solve_out_host *out);
+/* Row offsets of the compact element rows (cm_solve_out.eR_row_offsets) from a host mask matrix:
+ * offsets[b] = number of existing elements of the subsets before b, offsets[B] = all rows (host i64 [B+1]). */
+int cm_element_row_offsets(const uint32_t *masks_host, int64_t B, int32_t mask_words, int64_t *offsets);
 /* ... with a geometry variant per subset (geom_host i32 [B], NULL = variant 0; an index outside
  * [0, cm_geometry_count) is CM_ERR_INVALID) */
 int cm_solve_many_host_g(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, int64_t B,

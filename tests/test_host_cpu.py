@@ -285,3 +285,16 @@ def test_fragment_maps_of_the_factorisation_kernel():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
+
+
+def test_element_row_offsets_host_helper():
+    """cm_element_row_offsets (host-only C function): exclusive prefix sum of the masks' popcounts, odd and even
+    word counts, empty batch."""
+    from conmech_b200.cuda_stiffness import CudaStiffness
+    rng = np.random.default_rng(3)
+    for words in (1, 2, 7, 30):
+        m = rng.integers(0, 2 ** 32, size=(257, words), dtype=np.uint64).astype(np.uint32)
+        off = CudaStiffness.element_row_offsets(m)
+        ref = np.concatenate([[0], np.cumsum(np.bitwise_count(m).sum(axis=1, dtype=np.int64))])
+        assert off.dtype == np.int64 and np.array_equal(off, ref)
+    assert np.array_equal(CudaStiffness.element_row_offsets(np.zeros((0, 4), dtype=np.uint32)), [0])

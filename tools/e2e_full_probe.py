@@ -69,3 +69,10 @@ same = all(np.array_equal(out_host[n], od[n].cpu().numpy(), equal_nan=True) for 
 print('FLY={} TAPER={} MIN={} MB={} | host full {:.2f} ms = {:.1f} k/s ({} waves) | device full {:.2f} ms = {:.1f} k/s | ratio {:.3f} | same bits {}'.format(
     fly, os.environ.get('CM_TAPER', '-'), os.environ.get('CM_TAPER_MIN', '-'), os.environ.get('CM_HOST_WAVE_MB', '-'),
     host_ms, B / host_ms, waves, dev_ms, B / dev_ms, dev_ms / host_ms, same))
+if os.environ.get('PROBE_COMPACT') and os.environ.get('PROBE_PYTIME'):
+    # where the Python side of one call spends its time
+    t0 = time.perf_counter(); off = eng.element_row_offsets(hnp[0]); t1 = time.perf_counter()
+    print('element_row_offsets {:.3f} ms'.format((t1 - t0) * 1e3))
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable(); eng.solve_many(hnp[0], want=COMPACT, out=outs_c[0]); pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(8)
