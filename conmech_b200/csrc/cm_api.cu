@@ -909,7 +909,7 @@ void out_advance(const cm_handle *h, cm_solve_out_host *o, int64_t b0) {
 extern "C" {
 
 static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, const int32_t *trows_host, int group,
-                      int64_t B, const cm_solve_out_host *o);
+                      int64_t B, const cm_solve_out_host *o, int64_t chunk = 0, const volatile int32_t *ready = nullptr);
 
 // Host buffers.  Masks go up in one copy.  Outputs are staged per WAVE in a ring of device slots: right
 // after a wave's last kernel its slot is drained to the caller's arrays by a copy stream (one
@@ -946,9 +946,14 @@ int cm_solve_many_host_seq(cm_handle *h, const uint32_t *masks_host, int64_t B, 
 
 }  // extern "C"
 
+// chunk / ready (cm_solve_many_host_chunks): the masks arrive in consecutive chunks of `chunk` subsets, chunk k is complete
+// once ready[k] != 0 (< 0: cancelled).  A wave is enqueued as soon as the chunks it covers are there and takes its own
+// masks to the device - the producer (the Python facade packing id lists) runs beside the GPU, wave by wave.
 static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *geom_host, const int32_t *trows_host, int group,
-                      int64_t B, const cm_solve_out_host *o) {
+                      int64_t B, const cm_solve_out_host *o, int64_t chunk, const volatile int32_t *ready) {
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host: null argument");
+    if (ready && (chunk <= 0 || o->eR_rows || trows_host))
+        return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: chunk must be positive; compact element rows and sequences need all masks up front");
     if (h->m.n_lc == 0) return fail(CM_ERR_STATE, "cm_solve_many_host: call cm_set_loadcases first");
     if (B <= 0) return CM_OK;
     const auto host_t0 = std::chrono::steady_clock::now();
@@ -1020,7 +1025,8 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
     for (int i = 0; i < N_OUT; ++i) if (it[i].host) out_per_subset += it[i].stride;
     if (roff) out_per_subset += (size_t)((roff[B] - roff[0]) / B) * m.n_lc * 96;
     static const long long wave_mb = getenv("CM_HOST_WAVE_MB") ? atoll(getenv("CM_HOST_WAVE_MB")) : 64;
-    const long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
+    long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
+    if (ready && max_wave == 0) max_wave = 1;      // masks still being produced: small waves (two GPU fills) start early
     WavePlan P;
     { int rc = plan_waves(h, B, h->ws_bytes, &P, max_wave, out_per_subset); if (rc != CM_OK) return rc; }
     if (trows_host && group > 1) {
@@ -1071,11 +1077,23 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         host_mark[0] = host_ms();
         CU(cudaEventRecord(tev[0], st));
     }
-    CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
+    if (!ready) CU(cudaMemcpyAsync(h->stage, masks_host, Bn * m.mask_words * 4, cudaMemcpyHostToDevice, st));
+    int64_t chunks_seen = 0;
     if (aux_host) CU(cudaMemcpyAsync(h->d_geom, aux_host, Bn * sizeof(int), cudaMemcpyHostToDevice, st));
     if (roff) CU(cudaMemcpyAsync(h->d_rowoff, roff, (Bn + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     char *slots = h->stage + mask_bytes;
-    auto before = [&](long long w, long long first, int, cudaStream_t ls, cm_out_dev &od) -> int {
+    auto before = [&](long long w, long long first, int count, cudaStream_t ls, cm_out_dev &od) -> int {
+        if (ready) {
+            const int64_t need = (first + count - 1) / chunk + 1;           // chunks this wave reads
+            for (; chunks_seen < need; ++chunks_seen) {
+                int32_t r;
+                while ((r = __atomic_load_n(const_cast<const int32_t *>(ready) + chunks_seen, __ATOMIC_ACQUIRE)) == 0)
+                    std::this_thread::sleep_for(std::chrono::microseconds(20));
+                if (r < 0) return fail(CM_ERR_STATE, "cm_solve_many_host_chunks: cancelled by the producer");
+            }
+            CU(cudaMemcpyAsync(h->stage + (size_t)first * m.mask_words * 4, masks_host + (size_t)first * m.mask_words,
+                               (size_t)count * m.mask_words * 4, cudaMemcpyHostToDevice, ls));
+        }
         const int s = (int)(w % n_slots);
         if (w >= n_slots) CU(cudaStreamWaitEvent(ls, h->slot_free[s], 0));      // the slot's previous copies are done
         if (trace) CU(cudaEventRecord(tev[1 + 3 * (size_t)w], ls));
@@ -1153,21 +1171,8 @@ int cm_solve_many_host_chunks(cm_handle *h, const uint32_t *masks_host, int64_t 
                               int64_t chunk, const volatile int32_t *ready) {
     if (!h || !o || !masks_host) return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: null argument");
     if (chunk <= 0) return fail(CM_ERR_INVALID, "cm_solve_many_host_chunks: chunk must be positive");
-    int64_t k = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
-        if (ready) {
-            int32_t r;
-            while ((r = __atomic_load_n(const_cast<const int32_t *>(ready) + k, __ATOMIC_ACQUIRE)) == 0)
-                std::this_thread::sleep_for(std::chrono::microseconds(20));
-            if (r < 0) return fail(CM_ERR_STATE, "cm_solve_many_host_chunks: cancelled by the producer");
-        }
-        const int64_t n = std::min<int64_t>(chunk, B - b0);
-        cm_solve_out_host c = *o;
-        out_advance(h, &c, b0);
-        int rc = cm_solve_many_host(h, masks_host + (size_t)b0 * h->m.mask_words, n, &c);
-        if (rc != CM_OK) return rc;
-    }
-    return CM_OK;
+    if (!ready) return solve_host(h, masks_host, nullptr, nullptr, 0, B, o);
+    return solve_host(h, masks_host, nullptr, nullptr, 0, B, o, chunk, ready);
 }
 
 // One process, several GPUs: the batch is range-partitioned over the handles (one per device, same

@@ -33,6 +33,11 @@ __device__ __forceinline__ void ldg4(double (&v)[4], const double *p) {
 __device__ __forceinline__ void ldg4s(double (&v)[4], const double *p) {
 #if defined(CM_LD256) && CM_LD256       // experiment: one 256-bit load per lane instead of two 128-bit halves
     asm volatile("ld.global.L1::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+#elif defined(CM_L2_EL) && CM_L2_EL      // experiment: operand tiles are re-read by the following rows - last to be evicted from L2
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L1::evict_first.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol) : "memory");
+    asm volatile("ld.global.L1::evict_first.L2::cache_hint.v2.f64 {%0,%1}, [%2+16], %3;" : "=d"(v[2]), "=d"(v[3]) : "l"(p), "l"(pol) : "memory");
 #else
     asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
     asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
@@ -85,12 +90,20 @@ __device__ __forceinline__ void acc_load(TileAcc &a, const double *T, int lane) 
 // (cj, ri) are 16 contiguous bytes, a warp load covers eight 64-byte row segments
 __device__ __forceinline__ void acc_load_rm(TileAcc &a, const double *T, int lane) {
     const double *p = T + (lane >> 2) * 32 + 2 * (lane & 3);
+#if defined(CM_L2_EF) && CM_L2_EF      // experiment: the assembled tile is read exactly once - first to be evicted from L2 as well
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
 #pragma unroll
     for (int cj = 0; cj < 4; ++cj)
 #pragma unroll
         for (int ri = 0; ri < 4; ++ri) {
             double2 v;
+#if defined(CM_L2_EF) && CM_L2_EF
+            asm volatile("ld.global.L1::evict_first.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p + ri * 256 + cj * 8), "l"(pol) : "memory");
+#else
             asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + ri * 256 + cj * 8) : "memory");
+#endif
             a.c[cj][0][ri] = v.x; a.c[cj][1][ri] = v.y;
         }
 }

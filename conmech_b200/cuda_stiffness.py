@@ -395,7 +395,7 @@ class CudaStiffness(StiffnessBase):
             geom = np.ascontiguousarray(np.asarray(geometry, dtype=np.int32).reshape(-1))
             if geom.size != B:
                 raise ValueError('geometry must hold one variant index per subset')
-        if geom is not None or prepacked or B < 2 * self.PIPELINE_CHUNK:
+        if geom is not None or prepacked or B < self.PIPELINE_MIN:
             masks = masks0 if prepacked else pack_masks(subsets, self.nE)
             oh = out_struct()
             if geom is not None:
@@ -409,9 +409,10 @@ class CudaStiffness(StiffnessBase):
                 _capi.check(self._lib.cm_solve_many_host(self._handle, _ptr(masks), B, C.byref(oh)))
             return res
         # Python id lists, large batch: packing (this thread, GIL held, ~5 ns per id) is pipelined with
-        # the GPU work chunk by chunk.  ONE worker thread per device makes ONE call into the library for
-        # its share of the batch (cm_solve_many_host_chunks); inside it waits per chunk - without the
-        # GIL - for the 'ready' flag this thread release-stores after writing the chunk's masks.
+        # the GPU work.  ONE worker thread per device makes ONE call into the library for its share of the
+        # batch (cm_solve_many_host_chunks); the library enqueues a wave of subsets as soon as the chunks it
+        # covers are there - it waits, without the GIL, for the 'ready' flags this thread release-stores after
+        # writing each chunk's masks.
         import threading
         from .sharding import shard_range
         G = len(self._handles)
@@ -421,7 +422,7 @@ class CudaStiffness(StiffnessBase):
             lo, hi = shard_range(B, G, g)
             if hi == lo:
                 continue
-            n_chunks = max(1, min(8, (hi - lo) // self.PIPELINE_CHUNK))
+            n_chunks = max(1, min(64, (hi - lo) // self.PIPELINE_CHUNK))
             step = -(-(hi - lo) // n_chunks)
             n_chunks = -(-(hi - lo) // step)
             jobs.append((h, lo, hi, step, np.zeros(n_chunks, dtype=np.int32)))
@@ -540,7 +541,8 @@ class CudaStiffness(StiffnessBase):
         from .masks import pack_masks_csr
         return self.solve_many(pack_masks_csr(flat_ids, offsets, self.nE), want=want, out=out)
 
-    PIPELINE_CHUNK = 2048          # subsets per pipelined chunk of solve_many (id lists only)
+    PIPELINE_CHUNK = 512           # subsets per pipelined chunk of solve_many (id lists only): the GPU starts after the first ones
+    PIPELINE_MIN = 4096            # smaller batches are packed in one go
 
     def solve_many_device(self, masks, want=('flag', 'status', 'max_trans', 'compliance'), out=None,
                           max_in_flight=None, geometry=None):

@@ -392,7 +392,7 @@ def test_solve_many_from_id_lists_pipelined():
     sc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
     sc.set_nodal_displacement_tol(trans_tol=2e-5)
     eng = sc._sc_ins
-    B = 2 * eng.PIPELINE_CHUNK + 777
+    B = eng.PIPELINE_MIN + 777                      # above the threshold of the pipelined path
     lists = [syn.connected_subset(model, s) for s in range(B)]
     lists[5] = []
     want = ('flag', 'status', 'max_trans', 'compliance', 'n_free')
