@@ -995,11 +995,29 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         return fail(CM_ERR_INVALID, "cm_solve_many_host_seq: model too large for shared rows (solution vectors must fit shared memory)");
     const cm_model_dev &m = h->m;
     const size_t Bn = (size_t)B;
+    // device staging: the masks of the batch, then CM_STAGE_SLOTS slots of one wave's outputs each
+    OutItem it[N_OUT];
+    out_items(h, o, it);
+    // A wave's results leave for the host when its last kernel has finished, and the copies of consecutive waves
+    // queue on one copy engine: with full results (127 KB per subset on the 1k-element frame) a wave of 2500 subsets
+    // is a 6 ms copy, and the last waves of all lanes finish together - their copies are an unhidden tail.  Large
+    // outputs therefore run in waves of about 64 MB of results (never below what fills the GPU twice).
+    size_t out_per_subset = 0;
+    for (int i = 0; i < N_OUT; ++i) if (it[i].host) out_per_subset += it[i].stride;
+    if (roff) out_per_subset += (size_t)((roff[B] - roff[0]) / B) * m.n_lc * 96;
+    static const long long wave_mb = getenv("CM_HOST_WAVE_MB") ? atoll(getenv("CM_HOST_WAVE_MB")) : 64;
+    long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
+    if (ready && max_wave == 0) max_wave = 1;      // masks still being produced: small waves (two GPU fills) start early
     // workspace: enough subsets in flight to fill the GPU several times over, bounded by memory
     // (the driver is only asked about free memory when the workspace has to grow)
     const size_t per = h->L.per_subset;
     static const size_t ws_subsets = getenv("CM_WS_SUBSETS") ? (size_t)std::max(1, atoi(getenv("CM_WS_SUBSETS"))) : 8192;      // 4096: 266 k, 8192: 273 k, 12500: 272 k solves/s on config 3 (profiles/r01c_experiments.txt)
     size_t want_subsets = std::min<size_t>(Bn, ws_subsets);
+    if (max_wave > 0 && !(trows_host && group > 1)) {
+        // bounded waves (large outputs, chunked masks): no more slabs than the lanes' waves use (19 GB instead of 45 on the 1k frame)
+        const long long sm_fill = getenv("CM_LANE_MIN") ? atoi(getenv("CM_LANE_MIN")) : 8 * h->m.n_sm;
+        want_subsets = std::min<size_t>(want_subsets, (size_t)h->n_lanes * (size_t)std::max<long long>(max_wave, sm_fill));
+    }
     if (trows_host && group > 1) want_subsets = (want_subsets + group - 1) / group * group;     // whole groups
     size_t want = want_subsets * per;
     if (want > h->ws_bytes) {
@@ -1014,19 +1032,6 @@ static int solve_host(cm_handle *h, const uint32_t *masks_host, const int32_t *g
         CU(cudaMalloc((void **)&h->wsbuf, want));
         h->ws_bytes = want;
     }
-    // device staging: the masks of the batch, then CM_STAGE_SLOTS slots of one wave's outputs each
-    OutItem it[N_OUT];
-    out_items(h, o, it);
-    // A wave's results leave for the host when its last kernel has finished, and the copies of consecutive waves
-    // queue on one copy engine: with full results (127 KB per subset on the 1k-element frame) a wave of 2500 subsets
-    // is a 6 ms copy, and the last waves of all lanes finish together - their copies are an unhidden tail.  Large
-    // outputs therefore run in waves of about 64 MB of results (never below what fills the GPU twice).
-    size_t out_per_subset = 0;
-    for (int i = 0; i < N_OUT; ++i) if (it[i].host) out_per_subset += it[i].stride;
-    if (roff) out_per_subset += (size_t)((roff[B] - roff[0]) / B) * m.n_lc * 96;
-    static const long long wave_mb = getenv("CM_HOST_WAVE_MB") ? atoll(getenv("CM_HOST_WAVE_MB")) : 64;
-    long long max_wave = out_per_subset > 16384 ? std::max<long long>(1, (wave_mb << 20) / (long long)out_per_subset) : 0;
-    if (ready && max_wave == 0) max_wave = 1;      // masks still being produced: small waves (two GPU fills) start early
     WavePlan P;
     { int rc = plan_waves(h, B, h->ws_bytes, &P, max_wave, out_per_subset); if (rc != CM_OK) return rc; }
     if (trows_host && group > 1) {
