@@ -586,7 +586,7 @@ def test_two_gpus_one_process_bit_exact():
     B = 6001
     lists = [syn.connected_subset(model, s) for s in range(B)]
     masks = syn.pack_masks(lists, len(model.elements))
-    want = ('flag', 'status', 'max_trans', 'compliance', 'U', 'Rf', 'eR', 'n_free')
+    want = ('flag', 'status', 'max_trans', 'compliance', 'U', 'Rf', 'eR', 'n_free', 'Rf_sup', 'eR_rows')
     res = []
     for devices in ([0], [0, 1], [1]):
         sc = StiffnessChecker(model, checker_engine='cuda', devices=devices)
@@ -599,9 +599,12 @@ def test_two_gpus_one_process_bit_exact():
             assert_array_equal(r_lists['max_trans'], res[-1]['max_trans'])
             assert sc.solve(lists[7]) == bool(res[-1]['flag'][7, 0])
         sc._sc_ins.close()
-    for k in want:
+    for k in want + ('eR_row_offsets',):
         assert_array_equal(res[0][k], res[1][k], err_msg=k)
         assert_array_equal(res[0][k], res[2][k], err_msg=k)
+    off = res[1]['eR_row_offsets']           # the compact rows of both devices' shares are the dense rows of the existing elements
+    for b in (0, B // 2 - 1, B // 2, B // 2 + 1, B - 1):
+        assert_array_equal(res[1]['eR_rows'][off[b]:off[b + 1]], res[1]['eR'][b, 0][sorted(lists[b])], err_msg=str(b))
 
 
 def test_geometry_variants_many_models():
