@@ -132,6 +132,9 @@ __device__ __forceinline__ void frag_mma(TileAcc &acc, const double (&a)[4], con
 // the whole sum is one linear stream: A and B advance 128 doubles per k-step, d advances 4.
 // nsteps is a multiple of 8.  Software pipelined by hand: the fragments of step q+1 are in flight
 // while the MMAs of step q issue.  SYRK: A == B (diagonal tile; only the lower atoms are computed).
+#ifndef CM_PF_DIST
+#define CM_PF_DIST 2
+#endif
 template <bool SYRK>
 __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__restrict__ A,
                                                   const double *__restrict__ B, const double *__restrict__ d,
@@ -148,7 +151,10 @@ __device__ __forceinline__ void acc_update_stream(TileAcc &acc, const double *__
     if (!SYRK) ldg4s(b0, pb);
     d0 = pd[0];
     for (int q = 0; q < nsteps; q += 2) {
-#if defined(CM_PF_DIST) && CM_PF_DIST > 0      // experiment: pull the lane's sectors of k-steps q+D, q+D+1 into L1 with real (dummy) loads
+#if CM_PF_DIST > 0      // pull the lane's sectors of k-steps q+D, q+D+1 into L1 with real (dummy) 4-byte loads: the register look-ahead
+                        // is one k-step, this makes the following pair an L1 hit (9.93 -> 9.87 ms per 4096 subsets at D = 2; the
+                        // addresses stay inside the tile row's storage; with all operands resident in a larger L1 - timing only -
+                        // the gain is 1.8 %: operand latency is not what bounds the kernel, profiles/r02_experiments.txt)
         {
             unsigned z0, z1;
             asm volatile("ld.global.L1::evict_last.b32 %0, [%1];" : "=r"(z0) : "l"(pa + 128 * CM_PF_DIST) : "memory");
