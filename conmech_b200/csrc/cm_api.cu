@@ -658,7 +658,7 @@ size_t cm_workspace_bytes(const cm_handle *h, int64_t n) {
 
 int cm_set_variant(cm_handle *h, int32_t variant) {     // 0 scalar validation, 2/3 tensor-core kernel (4/8 warps per CTA), 4/5 instrumented
     if (!h) return fail(CM_ERR_INVALID, "cm_set_variant: null handle");
-    if (variant < 0 || variant > 12) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..12 (7/8/9: 2-/3-/1-warp CTAs; 10/11/12: operand ring)");
+    if (variant < 0 || variant > 13) return fail(CM_ERR_INVALID, "cm_set_variant: variant must be 0..13 (7/8/9: 2-/3-/1-warp CTAs; 10/11/12: operand ring; 13: tensor-memory look-ahead)");
     h->variant = variant;
     return CM_OK;
 }

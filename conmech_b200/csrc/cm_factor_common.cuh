@@ -32,6 +32,7 @@ struct K3Ctx {
     int trows;
     unsigned ring0, ringbar0;      // operand ring (OPS builds): shared-window address of warp 0's stages / barriers
     unsigned *ring_it;             // [NW] pairs each warp has consumed so far (stage index and barrier phase follow from it)
+    unsigned tmem;                 // look-ahead builds: base address of the CTA's tensor-memory allocation (128 columns)
     int bt, n_pad, n_lc, zero_bits;
 };
 __shared__ K3Ctx s_ctx;

@@ -260,6 +260,42 @@ __device__ __forceinline__ void acc_update_stream_ring(TileAcc &acc, const doubl
     R.it += npairs;
 }
 
+// ---- tensor memory as a parking place for an accumulator tile (the look-ahead variant of the factorisation kernel):
+// tcgen05.st / tcgen05.ld move the 64 registers of a lane to / from 64 columns of the lane's row of the CTA's allocation
+// (SASS STTM.x64 / LDTM.x64); warp w of a 4-warp CTA owns lanes 32w .. 32w+31.  No f64 MMA reads tensor memory - it is
+// used as 256 KB per SM of register-speed storage that the kernel otherwise leaves idle.
+// (Four x16 transfers, one per block column of the tile; a single x64 transfer - 64 consecutive registers - measured the same.)
+__device__ __forceinline__ void tm_park(unsigned taddr, const TileAcc &a) {
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj) {
+        unsigned r[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const double v = a.c[cj][i >> 2][i & 3];
+            r[2 * i] = (unsigned)__double2loint(v); r[2 * i + 1] = (unsigned)__double2hiint(v);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                     :: "r"(taddr + 16u * cj),
+                     "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),"r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15])
+                     : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_unpark(unsigned taddr, TileAcc &a) {
+    unsigned r[4][16];
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[cj][0]),"=r"(r[cj][1]),"=r"(r[cj][2]),"=r"(r[cj][3]),"=r"(r[cj][4]),"=r"(r[cj][5]),"=r"(r[cj][6]),"=r"(r[cj][7]),
+                       "=r"(r[cj][8]),"=r"(r[cj][9]),"=r"(r[cj][10]),"=r"(r[cj][11]),"=r"(r[cj][12]),"=r"(r[cj][13]),"=r"(r[cj][14]),"=r"(r[cj][15])
+                     : "r"(taddr + 16u * cj) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int cj = 0; cj < 4; ++cj)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.c[cj][i >> 2][i & 3] = __hiloint2double((int)r[cj][2 * i + 1], (int)r[cj][2 * i]);
+}
+
 // acc <- acc * M^T in place, M = D_J^-1 L_JJ^-1 lower triangular in the cm_mtile_off layout (the
 // triangular solve of an off-diagonal tile as a tile product).  The accumulator fragments ARE the A
 // operand: k-slot t of k-step (cj,e) stands for column 8cj + 2t + e, which is exactly the element

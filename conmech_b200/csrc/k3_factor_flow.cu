@@ -41,35 +41,59 @@ __device__ unsigned long long g_flow_prof[16];
 // solve against M_J, the tile's share of the forward substitution and, for the chain tile
 // (J == I-1), the newest term of the diagonal tile, handed to the diagonal factorisation through
 // the shared scratch.  Returns true when the diagonal tile was placed in the scratch.
-template <bool PROF, int OPS>
-__device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
+//
+// Look-ahead builds (LA): a visit may stop with the accumulator PARKED in tensor memory (slot J & 1 of the warp's lanes).
+//   Kfrom < 0: fresh visit; Kfrom >= 0: resume - the accumulator comes back from the slot, terms < Kfrom are in it.
+//   Kstop:     accumulate the terms K < min(Kstop, J).
+//   LA_AHEAD:  look-ahead call - park after those terms and return LA_K0 + (terms done); LA_NONE if there was nothing to do.
+//   LA_TRY:    after ALL terms: if M_J is not published yet, park and return LA_PARKED instead of waiting for it.
+// Return otherwise: 1 = chain tile (the diagonal tile was placed in the scratch), 0 = done.
+enum { LA_AHEAD = 1, LA_TRY = 2, LA_PARKED = 2, LA_NONE = 3, LA_K0 = 16 };
+#ifndef CM_LA_FAR
+#define CM_LA_FAR 0
+#endif
+#ifndef CM_LA_CHUNK
+#define CM_LA_CHUNK 0
+#endif
+template <bool PROF, int OPS, bool LA>
+__device__ __noinline__ int offdiag_tile(int I, int J, int kcI, int lane, int Kfrom, int Kstop, int la_flags) {
     const int bt = CTX(bt);
     long long *pc = PROF ? CTX(pc) + (threadIdx.x >> 5) * 16 : nullptr;
     double *T = cm_tile_ptr(CTX(tiles), bt, I, J);
     const int ab = J - I + bt - 1, aw = (bt + 63) >> 6;
     const unsigned long long *arow = CTX(arow);
     const bool has_a = (arow[I * aw + (ab >> 6)] >> (ab & 63)) & 1ull;         // K2 assembled entries into this tile
+    const unsigned slot = LA ? CTX(tmem) + ((unsigned)(threadIdx.x & ~31u) << 16) + 64u * (unsigned)(J & 1) : 0u;
+    const bool resume = LA && Kfrom >= 0, ahead = LA && (la_flags & LA_AHEAD);
+    const int Kto = LA ? min(Kstop, J) : J;
     // the next tile of the row that K2 assembled (the diagonal tile always is) comes from DRAM: start that read now
-    if ((arow[I * aw + ((ab + 1) >> 6)] >> ((ab + 1) & 63)) & 1ull) {
+    if (!resume && !ahead && ((arow[I * aw + ((ab + 1) >> 6)] >> ((ab + 1) & 63)) & 1ull)) {
         const double *nx = T + CM_TILE_ELEMS + lane * 16;
         asm volatile("prefetch.global.L2 [%0];" :: "l"(nx));
         asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 512));
     }
     // operand columns left of k-step qs are zero in row I or in row J (envelope): the stream starts there
-    int qs = max(kcI, CTX(kcol)[J]);
+    int qs = resume ? Kfrom * 8 : max(kcI, CTX(kcol)[J]);
     int K = qs >> 3;
     FP_T0(pc);
     const int trows = CTX(trows);                   // rows < trows live in the trunk's slab
     TileAcc acc;
-    if (K >= J && !has_a && J != I - 1) {         // no entries and no fill-in: the tile of L is zero (the chain tile still hands the diagonal over)
+    if (resume) {
+        tm_unpark(slot, acc);
+    } else {
+        if (K >= J && !has_a && J != I - 1) {         // no entries and no fill-in: the tile of L is zero (the chain tile still hands the diagonal over)
+            if (ahead) return LA_NONE;                // (left to the regular visit)
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) stg4(T + i * 128 + lane * 4, 0.0, 0.0, 0.0, 0.0);
-        return false;
+            for (int i = 0; i < 8; ++i) stg4(T + i * 128 + lane * 4, 0.0, 0.0, 0.0, 0.0);
+            return 0;
+        }
+        if (ahead && Kto <= K) return LA_NONE;        // no term of this tile can run yet
+        if (has_a) acc_load_rm(acc, T, lane); else acc_zero(acc);      // assembled K~ tiles are row-major (K2)
     }
-    if (has_a) acc_load_rm(acc, T, lane); else acc_zero(acc);      // assembled K~ tiles are row-major (K2)
-    while (K < J) {
-        int Kend = min(wait_prog_gt(CTX(prog), J, K), J);
+    while (K < Kto) {
+        int Kend = min(wait_prog_gt(CTX(prog), J, K), Kto);
         if (K < trows && Kend > trows) Kend = trows;           // the pivots of the shared columns come from the trunk
+        if (CM_LA_CHUNK && ahead) Kend = K + 1;                // one operand tile at a time, then look at M_{J-1} again
         FP_ADD(pc, 0);
         const double *tiles = CTX(tiles);
         const double *A = tiles + ((size_t)I * bt + (bt - 1 - I)) * CM_TILE_ELEMS + (size_t)qs * 128;   // tile (I,0) + qs k-steps
@@ -87,6 +111,16 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
         K = Kend;
         qs = K * 8;
         FP_ADD(pc, 1);
+#if CM_LA_CHUNK
+        // look-ahead call: the tile that was parked for this one (I, J-1) can go on as soon as M_{J-1} is there
+        if (ahead && K < Kto && flag_acquire(CTX(prog) + J - 1) > J - 1) break;
+#endif
+    }
+    if (LA) {
+        if (ahead) { tm_park(slot, acc); return LA_K0 + K; }
+        // M_J not there yet: let the caller start the next tile of the row meanwhile - if row J is far enough from publishing
+        // it (CM_LA_FAR tile columns short of its diagonal factor; 0 = any wait) that a round trip through tensor memory pays
+        if ((la_flags & LA_TRY) && flag_acquire(CTX(prog) + J) <= J - CM_LA_FAR) { tm_park(slot, acc); return LA_PARKED; }
     }
     wait_prog_gt(CTX(prog), J, J);                // M_J published
     FP_ADD(pc, 2);
@@ -136,7 +170,7 @@ __device__ __noinline__ bool offdiag_tile(int I, int J, int kcI, int lane) {
 }
 
 // OPS: stages of the shared-memory operand ring per warp (0 = operands through registers, one k-step of look-ahead)
-template <int NW, bool PROF, int OPS>
+template <int NW, bool PROF, int OPS, bool LA = false>
 #ifndef CM_K3_CTAS4
 #define CM_K3_CTAS4 4          // resident 4-warp CTAs per SM the register allocation aims at (timing experiments: 5)
 #endif
@@ -168,6 +202,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
     unsigned *s_ring_it = reinterpret_cast<unsigned *>(s_ringbar + NW * OPS);
     __shared__ long long s_pc[PROF ? NW : 1][16];
     __shared__ long long s_tpub;
+    __shared__ unsigned s_tmem;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // CTA r factors the subset with the r-th largest cost of the wave (k2_schedule): big ones first
@@ -206,7 +241,19 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
     volatile int *prog = s_prog;
     volatile int *yprog = s_yprog;
 
+    if (LA) {
+        // 128 columns of tensor memory per CTA (four CTAs per SM = all 512): two parked accumulator tiles per warp
+        static_assert(!LA || NW == 4, "one lane quarter of the allocation per warp");
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(&s_tmem)), "n"(128) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     if (t == 0) {
+        s_ctx.tmem = LA ? s_tmem : 0u;
         s_ctx.tiles = tiles; s_ctx.minv = minv; s_ctx.dpiv = dpiv; s_ctx.X = X;
         s_ctx.kcol = s_kcol; s_ctx.arow = s_arow; s_ctx.prog = s_prog; s_ctx.yprog = s_yprog;
         s_ctx.s_part = s_part; s_ctx.s_rhs = s_rhs; s_ctx.s_scr = s_scr; s_ctx.s_minpiv = s_minpiv; s_ctx.s_fail = s_fail; s_ctx.s_dacc = s_dacc;
@@ -271,8 +318,29 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
         }
         __syncwarp();
         bool handed = false;                     // diagonal tile already in the scratch (chain tile hand-over)
+        if (LA) {
+            // Look-ahead over the waits for M_J.  At a band of NW..2 NW tiles nearly every tile of a row depends on a row that
+            // is still being factored, and a warp that waits for M_J holds 64 accumulator registers idle (10 % of the kernel).
+            // Instead the finished accumulator is parked in tensor memory and the NEXT tile of the row runs the terms that are
+            // available (all but the one with the parked tile), is parked in the other slot, and the first is taken up again.
+            int pend = -1;                       // >= 0: tile J was started ahead, terms < pend are in its parked accumulator
+            for (int J = kfI; J < I; ++J) {
+                int r = offdiag_tile<PROF, OPS, LA>(I, J, kcI, lane, pend, J, J + 1 < I ? LA_TRY : 0);
+                pend = -1;
+                if (r == LA_PARKED) {
+                    const int avail = min(J, flag_acquire(prog + J + 1));        // terms K < J of tile (I, J+1) that row J+1 has reached
+                    const int r2 = offdiag_tile<PROF, OPS, LA>(I, J + 1, kcI, lane, -1, avail, LA_AHEAD);
+                    if (r2 >= LA_K0) pend = r2 - LA_K0;
+                    r = offdiag_tile<PROF, OPS, LA>(I, J, kcI, lane, J, J, 0);  // back to tile J: wait for M_J, finish
+                }
+                handed = r == 1;
+                release_fence<OPS>();
+                __syncwarp();
+                if (lane == 0) prog[I] = J + 1;
+            }
+        } else
         for (int J = kfI; J < I; ++J) {
-            handed = offdiag_tile<PROF, OPS>(I, J, kcI, lane);
+            handed = offdiag_tile<PROF, OPS, false>(I, J, kcI, lane, -1, J, 0) == 1;
             release_fence<OPS>();
             __syncwarp();
             if (lane == 0) prog[I] = J + 1;
@@ -309,6 +377,7 @@ k3_factor_flow(cm_model_dev m, cm_ws_layout L, char *ws, int rank0, int stride) 
         if (trows > 0) mp = fmin(mp, reinterpret_cast<const double *>(tslab + L.off_dpiv)[L.n_pad]);
         dpiv[L.n_pad] = mp;            // slot after the pivots
     }
+    if (LA && warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem), "n"(128) : "memory");
 }
 
 size_t flow_smem(const cm_model_dev &m, int nw, int ops) {
@@ -324,13 +393,13 @@ size_t flow_smem(const cm_model_dev &m, int nw, int ops) {
 
 }  // namespace
 
-template <int NW, bool PROF, int OPS>
+template <int NW, bool PROF, int OPS, bool LA = false>
 static cudaError_t launch_flow(const cm_model_dev &m, const cm_ws_layout &L, char *ws, int rank0, int count, int stride, cudaStream_t st) {
     static cm_smem_cache cache;
     const size_t smem = flow_smem(m, NW, OPS);
-    cudaError_t e = cm_ensure_smem(k3_factor_flow<NW, PROF, OPS>, smem, cache, m.device);
+    cudaError_t e = cm_ensure_smem(k3_factor_flow<NW, PROF, OPS, LA>, smem, cache, m.device);
     if (e != cudaSuccess) return e;
-    k3_factor_flow<NW, PROF, OPS><<<count, NW * 32, smem, st>>>(m, L, ws, rank0, stride);
+    k3_factor_flow<NW, PROF, OPS, LA><<<count, NW * 32, smem, st>>>(m, L, ws, rank0, stride);
     return cudaGetLastError();
 }
 
@@ -351,6 +420,7 @@ cudaError_t cm_launch_factor_flow(const cm_model_dev &m, const cm_ws_layout &L, 
     if (config == 10) return launch_flow<4, false, 1>(m, L, ws, rank0, count, stride, st);     // 59 KB per CTA: three CTAs per SM
     if (config == 11) return launch_flow<4, false, 2>(m, L, ws, rank0, count, stride, st);     // 76 KB: three CTAs per SM just fit
     if (config == 12) return launch_flow<8, false, 2>(m, L, ws, rank0, count, stride, st);      // 8-warp CTAs (wide bands)
+    if (config == 13) return launch_flow<4, false, 0, true>(m, L, ws, rank0, count, stride, st);   // look-ahead over the M_J waits, accumulators parked in tensor memory
     static const int ring16 = getenv("CM_K3_RING") ? atoi(getenv("CM_K3_RING")) : 0;
     if (config == 1) return prof ? launch_flow<8, true, 0>(m, L, ws, rank0, count, stride, st) : launch_flow<8, false, 0>(m, L, ws, rank0, count, stride, st);
     if (config == 3) return ring16 ? launch_flow<8, false, 2>(m, L, ws, rank0, count, stride, st) : launch_flow<16, false, 0>(m, L, ws, rank0, count, stride, st);

@@ -315,7 +315,8 @@ class CudaStiffness(StiffnessBase):
     def set_factor_variant(self, variant):
         """1 = FP64 tensor-core factorisation, CTA size chosen per launch (default); 2 / 3 / 6 = pinned to
         4 / 8 / 16-warp CTAs; 4 / 5 = 4 / 8-warp CTAs with activity cycle counters; 7 / 8 / 9 = 2 / 3 / 1-warp
-        CTAs; 10 / 11 / 12 = operands through a bulk-copy (TMA) shared-memory ring; 0 = scalar validation
+        CTAs; 10 / 11 / 12 = operands through a bulk-copy (TMA) shared-memory ring; 13 = look-ahead over the M_J waits with
+        accumulators parked in tensor memory; 0 = scalar validation
         variant."""
         for h in self._handles:
             _capi.check(self._lib.cm_set_variant(h, int(variant)))

@@ -187,7 +187,9 @@ typedef struct cm_solve_out {
  * 10 / 11 = 4-warp CTAs whose update-stream operands come through a shared-memory ring filled by the
  * bulk-copy engine (cp.async.bulk + mbarrier, one / two stages of two k-steps per warp, three CTAs per
  * SM), 12 = the same with 8-warp CTAs for wide bands - parity-clean, measured slower than the register
- * path at its higher occupancy, kept selectable;
+ * path at its higher occupancy, kept selectable; 13 = 4-warp CTAs that park a finished
+ * accumulator tile in TENSOR MEMORY (tcgen05.alloc / st / ld, 128 columns per CTA) when M_J is not published yet
+ * and run the available terms of the row's next tile meanwhile - parity-clean, measured slower;
  * 0 = scalar validation variant of the same algorithm
  * (csrc/k3_factor.cu; slow, used by the parity tests to cross-check the tensor-core path). */
 int cm_set_variant(cm_handle *h, int32_t variant);

@@ -88,7 +88,7 @@ def check_against_oracle(eng, orc, subsets, r, lc=0, tag=''):
     return n_marginal
 
 
-@pytest.mark.parametrize('variant', [1, 2, 6, 7, 8, 9, 10, 11, 12, 0],
+@pytest.mark.parametrize('variant', [1, 2, 6, 7, 8, 9, 10, 11, 12, 13, 0],
                          ids=['auto', 'w4', 'w16', 'w2', 'w3', 'w1', 'ring1', 'ring2', 'ring2w8', 'scalar'])
 @pytest.mark.parametrize('name', golden_names())
 def test_golden_cases(name, variant):
