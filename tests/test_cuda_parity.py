@@ -89,7 +89,7 @@ def check_against_oracle(eng, orc, subsets, r, lc=0, tag=''):
 
 
 @pytest.mark.parametrize('variant', [1, 2, 6, 7, 8, 9, 10, 11, 12, 13, 0],
-                         ids=['auto', 'w4', 'w16', 'w2', 'w3', 'w1', 'ring1', 'ring2', 'ring2w8', 'scalar'])
+                         ids=['auto', 'w4', 'w16', 'w2', 'w3', 'w1', 'ring1', 'ring2', 'ring2w8', 'tmem', 'scalar'])
 @pytest.mark.parametrize('name', golden_names())
 def test_golden_cases(name, variant):
     g = Golden(name)
