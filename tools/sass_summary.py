@@ -1,5 +1,6 @@
 """Opcode summary of every kernel in the built library: cuobjdump -sass, counted per kernel for the mnemonics that
 prove the hardware paths in use (DMMA = FP64 tensor MMA, UBLKCP / SYNCS = bulk-copy engine and mbarriers,
+STTM / LDTM / UTCATOMSWS = tensor-memory stores, loads and allocation,
 LDL / STL = local-memory spills).   python tools/sass_summary.py > profiles/rNN_sass_summary.txt"""
 import collections
 import os
@@ -10,7 +11,7 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(REPO, 'conmech_b200', 'lib', 'libconmech_b200.so')
 out = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
-WATCH = ['DMMA', 'UBLKCP', 'SYNCS', 'LDL', 'STL', 'LDG', 'STG', 'LDS', 'STS', 'MEMBAR', 'BAR', 'DFMA', 'DMUL', 'DADD', 'MUFU', 'ATOMS', 'NANOSLEEP']
+WATCH = ['DMMA', 'UBLKCP', 'SYNCS', 'STTM', 'LDTM', 'UTCATOMSWS', 'LDL', 'STL', 'LDG', 'STG', 'LDS', 'STS', 'MEMBAR', 'BAR', 'DFMA', 'DMUL', 'DADD', 'MUFU', 'ATOMS', 'NANOSLEEP']
 cur, counts, total = None, collections.OrderedDict(), {}
 for ln in out.splitlines():
     m = re.search(r'Function : (\S+)', ln)
