@@ -46,9 +46,9 @@ FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool's B
 HBM_FALLBACK_GBS = 6549.8        # MEASURED_PEAKS.json of this pool (round 1)
 # DRAM bytes (read + write) per subset of ONE launch over 4096 config-3 subsets, from the ncu --set full
 # capture summarised in profiles/ (file named in `traffic_source`)
-NCU_DRAM_BYTES_PER_SUBSET = {'k2': (0.405656e9 + 7.936521e9) / 4096, 'k3': (24.421107e9 + 9.587851e9) / 4096,
-                             'k4': (11.333352e9 + 0.018558e9) / 4096}      # (K4 captured with the scalar outputs only)
-NCU_SOURCE = 'profiles/r02c_ncu_k2_k3_k4.txt'
+NCU_DRAM_BYTES_PER_SUBSET = {'k2': (0.407226e9 + 7.938545e9) / 4096, 'k3': (23.888439e9 + 9.466585e9) / 4096,
+                             'k4': (11.314762e9 + 0.017875e9) / 4096}      # (K4 captured with the scalar outputs only)
+NCU_SOURCE = 'profiles/r02d_ncu_k2_k3_k4.txt'
 FULL = ('flag', 'status', 'max_trans', 'compliance', 'U', 'Rf', 'eR')
 SCALARS = ('flag', 'status', 'max_trans', 'compliance')
 

@@ -49,6 +49,13 @@ __device__ unsigned long long g_flow_prof[16];
 //   LA_TRY:    after ALL terms: if M_J is not published yet, park and return LA_PARKED instead of waiting for it.
 // Return otherwise: 1 = chain tile (the diagonal tile was placed in the scratch), 0 = done.
 enum { LA_AHEAD = 1, LA_TRY = 2, LA_PARKED = 2, LA_NONE = 3, LA_K0 = 16 };
+#ifndef CM_TILE_SMEM
+#define CM_TILE_SMEM 1
+#endif
+// a tile visit's own arguments, per warp: written at entry and re-read behind the update streams, so that they are not
+// live (= spilled to local memory, which misses L1 under the streams) while accumulator and operand buffers fill the
+// register file
+__shared__ int s_tilestate[16 * 4];
 #ifndef CM_LA_FAR
 #define CM_LA_FAR 0
 #endif
@@ -57,6 +64,10 @@ enum { LA_AHEAD = 1, LA_TRY = 2, LA_PARKED = 2, LA_NONE = 3, LA_K0 = 16 };
 #endif
 template <bool PROF, int OPS, bool LA>
 __device__ __noinline__ int offdiag_tile(int I, int J, int kcI, int lane, int Kfrom, int Kstop, int la_flags) {
+#if CM_TILE_SMEM
+    volatile int *ts = s_tilestate + (threadIdx.x >> 5) * 4;
+    ts[0] = I; ts[1] = J; ts[2] = kcI; ts[3] = la_flags;
+#endif
     const int bt = CTX(bt);
     long long *pc = PROF ? CTX(pc) + (threadIdx.x >> 5) * 16 : nullptr;
     double *T = cm_tile_ptr(CTX(tiles), bt, I, J);
@@ -116,6 +127,9 @@ __device__ __noinline__ int offdiag_tile(int I, int J, int kcI, int lane, int Kf
         if (ahead && K < Kto && flag_acquire(CTX(prog) + J - 1) > J - 1) break;
 #endif
     }
+#if CM_TILE_SMEM
+    I = ts[0]; J = ts[1]; kcI = ts[2]; la_flags = ts[3]; lane = threadIdx.x & 31;
+#endif
     if (LA) {
         if (ahead) { tm_park(slot, acc); return LA_K0 + K; }
         // M_J not there yet: let the caller start the next tile of the row meanwhile - if row J is far enough from publishing
