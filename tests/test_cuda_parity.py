@@ -808,3 +808,17 @@ def test_sigma_max_on_device():
     host = sc.get_sigma_max_per_element()
     for e, v in host.items():
         assert abs(abs(v) - abs(r['sigma_max'][3, 0][e])) <= REL_TOL * max(abs(v), 1e-300) + 1e-12 * scale
+
+
+def test_c_client_cantilever_analytic(tmp_path):
+    """A plain C host (tests/c_client/cantilever.c: no Python, no torch) drives the C ABI - cm_create, cm_set_loadcases,
+    cm_element_row_offsets, cm_solve_many_host with dense and compact outputs - and checks the Euler-Bernoulli closed
+    forms of a cantilever (tip deflection P L^3 / 3 E I, clamp reactions), the zero-load and no-support statuses."""
+    import os
+    import subprocess
+    from test_host_cpu import _build_c_client, REPO
+    exe = _build_c_client(tmp_path)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REPO, 'conmech_b200', 'lib'))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith('OK')

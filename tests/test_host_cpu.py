@@ -298,3 +298,28 @@ def test_element_row_offsets_host_helper():
         ref = np.concatenate([[0], np.cumsum(np.bitwise_count(m).sum(axis=1, dtype=np.int64))])
         assert off.dtype == np.int64 and np.array_equal(off, ref)
     assert np.array_equal(CudaStiffness.element_row_offsets(np.zeros((0, 4), dtype=np.uint32)), [0])
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / 'cantilever')
+    subprocess.check_call(['gcc', '-O2', '-Wall', '-Werror', '-I', os.path.join(REPO, 'include'),
+                           os.path.join(REPO, 'tests', 'c_client', 'cantilever.c'),
+                           '-L', os.path.join(REPO, 'conmech_b200', 'lib'), '-lconmech_b200', '-lm', '-o', exe])
+    return exe
+
+
+def test_c_client_compiles_against_header_and_fails_loudly_without_gpu(tmp_path):
+    """The drop-in boundary is a C ABI: a plain C program (tests/c_client/cantilever.c) compiles against
+    include/conmech_b200.h with -Wall -Werror and links the library.  Without a GPU cm_create reports the CUDA
+    error and the program exits 2 - nothing falls back to the CPU."""
+    import subprocess
+    import torch
+    from conmech_b200 import build as b
+    b.build()
+    exe = _build_c_client(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip('GPU present: the GPU suite runs the client')
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REPO, 'conmech_b200', 'lib'))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert r.returncode == 2 and 'cm_create' in r.stderr
