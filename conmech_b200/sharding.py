@@ -47,8 +47,35 @@ def solve_many_sharded(engine, masks, want=('flag', 'status', 'max_trans', 'comp
     use_cuda = dist.get_backend(group) == 'nccl'
     n_max = -(-B // world)
     out = {}
+    if 'eR_rows' in want:
+        # compact element rows: a rank's share is the rows of ITS subsets - (off[hi] - off[lo]) * n_lc of them, known to
+        # every rank from the masks - so the shares are padded to the largest one and cut back after the gather
+        from .cuda_stiffness import CudaStiffness
+        off = CudaStiffness.element_row_offsets(masks)
+        out['eR_row_offsets'] = off
     for name in want:
+        if name == 'eR_row_offsets':
+            continue
         mine = np.ascontiguousarray(local[name]) if hi > lo else None
+        if name == 'eR_rows':
+            shares = [shard_range(B, world, r) for r in range(world)]
+            n_lc = [None]
+            if rank == 0:
+                n_lc = [int(mine.shape[0] // max(1, off[hi] - off[lo])) if off[hi] > off[lo] else 1]
+            dist.broadcast_object_list(n_lc, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            L = n_lc[0]
+            r_max = max(int(off[b] - off[a]) for a, b in shares) * L
+            buf = np.zeros((max(r_max, 1), 12), dtype=np.float64)
+            if mine is not None and mine.size:
+                buf[:mine.shape[0]] = mine
+            tns = torch.from_numpy(buf.reshape(-1))
+            if use_cuda:
+                tns = tns.cuda()
+            parts = [torch.empty_like(tns) for _ in range(world)]
+            dist.all_gather(parts, tns, group=group)
+            out[name] = np.concatenate([p.cpu().numpy().reshape(-1, 12)[:int(off[b] - off[a]) * L]
+                                        for p, (a, b) in zip(parts, shares)], axis=0)
+            continue
         # every rank needs the trailing shape and dtype: rank 0 always has a non-empty share when B > 0
         meta = [None]
         if rank == 0:

@@ -245,6 +245,11 @@ class _FakeEngine(object):
         res = {'flag': (pop % 2 == 0).astype(np.uint8).reshape(-1, 1), 'status': np.zeros((len(masks), 1), np.uint8),
                'max_trans': pop.astype(np.float64).reshape(-1, 1) * 1e-4,
                'compliance': pop.astype(np.float64).reshape(-1, 1) * 0.5}
+        if 'eR_rows' in want:           # compact element rows: one row per existing element, value = 1000 * subset hash + element id
+            m = np.ascontiguousarray(masks)
+            bits = np.unpackbits(m.view(np.uint8), axis=1, bitorder='little')
+            rows = [np.outer(1000.0 * float(m[b].sum() % 997) + np.flatnonzero(bits[b]), np.ones(12)) for b in range(len(m))]
+            res['eR_rows'] = np.concatenate(rows, axis=0) if rows else np.zeros((0, 12))
         return {k: res[k] for k in want}
 
 
@@ -255,6 +260,7 @@ def _sharded_worker(rank, world, port, B, ret):
     rng = np.random.RandomState(0)
     masks = rng.randint(0, 2 ** 32, size=(B, 30), dtype=np.uint64).astype(np.uint32)
     out = solve_many_sharded(_FakeEngine(), masks.view(np.int32) if rank else masks)      # int32 views are masks too
+    out.update(solve_many_sharded(_FakeEngine(), masks, want=('eR_rows',)))
     ret[rank] = {k: v.copy() for k, v in out.items()}
     dist.destroy_process_group()
 
@@ -269,7 +275,10 @@ def test_solve_many_sharded_gloo_world2():
     mp.spawn(_sharded_worker, args=(world, port, B, ret), nprocs=world, join=True)
     rng = np.random.RandomState(0)
     masks = rng.randint(0, 2 ** 32, size=(B, 30), dtype=np.uint64).astype(np.uint32)
-    ref = _FakeEngine().solve_many(masks, ('flag', 'status', 'max_trans', 'compliance'))
+    from conmech_b200.cuda_stiffness import CudaStiffness
+    ref = _FakeEngine().solve_many(masks, ('flag', 'status', 'max_trans', 'compliance', 'eR_rows'))
+    ref['eR_row_offsets'] = CudaStiffness.element_row_offsets(masks)
+    assert ref['eR_rows'].shape[0] == ref['eR_row_offsets'][-1]
     for r in range(world):
         for k, v in ref.items():
             assert np.array_equal(ret[r][k], v), (r, k)
