@@ -169,7 +169,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(args, {'reference_sample_per_step': per_step}),
+            'data': 'synthetic', 'config': workload_config(args),        # identical to the CUDA arm's `config`
+            'reference_sample_per_step': per_step,
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_procs, 'kind': kind, 'what': what,
                              'sample': '{} subsets per step (seeds 0..), {} processes, {}'.format(
                                  per_step, n_procs, cpu_bench.cpu_model_name())},
@@ -694,10 +695,11 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': workload_config(args, {'mean_free_dofs_per_subset': nfree / n_sub,
-                                                 'half_bandwidth_full': info['half_bandwidth'],
-                                                 'flags_true_last_step_rank0': flags_true,
-                                                 'status_ok_last_step_rank0': status_ok}),
+                'config': workload_config(args),                         # identical to the reference arm's `config`
+                'workload_stats': {'mean_free_dofs_per_subset': nfree / n_sub,
+                                   'half_bandwidth_full': info['half_bandwidth'],
+                                   'flags_true_last_step_rank0': flags_true,
+                                   'status_ok_last_step_rank0': status_ok},
                 'value_flags_only': value_flags, 'host_placement': numa_note,
                 'clocks': clocks,
                 'e2e': {'value': e2e_full, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_full,
