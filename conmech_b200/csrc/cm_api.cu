@@ -182,7 +182,26 @@ int cm_create(const cm_model_desc *d, cm_handle **out) {
     if (d->n_nodes <= 0 || d->n_elems <= 0) return fail(CM_ERR_INVALID, "cm_create: empty model");
     if (d->n_supports <= 0)
         return fail(CM_ERR_INVALID, "there needs to be at least one support (fixed) vertex in the model!");
+    if (!d->xyz || !d->conn || !d->props || !d->cr || !d->sup_node || !d->sup_cond)
+        return fail(CM_ERR_INVALID, "cm_create: null table in the model description");
     const int nV = d->n_nodes, nE = d->n_elems, nS = d->n_supports;
+    {   // supports: in range, one entry per node (checked before any CUDA call, like the element checks below)
+        std::vector<char> is_sup(nV, 0);
+        for (int s = 0; s < nS; ++s) {
+            const int v = d->sup_node[s];
+            if (v < 0 || v >= nV) return fail(CM_ERR_INVALID, "cm_create: support node out of range");
+            if (is_sup[v]) return fail(CM_ERR_INVALID, "cm_create: duplicate support node");
+            is_sup[v] = 1;
+        }
+        if (d->node_order) {
+            std::vector<char> seen(nV, 0);
+            for (int p = 0; p < nV; ++p) {
+                const int v = d->node_order[p];
+                if (v < 0 || v >= nV || seen[v]) return fail(CM_ERR_INVALID, "cm_create: node_order is not a permutation of the node ids");
+                seen[v] = 1;
+            }
+        }
+    }
     for (int e = 0; e < nE; ++e) {
         int u = d->conn[2 * e], v = d->conn[2 * e + 1];
         if (u < 0 || u >= nV || v < 0 || v >= nV || u == v)

@@ -332,3 +332,69 @@ def test_c_client_compiles_against_header_and_fails_loudly_without_gpu(tmp_path)
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REPO, 'conmech_b200', 'lib'))
     r = subprocess.run([exe], capture_output=True, text=True, env=env)
     assert r.returncode == 2 and 'cm_create' in r.stderr
+
+
+def test_cm_create_validates_the_description_before_any_cuda_call():
+    """Programmer errors in a model description are reported as CM_ERR_INVALID with the reference's messages
+    (numpy_stiffness_assembly.py:288-289 bar length, :146 E / Iz, stiffness_base.py:25-26 supports) - checked on the
+    host before the library touches CUDA, so the same answers come back with and without a GPU."""
+    import ctypes as C
+    from conmech_b200 import _capi
+    lib = _capi.load()
+
+    def create(xyz, conn, props=None, cr=None, sup_node=(0,), sup_cond=None, node_order=None, null=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        nE = len(conn)
+        props = np.ascontiguousarray(np.tile([1e-3, 1e-6, 1e-6, 1e-6, 2.1e8, 0.3, 78.5], (nE, 1)) if props is None else props)
+        cr = np.full((nE, 6), np.inf) if cr is None else np.ascontiguousarray(cr, dtype=np.float64)
+        sup_node = np.ascontiguousarray(sup_node, dtype=np.int32)
+        sup_cond = np.ones((len(sup_node), 6), dtype=np.uint8) if sup_cond is None else sup_cond
+        d = _capi.ModelDesc(len(xyz), nE, len(sup_node), 0,
+                            xyz.ctypes.data_as(_capi.c_double_p), conn.ctypes.data_as(_capi.c_int32_p),
+                            props.ctypes.data_as(_capi.c_double_p), cr.ctypes.data_as(_capi.c_double_p),
+                            sup_node.ctypes.data_as(_capi.c_int32_p), sup_cond.ctypes.data_as(_capi.c_uint8_p), None)
+        if node_order is not None:
+            no = np.ascontiguousarray(node_order, dtype=np.int32)
+            d.node_order = no.ctypes.data_as(_capi.c_int32_p)
+        if null:
+            setattr(d, null, None)
+        h = C.c_void_p()
+        rc = lib.cm_create(C.byref(d), C.byref(h))
+        msg = lib.cm_last_error().decode()
+        if rc == 0:
+            lib.cm_destroy(h)
+        return rc, msg
+
+    xyz = [[0, 0, 0], [1, 0, 0], [1, 1, 0]]
+    conn = [[0, 1], [1, 2]]
+    INVALID = -1
+    assert lib.cm_create(None, None) == INVALID
+    for field in ('xyz', 'conn', 'props', 'cr', 'sup_node', 'sup_cond'):
+        rc, msg = create(xyz, conn, null=field)
+        assert rc == INVALID and 'null table' in msg, (field, rc, msg)
+    rc, msg = create(xyz, conn, sup_node=())
+    assert rc == INVALID and 'at least one support' in msg
+    rc, msg = create(xyz, conn, sup_node=(3,))
+    assert rc == INVALID and 'support node out of range' in msg
+    rc, msg = create(xyz, conn, sup_node=(0, 0))
+    assert rc == INVALID and 'duplicate support node' in msg
+    rc, msg = create(xyz, [[0, 1], [1, 3]])
+    assert rc == INVALID and 'element 1 has invalid end nodes' in msg
+    rc, msg = create(xyz, [[0, 1], [2, 2]])
+    assert rc == INVALID and 'invalid end nodes' in msg
+    rc, msg = create([[0, 0, 0], [1, 0, 0], [1, 0, 1e-15]], conn)
+    assert rc == INVALID and msg == 'E#1 - Bar length too small!'
+    p = np.tile([1e-3, 1e-6, 1e-6, 1e-6, 2.1e8, 0.3, 78.5], (2, 1))
+    p[1, 4] = 0.0
+    rc, msg = create(xyz, conn, props=p)
+    assert rc == INVALID and msg == 'E#1 - E and Iz must be non-zero'
+    rc, msg = create(xyz, conn, node_order=[0, 1, 1])
+    assert rc == INVALID and 'not a permutation' in msg
+    # a valid description gets as far as the device: OK with a GPU, the CUDA error (never a CPU fallback) without
+    rc, msg = create(xyz, conn)
+    import torch
+    if torch.cuda.is_available():
+        assert rc == 0, msg
+    else:
+        assert rc not in (0, INVALID) and 'cuda' in msg.lower()
