@@ -23,6 +23,8 @@ max_trans / compliance - materialised, as the reference does on every solve
                     call, packing included)
   roofline          the dominant kernel (K3, FP64 tensor pipe) + roofline.kernels = K2 / K3 / K4
   other_configs     (N = 1) BASELINE configs 1, 2, 4, 5 on the GPU next to the CPU rate of each
+  parity_in_run     (N = 1) the CUDA results of this run against the CPU arm's results for the same first subsets
+                    (flags equal, U / Rf / eR / max_trans / compliance within 1e-9)
   single_process    (N > 1, rank 0 after the SPMD legs) ONE process driving all N GPUs through
                     cm_solve_many_host_multi, host gather inside the timed region
 Prints ONE JSON line on rank 0.
@@ -62,6 +64,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=12500, help='subsets per GPU per step')
     ap.add_argument('--cpu-sample', type=int, default=0, help='subsets in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parity-sample', type=int, default=128, help='subsets of the in-run parity check against the CPU arm')
     ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--distinct-batches', type=int, default=2)
     return ap.parse_args()
@@ -212,6 +215,44 @@ def measured_peaks():
         return float(p['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (burst copy rate; driver-written)'
     except (OSError, KeyError, ValueError):
         return HBM_FALLBACK_GBS, 'fallback: the copy rate MEASURED_PEAKS.json held in round 1 (file absent)'
+
+
+def parity_in_run(ref, got, masks, n_elems, tol=1e-9):
+    """Results of THIS run's CUDA path against the CPU arm's results for the same subsets (BASELINE.md section 3,
+    step 6).  ``ref``: the arrays oracle.cpu_bench.parity_sample stored (flag, has, max_trans, compliance, U, R, eR
+    with NaN rows for absent elements); ``got``: flag / status / max_trans / compliance / U / Rf / eR of the first
+    ``len(ref['flag'])`` subsets as numpy arrays shaped [n, 1, ...]; ``masks``: their uint32 bit masks.  Flags must be
+    equal; values are compared with the survey's metric - max |a - b| / max |b| per array and solve, translations /
+    forces and rotations / moments separately - against ``tol``."""
+    import numpy as np
+    from conmech_b200 import masks as cm_masks
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+        return 0.0 if b.size == 0 else float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    def split(a, b):
+        a, b = np.asarray(a, dtype=float).reshape(-1, 6), np.asarray(b, dtype=float).reshape(-1, 6)
+        return max(rel(a[:, :3], b[:, :3]), rel(a[:, 3:], b[:, 3:]))
+
+    n = int(len(ref['flag']))
+    gflag = np.asarray(got['flag']).reshape(len(got['flag']), -1)[:n, 0].astype(bool)
+    gstat = np.asarray(got['status']).reshape(len(got['status']), -1)[:n, 0]
+    has = np.asarray(ref['has']).astype(bool)
+    worst = {'U': 0.0, 'Rf': 0.0, 'eR': 0.0, 'max_trans': 0.0, 'compliance': 0.0}
+    for b in np.flatnonzero(has):
+        ids = cm_masks.mask_to_ids(masks[b], n_elems)
+        worst['U'] = max(worst['U'], split(got['U'][b, 0], ref['U'][b]))
+        worst['Rf'] = max(worst['Rf'], split(got['Rf'][b, 0], ref['R'][b]))
+        worst['eR'] = max(worst['eR'], split(np.asarray(got['eR'][b, 0]).reshape(n_elems, 12)[ids], ref['eR'][b][ids]))
+        worst['max_trans'] = max(worst['max_trans'], rel(got['max_trans'][b, 0], ref['max_trans'][b]))
+        worst['compliance'] = max(worst['compliance'], rel(got['compliance'][b, 0], ref['compliance'][b]))
+    flags_equal = bool(np.array_equal(gflag, np.asarray(ref['flag']).astype(bool)))
+    solved_equal = bool(np.array_equal((gstat == 0) | (gstat == 4), has))       # 0 ok, 4 zero load: a result is stored
+    return {'subsets': n, 'against': str(ref['kind']) if 'kind' in ref else 'unknown', 'flags_equal': flags_equal,
+            'solved_equal': solved_equal, 'flags_true': int(gflag.sum()), 'with_result': int(has.sum()),
+            'max_rel_err': worst, 'tolerance': tol,
+            'pass': bool(flags_equal and solved_equal and max(worst.values()) <= tol)}
 
 
 def other_configs_gpu(torch, np, dev, cpu_rates):
@@ -405,15 +446,20 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) in a child process of its own, before the GPU work starts
     cpu_baseline = None
     cpu_others = None
+    parity_file = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cmd = [sys.executable, '-m', 'oracle.cpu_bench', str(GRID[0]), str(GRID[1]), str(GRID[2]),
                str(TRANS_TOL), str(args.batch), str(args.cpu_sample)]
         if not args.no_other_configs:
             cmd.append('others')
+        import tempfile
+        parity_path = os.path.join(tempfile.gettempdir(), 'conmech_b200_parity_{}.npz'.format(os.getpid()))
+        cmd.append('parity={},{}'.format(parity_path, min(args.batch, args.parity_sample)))
         r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True)
         if r.returncode == 0 and r.stdout.strip():
             cpu_baseline = json.loads(r.stdout.strip().splitlines()[-1])
             cpu_others = cpu_baseline.pop('other_configs', None)
+            parity_file = cpu_baseline.pop('parity_file', None)
         else:
             sys.stderr.write('cpu baseline failed: ' + r.stderr[-2000:] + '\n')
 
@@ -565,6 +611,20 @@ def main():
     torch.cuda.synchronize(dev)
     for n in FULL:
         assert np.array_equal(out_host[n], outs[FULL][n].cpu().numpy(), equal_nan=(n in ('max_trans',))), n
+    # the same subsets the CPU arm solved (seeds 0.. of rank 0's first batch): flags equal, values within 1e-9
+    parity = None
+    if parity_file is not None:
+        try:
+            if 'error' in parity_file:
+                raise RuntimeError(parity_file['error'])
+            with np.load(parity_file['path']) as z:
+                ref = {k: z[k] for k in z.files}
+            n_par = len(ref['flag'])
+            got = {n: outs[FULL][n][:n_par].cpu().numpy() for n in FULL}
+            parity = parity_in_run(ref, got, host_np[0][:n_par], nE)
+            os.remove(parity_file['path'])
+        except Exception as ex:          # reported, never fatal for the line
+            parity = {'error': repr(ex)}
     e2e_flags = timed_host(lambda k: eng.solve_many(host_np[k % n_batches], want=SCALARS, out=out_host))
     d2h_flags = int(sum(out_host[n].nbytes for n in SCALARS))
     # the facade's own calling convention: Python id lists in, list of bools out
@@ -719,6 +779,8 @@ def main():
                 'gpu_launches': launches, 'roofline': roofline}
         if cpu_baseline is not None:
             line['cpu_baseline'] = cpu_baseline
+        if parity is not None:
+            line['parity_in_run'] = parity
         if others is not None:
             line['other_configs'] = others
         if single is not None:

@@ -79,6 +79,7 @@ def _init_worker(spec, kind='port'):
         pass
     model, lcs, sub = build_workload(spec)
     solvers = []
+    checkers = []
     for lc in lcs:
         if kind == 'reference':
             from oracle import ref_bridge
@@ -98,7 +99,11 @@ def _init_worker(spec, kind='port'):
             def solve(ids, orc=orc):
                 return orc.solve(ids).success
         solvers.append(solve)
+        checkers.append(sc if kind == 'reference' else orc)
     _STATE['solvers'] = solvers
+    _STATE['checkers'] = checkers
+    _STATE['kind'] = kind
+    _STATE['shape'] = (len(model.nodes), len(model.elements))
     _STATE['sub'] = sub
 
 
@@ -115,6 +120,75 @@ def _solve_seeds(seeds):
                 n_ok += 1 if solve(ids) else 0
         dt = time.perf_counter() - t0
     return dt, len(seeds) * len(solvers), n_ok
+
+
+def _parity_seeds(seeds):
+    """Dense results (first load case) of the subsets of ``seeds`` from this worker's checker - the reference's
+    engine (``get_solved_results`` rows scattered by node / element id, SURVEY section 8c: never compare on row
+    order) or the port.  Rows of absent elements are NaN."""
+    import contextlib
+    import io
+    import numpy as np
+    chk, kind, sub = _STATE['checkers'][0], _STATE['kind'], _STATE['sub']
+    nV, nE = _STATE['shape']
+    n = len(seeds)
+    out = {'flag': np.zeros(n, np.uint8), 'has': np.zeros(n, np.uint8), 'max_trans': np.full(n, np.nan),
+           'compliance': np.full(n, np.nan), 'U': np.zeros((n, 6 * nV)), 'R': np.zeros((n, 6 * nV)),
+           'eR': np.full((n, nE, 12), np.nan)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k, s in enumerate(seeds):
+            ids = sub(s)
+            if kind == 'reference':
+                eng = chk._sc_ins
+                try:
+                    flag = bool(chk.solve(ids))
+                except TypeError:                               # SURVEY Q10
+                    flag = False
+                    eng._has_stored_deformation = False
+                has = bool(chk.has_stored_result())
+                if has:
+                    _, nD, fR, eR = eng.get_solved_results()
+                    out['max_trans'][k] = eng.get_max_nodal_deformation()[0]
+                    out['compliance'][k] = eng.get_compliance()
+                    for row in nD:
+                        out['U'][k, 6 * int(row[0]):6 * int(row[0]) + 6] = row[1:]
+                    for row in fR:
+                        out['R'][k, 6 * int(row[0]):6 * int(row[0]) + 6] = row[1:]
+                    for row in eR:
+                        out['eR'][k, int(row[0])] = row[1:]
+            else:
+                o = chk.solve(ids)
+                flag, has = bool(o.success), bool(o.has_result)
+                if has:
+                    out['max_trans'][k], out['compliance'][k] = o.max_trans, o.compliance
+                    out['U'][k], out['R'][k] = o.U, o.R
+                    e_ids = ids if len(ids) else list(range(nE))
+                    out['eR'][k, e_ids] = np.asarray(o.eR)[e_ids]
+            out['flag'][k], out['has'][k] = flag, has
+    return out
+
+
+def parity_sample(spec, n, path, kind=None):
+    """Solve the first ``n`` subsets of a workload with the reference (the port when it is not installed) on all
+    host cores and store the dense results in ``path`` (.npz): the parity set bench.py checks the GPU results of the
+    SAME run against.  Returns the kind used."""
+    import multiprocessing as mp
+    import numpy as np
+    kind = kind or ('reference' if reference_available() else 'port')
+    seeds = list(range(n))
+    n_procs = max(1, min(os.cpu_count() or 1, n))
+    chunks = [seeds[i::n_procs] for i in range(n_procs)]
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(n_procs, initializer=_init_worker, initargs=(spec, kind)) as pool:
+        res = pool.map(_parity_seeds, chunks)
+    merged = {}
+    for key in res[0]:
+        arr = np.zeros((n,) + res[0][key].shape[1:], dtype=res[0][key].dtype)
+        for i, r in enumerate(res):
+            arr[i::n_procs] = r[key]
+        merged[key] = arr
+    np.savez(path, kind=np.array(kind), **merged)
+    return kind
 
 
 def time_workload(spec, seeds, n_procs=1, kind='port'):
@@ -263,12 +337,20 @@ def other_configs_record():
 
 
 if __name__ == '__main__':
-    # python -m oracle.cpu_bench nx ny nz trans_tol batch sample [others]  ->  one JSON line (used by bench.py
+    # python -m oracle.cpu_bench nx ny nz trans_tol batch sample [others] [parity=PATH,N]  ->  one JSON line (used by bench.py
     # in a child process so that the CPU run shares no state - threads, allocator - with the GPU process)
     import json
     import sys
     a = sys.argv[1:]
     rec = baseline_record((int(a[0]), int(a[1]), int(a[2])), float(a[3]), int(a[4]), int(a[5]))
-    if len(a) > 6 and a[6] == 'others':
+    if 'others' in a[6:]:
         rec['other_configs'] = other_configs_record()
+    for tok in a[6:]:
+        if tok.startswith('parity='):                  # parity=PATH,N : the in-run parity set (never fails the baseline)
+            path, n = tok[7:].rsplit(',', 1)
+            try:
+                spec = dict(CONFIG3, model=('grid', int(a[0]), int(a[1]), int(a[2]), False), trans_tol=float(a[3]))
+                rec['parity_file'] = {'path': path, 'subsets': int(n), 'kind': parity_sample(spec, int(n), path)}
+            except Exception as ex:
+                rec['parity_file'] = {'error': repr(ex)}
     print(json.dumps(rec))

@@ -398,3 +398,57 @@ def test_cm_create_validates_the_description_before_any_cuda_call():
         assert rc == 0, msg
     else:
         assert rc not in (0, INVALID) and 'cuda' in msg.lower()
+
+
+def test_bench_parity_in_run_check(tmp_path):
+    """bench.py compares the CUDA results of a run with the CPU arm's results for the same subsets (BASELINE.md
+    section 3, step 6).  Here the comparison itself is exercised without a GPU: the CPU arm's parity set (the
+    unmodified reference when baseline/_ref is installed, else the port) against the oracle port's results laid out
+    like the device outputs - which also pins the port to the reference on config-3 subsets once more."""
+    import importlib.util
+    from oracle import cpu_bench
+    from conmech_b200 import synthetic as syn
+    spec = importlib.util.spec_from_file_location('bench_module', os.path.join(REPO, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n = 6
+    wl = dict(cpu_bench.CONFIG3)
+    path = str(tmp_path / 'parity.npz')
+    kind = cpu_bench.parity_sample(wl, n, path)
+    assert kind in ('reference', 'port')
+    with np.load(path) as z:
+        ref = {k: z[k] for k in z.files}
+    assert ref['has'].all() and ref['U'].shape == (n, 6 * 392) and ref['eR'].shape == (n, 931, 12)
+
+    # "device" results: the port, dense, zero rows for absent elements, [n, load case, ...]
+    model = syn.grid_frame(7, 7, 8)
+    from oracle.frame_oracle import FrameOracle
+    from conmech_b200 import LoadCase, GravityLoad
+    orc = FrameOracle(model)
+    orc.set_loads(LoadCase(gravity_load=GravityLoad([0, 0, -1])))
+    orc.set_nodal_displacement_tol(1e-3)
+    subsets = [syn.connected_subset(model, s) for s in range(n)]
+    got = {'flag': np.zeros((n, 1), np.uint8), 'status': np.zeros((n, 1), np.uint8), 'max_trans': np.zeros((n, 1)),
+           'compliance': np.zeros((n, 1)), 'U': np.zeros((n, 1, 6 * 392)), 'Rf': np.zeros((n, 1, 6 * 392)),
+           'eR': np.zeros((n, 1, 931, 12))}
+    for b, ids in enumerate(subsets):
+        o = orc.solve(ids)
+        got['flag'][b, 0], got['max_trans'][b, 0], got['compliance'][b, 0] = o.success, o.max_trans, o.compliance
+        got['U'][b, 0], got['Rf'][b, 0] = o.U, o.R
+        got['eR'][b, 0][ids] = np.asarray(o.eR)[ids]
+    masks = syn.pack_masks(subsets, 931)
+    rec = bench.parity_in_run(ref, got, masks, 931)
+    assert rec['pass'] and rec['flags_equal'] and rec['solved_equal'] and rec['subsets'] == n and rec['against'] == kind
+    assert max(rec['max_rel_err'].values()) <= 1e-9
+    # a wrong displacement, a wrong flag and a missing result are all caught
+    bad = {k: v.copy() for k, v in got.items()}
+    bad['U'][2, 0, 6 * 200 + 2] += 1e-6
+    r2 = bench.parity_in_run(ref, bad, masks, 931)
+    assert not r2['pass'] and r2['max_rel_err']['U'] > 1e-9 and r2['flags_equal']
+    bad = {k: v.copy() for k, v in got.items()}
+    bad['flag'][1, 0] ^= 1
+    assert not bench.parity_in_run(ref, bad, masks, 931)['flags_equal']
+    bad = {k: v.copy() for k, v in got.items()}
+    bad['status'][3, 0] = 3
+    r3 = bench.parity_in_run(ref, bad, masks, 931)
+    assert not r3['solved_equal'] and not r3['pass']
