@@ -110,6 +110,15 @@ def test_native_mask_packer_matches_numpy():
             masks.USE_NATIVE = True
     with pytest.raises(ValueError):
         masks.pack_masks_csr(np.array([4, 9, 4]), np.array([0, 3]), nE)
+    # every kind of id object takes the same decisions on the fast path (exact one-digit ints read from the object)
+    # and on the number-protocol path (numpy scalars, bools, big ints)
+    mixed = [[1, 2, 3], [np.int64(5), np.int32(7), True], (nE - 1, 0), range(3), {4, 5}, np.array([1, 2], dtype=np.int16)]
+    got = [masks.mask_to_ids(r, nE).tolist() for r in masks.pack_masks(mixed, nE)]
+    assert got == [[1, 2, 3], [1, 5, 7], [0, nE - 1], [0, 1, 2], [4, 5], [1, 2]]
+    for bad, exc in (([[-1]], IndexError), ([[2 ** 40]], IndexError), ([[2 ** 80]], IndexError), ([[1.5]], TypeError),
+                     ([['a']], TypeError), ([[None]], TypeError)):
+        with pytest.raises(exc):
+            masks.pack_masks(bad, nE)
     # release-store hand-over flag and the mask-matrix detection of solve_many
     fl = np.zeros(4, dtype=np.int32)
     masks.publish(fl, 2, 1)
